@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the LINE-MOD match path on B200 (BASELINE.json metric: RGB-D frames/s,
+640x480, N templates; similarity GB/s vs roofline).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
+
+A step = one pass of the hot path over a batch of B synthetic frames (distinct frames, B*1.5 MB of
+inputs > L2) against the template set of BASELINE.json configs[1] (3 000 templates, 10 % planted).
+value  = frames/s with the frames resident in HBM (device pipeline only, CUDA events on the library's stream).
+e2e    = frames/s through lmb200_match_batch with pinned HOST frames: H2D of every frame, kernels,
+         D2H of the match lists and the host sort/unique inside the timed region.
+Multi-GPU (default --shard frames, BASELINE configs[2]): each rank streams its own frames against the
+full template set (weak scaling, no data-path collective).  --shard templates (configs[3]) splits
+the template set across ranks and merges the match lists with one ncclAllGather per step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS = 480, 640
+FRAME_BYTES = ROWS * COLS * 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=96, help="frames per step per GPU")
+    ap.add_argument("--templates", type=int, default=3000)
+    ap.add_argument("--threshold", type=float, default=80.0)
+    ap.add_argument("--shard", default="frames", choices=["frames", "templates"])
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_templates_product(det, n_templates, bgr, depth):
+    """configs[1] template set through the PRODUCT's own addTemplate: ~10 % planted on frame 0, rest random (seed 99)."""
+    from line_mod_pipeline_b200 import synth
+    planted = 0
+    for m in synth.planted_masks(n_templates // 10, seed=17):
+        tid, _ = det.addTemplate([bgr, depth], "planted", m)
+        planted += tid >= 0
+    for tp in synth.random_templates(n_templates - planted):
+        det.addSyntheticTemplate(tp, "rand")
+    return planted
+
+
+def copy_templates_to_oracle(det, ora):
+    from oracle import oracle as O
+    for cid in det.classIds():
+        for t in range(det.numTemplates(cid)):
+            ora.add_synthetic(det.getTemplates(cid, t), cid)
+
+
+def cpu_sample(ora_templates_from, n_frames, threshold, threads, frames_fn):
+    """Times the oracle (CPU port of the reference path) on n_frames frames; returns (fps, seconds)."""
+    from oracle import oracle as O
+    ora = ora_templates_from
+    t0 = time.perf_counter()
+    nm = 0
+    for i in range(n_frames):
+        bgr, depth = frames_fn(i)
+        nm += len(ora.match([bgr, depth], threshold, threads=threads).matches(0))
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt, nm
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of cv::linemod::Detector::match (real OpenCV-contrib linemod is not
+    buildable offline — DESIGN.md), all host threads, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from line_mod_pipeline_b200 import synth
+    from oracle import oracle as O
+    threads = O.max_threads()
+    lut = synth.default_normal_lut()
+    ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], normal_lut=lut)
+    bgr0, depth0 = synth.make_frame(0)
+    planted = 0
+    for m in synth.planted_masks(args.templates // 10, seed=17):
+        tid, _ = ora.add_template([bgr0, depth0], "planted", m)
+        planted += tid >= 0
+    for tp in synth.random_templates(args.templates - planted):
+        ora.add_synthetic(tp, "rand")
+    per_step = 4
+    frames = [synth.make_frame(i) for i in range(per_step)]
+    for _ in range(args.warmup):
+        ora.match(list(frames[0]), args.threshold, threads=threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for f in frames:
+            ora.match(list(f), args.threshold, threads=threads)
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    line = {"impl": "reference", "metric": "rgbd_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 640x480 RGB-D frame vs %d templates (CG+DN, T={5,8}), threshold %g" % (args.templates, args.threshold),
+                       "frames_per_step": per_step},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps x %d frames x %d templates, oracle C++ port, %d threads over templates" % (args.steps, per_step, args.templates, threads)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import line_mod_pipeline_b200 as lm
+    from line_mod_pipeline_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B, K, W = args.frames, args.steps, max(args.warmup, 3)
+    n_tpl = args.templates * (world if args.shard == "templates" else 1)
+    det = lm.getDefaultLINEMOD(device=local, max_batch=B)
+    bgr0, depth0 = synth.make_frame(0)
+    planted = build_templates_product(det, n_tpl, bgr0, depth0)
+    if args.shard == "templates" and world > 1:
+        det.setTemplateShard(rank, world)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.from_numpy(lm.comm_unique_id().copy())
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        det.commInit(uid.cpu().numpy(), rank, world)
+
+    # ---- frames: pinned host memory (e2e) + resident copies (value)
+    L = lm.capi.lib()
+    nb, nd = ROWS * COLS * 3, ROWS * COLS * 2
+    ptr = C.c_void_p()
+    assert L.lmb200_host_alloc(B * (nb + nd), C.byref(ptr)) == 0
+    host = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(B * (nb + nd),))
+    frames = []
+    first = 0 if args.shard == "templates" else rank * B
+    for i in range(B):
+        bgr, depth = synth.make_frame(first + i)
+        hb = host[i * (nb + nd): i * (nb + nd) + nb].reshape(ROWS, COLS, 3)
+        hd = host[i * (nb + nd) + nb: (i + 1) * (nb + nd)].view(np.uint16).reshape(ROWS, COLS)
+        hb[:] = bgr; hd[:] = depth
+        frames.append([hb, hd])
+    det.uploadFrames(frames, 0)
+
+    allg = args.shard == "templates" and world > 1
+
+    def step():
+        det.matchResident(0, B, args.threshold)
+        if allg:
+            return det.fetchResident(0, B, allgather=True, cap=16384 * B)
+        return None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        det.synchronize()
+
+    for _ in range(W):
+        step()
+    det.synchronize()
+    det.setProfiling(True)
+    det.getProfile(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    det.timerRecord(0)          # CUDA events on the library's compute stream
+    for _ in range(K):
+        step()
+    det.timerRecord(1)
+    barrier()
+    ms = det.timerElapsedMs()
+    clocks = sampler.summary()
+    prof = det.getProfile(reset=True)
+    det.setProfiling(False)
+    res = det.fetchResident(0, B) if not allg else step()
+    n_matches = int(sum(len(r) for r in res))
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames_total = B * K * (world if args.shard == "frames" else 1)
+    value = frames_total / (ms * 1e-3)
+
+    # ---- e2e: host frames through lmb200_match_batch (H2D + kernels + D2H + host sort/unique)
+    e2e = None
+    if not args.no_e2e and not allg:
+        for _ in range(2):
+            det.matchBatch(frames, args.threshold, cap=16384 * B)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            det.matchBatch(frames, args.threshold, cap=16384 * B)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": B * K * world / dt, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES,
+               "d2h_bytes_per_step": B * (16 + 1024 * 16), "ms_per_step": 1e3 * dt / K}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant similarity kernel (algorithmic bytes / CUDA-event time)
+    peak, peak_src = measured_peaks()
+    launches = {k: v for k, v in prof["launches"].items() if k != "upload"}
+    kernels = {}
+    for k in launches:
+        if launches[k]:
+            kernels[k] = {"ms_total": round(prof["ms"][k], 4), "launches": launches[k], "ms_per_launch": round(prof["ms"][k] / launches[k], 5)}
+    bytes_frame_side = K * B * (FRAME_BYTES + 2 * 8 * (ROWS * COLS + ROWS * COLS // 4))
+    alg = {"sim_coarse": prof["bytes_coarse"], "sim_local": prof["bytes_local"], "linearize": K * B * 2 * 9 * (ROWS * COLS + ROWS * COLS // 4)}
+    for k, b in alg.items():
+        if k in kernels and prof["ms"][k] > 0:
+            kernels[k]["alg_bytes_per_launch"] = b / launches[k]
+            kernels[k]["alg_GBps"] = round(b / (prof["ms"][k] * 1e-3) / 1e9, 1)
+    dom = "sim_coarse"
+    ach = kernels.get(dom, {}).get("alg_GBps", 0.0)
+    roofline = {"kernel": "similarity_coarse_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4) if peak else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kernels.get(dom, {}).get("alg_bytes_per_launch"),
+                "note": "linear memories are L2-resident: the gather is bounded by L2, HBM copy bandwidth is the reported denominator"}
+    sim_ms = prof["ms"]["sim_coarse"] + prof["ms"]["sim_local"]
+    sim_gbps = (prof["bytes_coarse"] + prof["bytes_local"]) / (sim_ms * 1e-3) / 1e9 if sim_ms > 0 else None
+
+    # ---- cpu baseline: the oracle port on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
+        copy_templates_to_oracle(det, ora)
+        threads = O.max_threads()
+        nfr = args.cpu_frames or 24
+        fps, dt, nm = cpu_sample(ora, nfr, args.threshold, threads, lambda i: frames[i % B])
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d of the step's frames x %d templates, oracle C++ port (frame side 1 thread, templates on %d threads), %.1f s" % (nfr, n_tpl, threads, dt)}
+
+    line = {"metric": "rgbd_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: 640x480 RGB-D frame vs %d templates (CG+DN, T={5,8}), threshold %g; step = batch of %d distinct frames per GPU"
+                                   % (n_tpl, args.threshold, B),
+                       "frames_per_step_per_gpu": B, "templates": n_tpl, "planted_templates": planted, "shard": args.shard,
+                       "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of linear memories per step" % (B * FRAME_BYTES / 1e6, B * 6.144)},
+            "e2e": e2e, "gpu_launches": int(sum(launches.values())), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "kernels": kernels, "similarity_GBps": sim_gbps, "matches_per_step": n_matches,
+            "candidates_per_step": None}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

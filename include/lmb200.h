@@ -1,0 +1,229 @@
+/* lmb200.h — C ABI of the B200-native LINE-MOD matcher.
+ *
+ * Drop-in boundary for the `cv::linemod::Detector` path that aelmiger/LINE-MOD-Pipeline
+ * drives from HighLevelLineMOD (reference file:line each entry point replaces is cited).
+ * Plain pointers and sizes only; no C++/torch types; no exceptions cross this ABI.
+ * All functions return LMB200_OK (0) or a negative lmb200_status, unless stated otherwise.
+ *
+ * Image conventions (reference: detector.cpp:12,:24-26, HighLevelLinemod.cpp:86-90):
+ *   sources[] are in modality order; ColorGradient takes BGR8 (LMB200_8UC3),
+ *   DepthNormal takes 16-bit depth in millimetres (LMB200_16UC1); masks are LMB200_8UC1.
+ *   `step` is the row pitch in bytes (0 = tightly packed).  Buffers are caller-owned host
+ *   memory, read-only for the duration of the call.
+ */
+#ifndef LMB200_H
+#define LMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmb200_detector* lmb200_handle;
+
+typedef enum {
+  LMB200_OK = 0,
+  LMB200_E_INVALID = -1,    /* bad argument / handle */
+  LMB200_E_SOURCES = -2,    /* upstream CV_Assert(sources.size()==modalities.size()), wrong type or size */
+  LMB200_E_SIZE = -3,       /* upstream CV_Assert in linearize/computeResponseMaps: rows%T, cols%T, (rows*cols)%16 */
+  LMB200_E_FEATURES = -4,   /* upstream CV_Assert(templ.features.size() <= 63) */
+  LMB200_E_CLASS = -5,      /* unknown class / class already present (readClass) / bad template id */
+  LMB200_E_IO = -6,         /* file open / parse error */
+  LMB200_E_CUDA = -7,       /* CUDA runtime error (message in lmb200_last_error) */
+  LMB200_E_TRUNCATED = -8,  /* output buffer too small; *n_out holds the required count */
+  LMB200_E_COMM = -9,       /* NCCL not available / communicator error */
+  LMB200_E_NODEVICE = -10   /* no CUDA device: the library has NO CPU fallback */
+} lmb200_status;
+
+/* OpenCV type codes, so a cv::Mat's type() can be passed through unchanged. */
+enum { LMB200_8UC1 = 0, LMB200_16UC1 = 2, LMB200_8UC3 = 16 };
+enum { LMB200_COLOR_GRADIENT = 0, LMB200_DEPTH_NORMAL = 1 };
+
+/* Modality parameters; defaults are upstream's (linemod.hpp ColorGradient()/DepthNormal()),
+ * which the reference never overrides (HighLevelLinemod.cpp:28-30,:38). */
+typedef struct {
+  int type;                 /* LMB200_COLOR_GRADIENT | LMB200_DEPTH_NORMAL */
+  float weak_threshold;     /* CG: 10.0 */
+  int num_features;         /* 63 */
+  float strong_threshold;   /* CG: 55.0 */
+  int distance_threshold;   /* DN: 2000 */
+  int difference_threshold; /* DN: 50 */
+  int extract_threshold;    /* DN: 2 */
+} lmb200_modality;
+
+#define LMB200_MAX_MODALITIES 4
+#define LMB200_MAX_LEVELS 8
+
+/* Replaces: cv::linemod::Detector(modalities, T_pyramid)  (HighLevelLinemod.cpp:26-43). */
+typedef struct {
+  int num_modalities;
+  lmb200_modality modalities[LMB200_MAX_MODALITIES];
+  int pyramid_levels;
+  int T[LMB200_MAX_LEVELS];
+  int device;               /* CUDA ordinal; -1 = current device */
+  int max_batch;            /* frames resident per batch call; 0 = default (64) */
+  int candidate_capacity;   /* coarse candidates per frame; 0 = default (16384); grows on overflow */
+} lmb200_config;
+
+typedef struct {
+  const void* data;
+  int rows, cols;
+  int type;                 /* LMB200_8UC3 / LMB200_16UC1 / LMB200_8UC1 */
+  size_t step;              /* bytes per row, 0 = packed */
+} lmb200_image;
+
+typedef struct { int x, y, label; } lmb200_feature;            /* cv::linemod::Feature */
+typedef struct {                                               /* cv::linemod::Template */
+  int width, height, pyramid_level, num_features;
+  const lmb200_feature* features;
+} lmb200_template;
+typedef struct {                                               /* cv::linemod::Match */
+  int x, y;
+  float similarity;
+  int class_index;          /* index into lmb200_class_id(); the C++ wrapper rehydrates the string */
+  int template_id;
+} lmb200_match_rec;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+void lmb200_default_modality(int type, lmb200_modality* out);
+void lmb200_default_config(lmb200_config* out, int with_depth); /* getDefaultLINEMOD / getDefaultLINE: T={5,8} */
+int lmb200_create(const lmb200_config* cfg, lmb200_handle* out);
+void lmb200_destroy(lmb200_handle h);
+const char* lmb200_last_error(lmb200_handle h);                /* h may be NULL: last create error */
+const char* lmb200_version(void);
+
+/* ---- introspection (HighLevelLinemod.cpp:55,:60,:65,:115,:119,:184) ----------------- */
+int lmb200_num_modalities(lmb200_handle h);
+const char* lmb200_modality_name(lmb200_handle h, int i);      /* "ColorGradient" / "DepthNormal" */
+int lmb200_pyramid_levels(lmb200_handle h);
+int lmb200_get_T(lmb200_handle h, int level);
+int lmb200_num_classes(lmb200_handle h);
+const char* lmb200_class_id(lmb200_handle h, int class_index); /* classIds(), std::map key order */
+int lmb200_num_templates(lmb200_handle h, const char* class_id /* NULL = all classes */);
+/* getTemplates(class_id, template_id)[pyramid_index]; pyramid_index = level*num_modalities+modality.
+ * out->features points into handle-owned memory, valid until the template set changes. */
+int lmb200_get_template(lmb200_handle h, const char* class_id, int template_id, int pyramid_index,
+                        lmb200_template* out);
+
+/* ---- template set ------------------------------------------------------------------ */
+/* Replaces detector->addTemplate(sources, class_id, object_mask, &bb)  (HighLevelLinemod.cpp:93).
+ * Quantisation runs on the GPU, feature selection on the host.  *template_id = -1 when extraction
+ * fails (too few features), exactly what the reference tests for (HighLevelLinemod.cpp:97).
+ * bb4 (nullable) = x, y, width, height of the cropped bounding box. */
+int lmb200_add_template(lmb200_handle h, const char* class_id, const lmb200_image* sources, int n_sources,
+                        const lmb200_image* object_mask /* nullable */, int* bb4, int* template_id);
+/* Detector::addSyntheticTemplate: n = pyramid_levels*num_modalities templates, index level*M+modality. */
+int lmb200_add_synthetic_template(lmb200_handle h, const char* class_id, const lmb200_template* templates,
+                                  int n, int* template_id);
+int lmb200_clear_templates(lmb200_handle h);
+
+/* ---- persistence (OpenCV FileStorage YAML 1.0, optional .gz) ------------------------ */
+/* lmb200_write: what HighLevelLineMOD::writeLinemod puts in linemod_templates.yml.gz
+ *   (HighLevelLinemod.cpp:256-270): Detector::write at the root + "classes": [ {writeClass}, ... ].
+ * lmb200_read : the mirror (HighLevelLinemod.cpp:288-300): creates a detector from the file's
+ *   pyramid_levels/T/modalities and readClass()es every entry of "classes". */
+int lmb200_write(lmb200_handle h, const char* path);
+int lmb200_read(const char* path, int device, lmb200_handle* out);
+/* Detector::writeClasses / readClasses with format("templates_%s.yml.gz", class_id). */
+int lmb200_write_classes(lmb200_handle h, const char* format);
+int lmb200_read_classes(lmb200_handle h, const char* const* class_ids, int n, const char* format);
+
+/* ---- matching ------------------------------------------------------------------------ */
+/* Replaces detector->match(sources, threshold, matches, class_ids, quantized_images, masks)
+ * (HighLevelLinemod.cpp:152).  Result order is upstream's: generation order (class, template_id,
+ * coarse raster) -> std::sort -> std::unique.  class_ids NULL/0 = all classes in map order; unknown
+ * ids are skipped silently like upstream.  quantized_out (nullable): pyramid_levels*num_modalities
+ * caller-allocated LMB200_8UC1 images, index level*M+modality, sized rows>>level x cols>>level.
+ * masks (nullable): num_modalities LMB200_8UC1 images (data may be NULL per entry = no mask).
+ * If cap < matches: fills cap records, sets *n_out to the full count, returns LMB200_E_TRUNCATED. */
+int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, float threshold,
+                 const char* const* class_ids, int n_class_ids,
+                 lmb200_match_rec* out, size_t cap, size_t* n_out,
+                 lmb200_image* quantized_out, const lmb200_image* masks);
+
+/* Streams n_frames frames (frames[f*n_sources + m]) through the same path: chunked H2D copies,
+ * kernels and D2H of the match lists overlap on two CUDA streams.  Per-frame results are written
+ * at out[offsets[f] .. offsets[f+1]) (offsets has n_frames+1 entries).  Use pinned host memory
+ * (lmb200_host_alloc) for the frames to get asynchronous copies. */
+int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
+                       const char* const* class_ids, int n_class_ids,
+                       lmb200_match_rec* out, size_t cap, size_t* offsets);
+
+/* Device-resident variant used to time the path without PCIe: upload once, match many times.
+ * lmb200_match_resident enqueues the whole device pipeline for frames [first, first+count) and
+ * returns without synchronising; lmb200_fetch_resident synchronises, copies the packed match lists
+ * back and applies the host sort/unique. */
+int lmb200_upload_frames(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, int first_slot);
+int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float threshold,
+                          const char* const* class_ids, int n_class_ids);
+int lmb200_fetch_resident(lmb200_handle h, int first_slot, int count,
+                          lmb200_match_rec* out, size_t cap, size_t* offsets);
+int lmb200_synchronize(lmb200_handle h);
+void* lmb200_stream(lmb200_handle h);                           /* cudaStream_t of the compute lane */
+/* CUDA-event stopwatch on the compute stream: which = 0 records "start", 1 records "stop". */
+int lmb200_timer_record(lmb200_handle h, int which);
+int lmb200_timer_elapsed_ms(lmb200_handle h, float* ms);        /* synchronises on "stop" */
+
+int lmb200_host_alloc(size_t bytes, void** out);                /* cudaHostAlloc (pinned) */
+int lmb200_host_free(void* p);
+
+/* ---- tables --------------------------------------------------------------------------- */
+/* 256-byte SIMILARITY_LUT (layout of upstream's table: [32*ori + 16*half + nibble]).
+ * Default = the table upstream ships (non-circular |ori-j| distance). */
+int lmb200_set_similarity_lut(lmb200_handle h, const uint8_t* lut256);
+int lmb200_get_similarity_lut(lmb200_handle h, uint8_t* lut256);
+/* 8000-byte NORMAL_LUT[20][20][20] (index [v3][v2][v1]); entries must be 0 or one-hot.
+ * Default = documented stand-in generator (upstream normal_lut.i is not redistributable here). */
+int lmb200_set_normal_lut(lmb200_handle h, const uint8_t* lut8000);
+int lmb200_get_normal_lut(lmb200_handle h, uint8_t* lut8000);
+
+/* ---- multi-GPU (one process per GPU) -------------------------------------------------- */
+/* Template sharding: this handle scores only shard `rank` of `world` contiguous, cost-balanced
+ * blocks of the generation-ordered template list.  world=1 restores the full set. */
+int lmb200_set_template_shard(lmb200_handle h, int rank, int world);
+/* NCCL plumbing (libnccl.so.2 is dlopen'ed on first use). unique_id is 128 bytes. */
+int lmb200_comm_unique_id(uint8_t* unique_id128);
+int lmb200_comm_init(lmb200_handle h, const uint8_t* unique_id128, int rank, int world);
+int lmb200_comm_destroy(lmb200_handle h);
+/* After lmb200_match_resident on every rank: one ncclAllGather of the fixed-capacity per-frame match
+ * buffers on the compute stream, then the rank-ordered concatenation (= reference generation order)
+ * goes through the same host sort/unique.  Every rank returns the identical merged list.
+ * Template-sharded mode: all ranks hold the same frames. */
+int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, int count,
+                                    lmb200_match_rec* out, size_t cap, size_t* offsets);
+/* Pure host helper (no GPU): merge per-rank, generation-ordered partial lists exactly as above.
+ * parts[r] has counts[r] records.  Used by the gloo CPU tests and by callers with their own transport. */
+int lmb200_merge_matches(const lmb200_match_rec* const* parts, const size_t* counts, int world,
+                         lmb200_match_rec* out, size_t cap, size_t* n_out);
+/* Cost-balanced contiguous split of n templates with costs[] into `world` shards: begin[world+1]. */
+int lmb200_shard_plan(const double* costs, int n, int world, int* begin);
+
+/* ---- measurement / debug --------------------------------------------------------------- */
+enum {
+  LMB200_K_UPLOAD = 0, LMB200_K_PYRDOWN, LMB200_K_CG_QUANTIZE, LMB200_K_DN_QUANTIZE, LMB200_K_MEDIAN,
+  LMB200_K_DECIMATE, LMB200_K_LINEARIZE, LMB200_K_SIM_COARSE, LMB200_K_SIM_LOCAL, LMB200_K_PACK,
+  LMB200_K_COUNT
+};
+typedef struct {
+  double ms[LMB200_K_COUNT];          /* accumulated CUDA-event time per kernel family */
+  long long launches[LMB200_K_COUNT]; /* launches per family */
+  long long bytes_coarse;             /* algorithmic bytes gathered by similarity (sum nf*P) */
+  long long bytes_local;              /* algorithmic bytes gathered by similarityLocal (sum nf*256) */
+  long long frames;
+  long long candidates, matches;
+} lmb200_profile;
+int lmb200_set_profiling(lmb200_handle h, int enabled);        /* CUDA events around every launch */
+int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset);
+
+enum { LMB200_DBG_QUANTIZED = 0, LMB200_DBG_LINMEM = 1, LMB200_DBG_COARSE = 2, LMB200_DBG_UNSORTED = 3,
+       LMB200_DBG_MAGNITUDE = 4, LMB200_DBG_DN_INDICES = 5 };
+/* Copies an intermediate of the LAST match on `slot` to host: QUANTIZED/LINMEM take index=level*M+modality;
+ * COARSE/UNSORTED return lmb200_match_rec arrays (generation order).  *n_bytes in: capacity, out: size. */
+int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst, size_t* n_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMB200_H */

@@ -1,0 +1,1080 @@
+// detector.cu — host orchestration of the match path: device template tables, frame plan,
+// kernel sequencing on CUDA streams, result fetch + the reference's sort/unique epilogue.
+// Mirrors cv::linemod::Detector::match / matchClass (opencv_contrib rgbd/linemod.cpp; SURVEY.md
+// Appendix A.6-A.7) as called from the reference at src/HighLevelLinemod.cpp:152.
+// There is NO CPU fallback: without a CUDA device every compute entry point fails with
+// LMB200_E_NODEVICE.
+#include "detector.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+using namespace lmk;
+
+namespace lmh {
+
+void finalize_matches(std::vector<Match>& m) {
+  std::sort(m.begin(), m.end());
+  m.erase(std::unique(m.begin(), m.end()), m.end());
+}
+
+int DevBuf::alloc(size_t n) {
+  if (n <= bytes && p) return 0;
+  release();
+  cudaError_t e = cudaMalloc(&p, n);
+  if (e != cudaSuccess) { p = nullptr; bytes = 0; return (int)e; }
+  bytes = n;
+  return 0;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr; bytes = 0;
+}
+
+int set_error(lmb200_detector* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int cuda_fail(lmb200_detector* h, cudaError_t e, const char* what) {
+  return set_error(h, LMB200_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                                   \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);       \
+  } while (0)
+#define ALLOC(buf, n)                                              \
+  do {                                                             \
+    int e__ = (buf).alloc(n);                                      \
+    if (e__) return cuda_fail(h, (cudaError_t)e__, "cudaMalloc");  \
+  } while (0)
+
+int ensure_device(lmb200_detector* h) {
+  if (h->device_ready) {
+    cudaSetDevice(h->device);
+    return LMB200_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(h, LMB200_E_NODEVICE, "no CUDA device available (this library has no CPU fallback)");
+  }
+  int dev = h->cfg.device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= n) return set_error(h, LMB200_E_INVALID, "device ordinal out of range");
+  CU(cudaSetDevice(dev));
+  h->device = dev;
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaStreamCreateWithFlags(&h->lanes[i].stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->lanes[i].done, cudaEventDisableTiming));
+  }
+  h->device_ready = true;
+  return LMB200_OK;
+}
+
+// ---------------------------------------------------------------- profiling helpers
+struct ProfScope {
+  lmb200_detector* h; int family; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(lmb200_detector* h_, int fam, cudaStream_t s) : h(h_), family(fam), st(s) {
+    h->prof.launches[fam]++;
+    if (!h->profiling) return;
+    auto take = [&]() {
+      cudaEvent_t ev;
+      if (!h->event_pool.empty()) { ev = h->event_pool.back(); h->event_pool.pop_back(); }
+      else cudaEventCreate(&ev);
+      return ev;
+    };
+    a = take(); b = take();
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    h->prof_pending.push_back(ProfRec{family, a, b});
+  }
+};
+
+static void collect_profile(lmb200_detector* h) {
+  for (auto& r : h->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) h->prof.ms[r.family] += ms;
+    h->event_pool.push_back(r.a);
+    h->event_pool.push_back(r.b);
+  }
+  h->prof_pending.clear();
+}
+
+// ---------------------------------------------------------------- tables
+static int upload_luts(lmb200_detector* h) {
+  if (!h->luts_dirty) return LMB200_OK;
+  uint2 table[256];
+  for (int s = 0; s < 256; ++s) {
+    u32 lo = 0, hi = 0;
+    for (int o = 0; o < 8; ++o) {
+      u32 v = std::max(h->sim_lut[32 * o + (s & 15)], h->sim_lut[32 * o + 16 + (s >> 4)]);
+      if (o < 4) lo |= v << (8 * o); else hi |= v << (8 * (o - 4));
+    }
+    table[s] = make_uint2(lo, hi);
+  }
+  ALLOC(h->d_table, sizeof(table));
+  ALLOC(h->d_normal_lut, 8000);
+  CU(cudaMemcpy(h->d_table.p, table, sizeof(table), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_normal_lut.p, h->normal_lut, 8000, cudaMemcpyHostToDevice));
+  h->luts_dirty = false;
+  return LMB200_OK;
+}
+
+static int rebuild_templates(lmb200_detector* h) {
+  if (!h->templates_dirty) return LMB200_OK;
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  h->class_list.clear(); h->g_class.clear(); h->g_tid.clear();
+  int ci = 0;
+  for (auto& kv : h->classes) {
+    h->class_list.push_back(kv.first);
+    for (size_t t = 0; t < kv.second.size(); ++t) { h->g_class.push_back(ci); h->g_tid.push_back((int)t); }
+    ++ci;
+  }
+  h->ntpl = (int)h->g_class.size();
+  std::vector<TplHdr> hdr((size_t)std::max(1, h->ntpl));
+  std::vector<u32> feat((size_t)std::max(1, h->ntpl) * M * FEAT_SLOTS);
+  for (int l = 0; l < L; ++l) {
+    std::fill(feat.begin(), feat.end(), 0u);
+    int g = 0;
+    for (auto& kv : h->classes)
+      for (auto& tp : kv.second) {
+        TplHdr& hd = hdr[g];
+        std::memset(&hd, 0, sizeof(hd));
+        for (int m = 0; m < M; ++m) {
+          const Template& t = tp[(size_t)l * M + m];
+          if (t.features.size() > 63)
+            return set_error(h, LMB200_E_FEATURES, "template has more than 63 features (upstream CV_Assert)");
+          hd.width[m] = (short)std::max(-32768, std::min(32767, t.width));
+          hd.height[m] = (short)std::max(-32768, std::min(32767, t.height));
+          hd.nf[m] = (u8)t.features.size();
+          for (size_t k = 0; k < t.features.size(); ++k)
+            feat[((size_t)g * M + m) * FEAT_SLOTS + k] = pack_feature(t.features[k].x, t.features[k].y, t.features[k].label);
+        }
+        ++g;
+      }
+    ALLOC(h->d_hdr[l], hdr.size() * sizeof(TplHdr));
+    ALLOC(h->d_feat[l], feat.size() * sizeof(u32));
+    ALLOC(h->d_offs[l], feat.size() * sizeof(u32));
+    CU(cudaMemcpy(h->d_hdr[l].p, hdr.data(), hdr.size() * sizeof(TplHdr), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_feat[l].p, feat.data(), feat.size() * sizeof(u32), cudaMemcpyHostToDevice));
+  }
+  h->templates_dirty = false;
+  h->plan_dirty = true;
+  h->sel_key.clear();  // force selection rebuild
+  h->h_sel.clear();
+  return LMB200_OK;
+}
+
+static void free_host_mirrors(lmb200_detector* h) {
+  if (h->h_out_count) cudaFreeHost(h->h_out_count);
+  if (h->h_overflow) cudaFreeHost(h->h_overflow);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  h->h_out_count = nullptr; h->h_overflow = nullptr; h->h_stats = nullptr; h->h_out = nullptr;
+}
+
+static int alloc_match_buffers(lmb200_detector* h) {
+  const int S = h->slots;
+  h->nsel_stride = std::max(1, h->ntpl);
+  ALLOC(h->d_cand, (size_t)S * h->cand_cap * sizeof(Cand));
+  ALLOC(h->d_out, (size_t)S * h->out_cap * sizeof(Cand));
+  ALLOC(h->d_cand_count, (size_t)S * sizeof(int));
+  ALLOC(h->d_out_count, (size_t)S * sizeof(int));
+  ALLOC(h->d_overflow, (size_t)S * sizeof(int));
+  ALLOC(h->d_stats, (size_t)S * sizeof(unsigned long long));
+  ALLOC(h->d_tpl_start, (size_t)S * h->nsel_stride * sizeof(int));
+  ALLOC(h->d_tpl_cnt, (size_t)S * h->nsel_stride * sizeof(int));
+  free_host_mirrors(h);
+  h->h_head = std::min(h->out_cap, 1024);
+  CU(cudaHostAlloc((void**)&h->h_out_count, (size_t)S * sizeof(int), cudaHostAllocDefault));
+  CU(cudaHostAlloc((void**)&h->h_overflow, (size_t)S * sizeof(int), cudaHostAllocDefault));
+  CU(cudaHostAlloc((void**)&h->h_stats, (size_t)S * sizeof(unsigned long long), cudaHostAllocDefault));
+  CU(cudaHostAlloc((void**)&h->h_out, (size_t)S * h->out_cap * sizeof(Cand), cudaHostAllocDefault));
+  h->slot_threshold.assign(S, 0.f);
+  return LMB200_OK;
+}
+
+// Frame plan: per-level geometry + every per-slot device buffer.  Re-planned when the frame size changes.
+static int ensure_plan(lmb200_detector* h, int rows, int cols) {
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  int rc = upload_luts(h);
+  if (rc) return rc;
+  rc = rebuild_templates(h);
+  if (rc) return rc;
+  const int S = h->cfg.max_batch > 0 ? h->cfg.max_batch : 64;
+  bool geom_changed = rows != h->rows || cols != h->cols || S != h->slots || (int)h->levels.size() != L;
+  if (geom_changed) {
+    // validate like upstream's CV_Asserts (linearize: rows%T, cols%T; computeResponseMaps: (rows*cols)%16)
+    int r = rows, c = cols;
+    for (int l = 0; l < L; ++l) {
+      int T = h->cfg.T[l];
+      if (T <= 0 || r <= 0 || c <= 0 || r % T || c % T || (r * c) % 16)
+        return set_error(h, LMB200_E_SIZE, "image size at pyramid level " + std::to_string(l) + " (" + std::to_string(c) +
+                                                "x" + std::to_string(r) + ") must be divisible by T and rows*cols by 16");
+      if (c > 16383 || r > 16383) return set_error(h, LMB200_E_SIZE, "image larger than 16383 pixels per side");
+      r /= 2; c /= 2;
+    }
+    CU(cudaDeviceSynchronize());
+    h->levels.assign(L, LevelBuffers());
+    r = rows; c = cols;
+    auto up256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    for (int l = 0; l < L; ++l) {
+      LevelBuffers& lb = h->levels[l];
+      int T = h->cfg.T[l];
+      lb.g.T = T; lb.g.rows = r; lb.g.cols = c; lb.g.W = c / T; lb.g.H = r / T;
+      lb.g.per_label = (u32)((size_t)r * c);
+      lb.q_stride = up256((size_t)r * c);
+      lb.lm_stride = up256((size_t)8 * r * c + LM_PAD);
+      lb.bgr_stride = up256((size_t)r * c * 3);
+      for (int m = 0; m < M; ++m) {
+        ALLOC(lb.q[m], lb.q_stride * S);
+        ALLOC(lb.lm[m], lb.lm_stride * S);
+        CU(cudaMemset(lb.lm[m].p, 0, lb.lm_stride * S));  // the pad bytes stay zero forever
+        if (h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT) ALLOC(lb.bgr[m], lb.bgr_stride * S);
+      }
+      r /= 2; c /= 2;
+    }
+    h->depth_stride = up256((size_t)rows * cols * 2) / 2;
+    for (int m = 0; m < M; ++m)
+      if (h->cfg.modalities[m].type == LMB200_DEPTH_NORMAL) {
+        ALLOC(h->d_depth[m], h->depth_stride * 2 * S);
+        ALLOC(h->d_dnraw[m], h->levels[0].q_stride * S);
+      }
+    h->rows = rows; h->cols = cols; h->slots = S;
+    if (h->cand_cap <= 0) h->cand_cap = h->cfg.candidate_capacity > 0 ? h->cfg.candidate_capacity : 16384;
+    if (h->out_cap <= 0) h->out_cap = h->cand_cap;
+    h->nsel_stride = 0;
+    h->plan_dirty = true;
+    h->masks_in_use = false;
+  }
+  if (h->nsel_stride < std::max(1, h->ntpl) || !h->d_cand.p) {
+    rc = alloc_match_buffers(h);
+    if (rc) return rc;
+  }
+  if (h->plan_dirty) {
+    cudaStream_t st = h->lanes[0].stream;
+    for (int l = 0; l < L; ++l)
+      launch_build_offsets(h->d_feat[l].as<u32>(), h->d_offs[l].as<u32>(), h->d_hdr[l].as<TplHdr>(), h->ntpl, M,
+                           h->levels[l].g, st);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    // algorithmic coarse bytes per template: sum_m nf * P  
+    h->tpl_cost.assign(h->ntpl, 0.0);
+    const LevelGeom& g = h->levels[L - 1].g;
+    int gi = 0;
+    for (auto& kv : h->classes)
+      for (auto& tp : kv.second) {
+        double cost = 0;
+        for (int m = 0; m < M; ++m) {
+          const Template& t = tp[(size_t)(L - 1) * M + m];
+          int wf = (t.width - 1) / g.T + 1, hf = (t.height - 1) / g.T + 1;
+          long long P = (long long)(g.H - hf) * g.W + (g.W - wf) + 1;
+          if (P > (long long)g.W * g.H) P = (long long)g.W * g.H;
+          if (P > 0) cost += (double)P * (double)t.features.size();
+        }
+        h->tpl_cost[gi++] = cost;
+      }
+    h->plan_dirty = false;
+    h->sel_key.clear();
+  }
+  return LMB200_OK;
+}
+
+}  // namespace lmh
+
+using namespace lmh;
+
+extern "C" int lmb200_shard_plan(const double* costs, int n, int world, int* begin);
+
+// Selection list = templates this handle scores, in generation order (class order as requested,
+// template_id ascending), then restricted to this rank's cost-balanced shard.
+static int ensure_selection(lmb200_detector* h, const char* const* class_ids, int n_class_ids) {
+  std::string key = std::to_string(h->shard_rank) + "/" + std::to_string(h->shard_world) + ":";
+  for (int i = 0; i < n_class_ids; ++i) { key += class_ids[i]; key.push_back('\x1f'); }
+  if (key == h->sel_key && h->d_sel.p) return LMB200_OK;
+  std::vector<int> sel;
+  if (n_class_ids <= 0) {
+    sel.resize(h->ntpl);
+    for (int i = 0; i < h->ntpl; ++i) sel[i] = i;
+  } else {
+    // first global index of each class
+    std::vector<int> first(h->class_list.size() + 1, 0);
+    for (int i = 0; i < h->ntpl; ++i) first[h->g_class[i] + 1] = i + 1;
+    for (size_t c = 1; c < first.size(); ++c) first[c] = std::max(first[c], first[c - 1]);
+    for (int i = 0; i < n_class_ids; ++i) {
+      auto it = std::lower_bound(h->class_list.begin(), h->class_list.end(), std::string(class_ids[i]));
+      if (it == h->class_list.end() || *it != class_ids[i]) continue;  // unknown ids are skipped like upstream
+      int c = (int)(it - h->class_list.begin());
+      for (int g = first[c]; g < first[c + 1]; ++g) sel.push_back(g);
+    }
+  }
+  if (h->shard_world > 1) {
+    std::vector<double> costs(sel.size());
+    for (size_t i = 0; i < sel.size(); ++i) costs[i] = h->tpl_cost[sel[i]] + 1.0;
+    std::vector<int> begin(h->shard_world + 1);
+    lmb200_shard_plan(costs.data(), (int)sel.size(), h->shard_world, begin.data());
+    sel = std::vector<int>(sel.begin() + begin[h->shard_rank], sel.begin() + begin[h->shard_rank + 1]);
+  }
+  h->h_sel = sel;
+  h->sel_bytes_coarse = 0;
+  for (int g : sel) h->sel_bytes_coarse += (long long)h->tpl_cost[g];
+  ALLOC(h->d_sel, std::max<size_t>(1, sel.size()) * sizeof(int));
+  if (!sel.empty()) CU(cudaMemcpy(h->d_sel.p, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice));
+  h->sel_key = key;
+  return LMB200_OK;
+}
+
+static int check_sources(lmb200_detector* h, const lmb200_image* srcs, int n_sources, int* rows, int* cols) {
+  const int M = h->cfg.num_modalities;
+  if (n_sources != M) return set_error(h, LMB200_E_SOURCES, "sources.size() != modalities.size()");
+  for (int m = 0; m < M; ++m) {
+    int want = h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT ? LMB200_8UC3 : LMB200_16UC1;
+    if (!srcs[m].data || srcs[m].type != want)
+      return set_error(h, LMB200_E_SOURCES, "source " + std::to_string(m) + " must be " + (want == LMB200_8UC3 ? "8UC3" : "16UC1"));
+    if (srcs[m].rows != srcs[0].rows || srcs[m].cols != srcs[0].cols)
+      return set_error(h, LMB200_E_SOURCES, "sources differ in size");
+  }
+  *rows = srcs[0].rows; *cols = srcs[0].cols;
+  return LMB200_OK;
+}
+
+// H2D of one frame's sources into `slot` on `st`.
+static int upload_one(lmb200_detector* h, const lmb200_image* srcs, int slot, cudaStream_t st) {
+  const int M = h->cfg.num_modalities;
+  for (int m = 0; m < M; ++m) {
+    const lmb200_image& im = srcs[m];
+    if (h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT) {
+      size_t rowb = (size_t)im.cols * 3, step = im.step ? im.step : rowb;
+      u8* dst = h->levels[0].bgr[m].as<u8>() + (size_t)slot * h->levels[0].bgr_stride;
+      if (step == rowb) CU(cudaMemcpyAsync(dst, im.data, rowb * im.rows, cudaMemcpyHostToDevice, st));
+      else CU(cudaMemcpy2DAsync(dst, rowb, im.data, step, rowb, im.rows, cudaMemcpyHostToDevice, st));
+    } else {
+      size_t rowb = (size_t)im.cols * 2, step = im.step ? im.step : rowb;
+      u16* dst = h->d_depth[m].as<u16>() + (size_t)slot * h->depth_stride;
+      if (step == rowb) CU(cudaMemcpyAsync(dst, im.data, rowb * im.rows, cudaMemcpyHostToDevice, st));
+      else CU(cudaMemcpy2DAsync(dst, rowb, im.data, step, rowb, im.rows, cudaMemcpyHostToDevice, st));
+    }
+  }
+  return LMB200_OK;
+}
+
+// Frame side for slots [first, first+count): quantise every modality at every level, then
+// spread + response + linearize.  (Detector::match, first half.)
+static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st) {
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  for (int l = 0; l < L; ++l) {
+    LevelBuffers& lb = h->levels[l];
+    for (int m = 0; m < M; ++m) {
+      const lmb200_modality& mod = h->cfg.modalities[m];
+      u8* q = lb.q[m].as<u8>() + (size_t)first * lb.q_stride;
+      if (mod.type == LMB200_COLOR_GRADIENT) {
+        u8* bgr = lb.bgr[m].as<u8>() + (size_t)first * lb.bgr_stride;
+        if (l > 0) {
+          LevelBuffers& pb = h->levels[l - 1];
+          ProfScope ps(h, LMB200_K_PYRDOWN, st);
+          launch_pyrdown_bgr(pb.bgr[m].as<u8>() + (size_t)first * pb.bgr_stride, pb.bgr_stride, bgr, lb.bgr_stride,
+                             pb.g.rows, pb.g.cols, count, st);
+        }
+        ProfScope ps(h, LMB200_K_CG_QUANTIZE, st);
+        launch_cg_quantize(bgr, lb.bgr_stride, q, lb.q_stride, nullptr, 0, lb.g.rows, lb.g.cols,
+                           mod.weak_threshold * mod.weak_threshold, count, st);
+      } else {
+        if (l == 0) {
+          u8* raw = h->d_dnraw[m].as<u8>() + (size_t)first * lb.q_stride;
+          {
+            ProfScope ps(h, LMB200_K_DN_QUANTIZE, st);
+            launch_dn_quantize(h->d_depth[m].as<u16>() + (size_t)first * h->depth_stride, h->depth_stride, raw,
+                               lb.q_stride, nullptr, lb.g.rows, lb.g.cols, mod.distance_threshold,
+                               mod.difference_threshold, h->d_normal_lut.as<u8>(), count, st);
+          }
+          ProfScope ps(h, LMB200_K_MEDIAN, st);
+          launch_median5(raw, lb.q_stride, q, lb.q_stride, lb.g.rows, lb.g.cols, count, st);
+        } else {
+          LevelBuffers& pb = h->levels[l - 1];
+          ProfScope ps(h, LMB200_K_DECIMATE, st);
+          launch_resize_nn(pb.q[m].as<u8>() + (size_t)first * pb.q_stride, pb.q_stride, pb.g.rows, pb.g.cols, q,
+                           lb.q_stride, lb.g.rows, lb.g.cols, count, st);
+        }
+      }
+      const u8* mask = nullptr;
+      if (h->masks_in_use && lb.mask[m].p) mask = lb.mask[m].as<u8>() + (size_t)first * lb.q_stride;
+      ProfScope ps(h, LMB200_K_LINEARIZE, st);
+      launch_spread_linearize(q, lb.q_stride, mask, lb.q_stride, lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride,
+                              lb.lm_stride, lb.g, h->d_table.as<uint2>(), count, st);
+    }
+  }
+  CU(cudaGetLastError());
+  return LMB200_OK;
+}
+
+static MatchParams make_match_params(lmb200_detector* h, int first, int count, float threshold) {
+  MatchParams mp;
+  mp.M = h->cfg.num_modalities;
+  mp.nsel = (int)h->h_sel.size();
+  mp.frames = count;
+  mp.sel = h->d_sel.as<int>();
+  mp.threshold = threshold;
+  mp.cand = h->d_cand.as<Cand>() + (size_t)first * h->cand_cap;
+  mp.cand_cap = h->cand_cap;
+  mp.cand_count = h->d_cand_count.as<int>() + first;
+  mp.nsel_stride = h->nsel_stride;
+  mp.tpl_start = h->d_tpl_start.as<int>() + (size_t)first * h->nsel_stride;
+  mp.tpl_cnt = h->d_tpl_cnt.as<int>() + (size_t)first * h->nsel_stride;
+  mp.overflow = h->d_overflow.as<int>() + first;
+  mp.stats = h->d_stats.as<unsigned long long>() + first;
+  return mp;
+}
+
+static LevelParams make_level_params(lmb200_detector* h, int l, int first) {
+  LevelParams lp;
+  LevelBuffers& lb = h->levels[l];
+  lp.g = lb.g;
+  for (int m = 0; m < MAX_MOD; ++m) {
+    int mm = m < h->cfg.num_modalities ? m : 0;
+    lp.lm[m] = lb.lm[mm].as<u8>() + (size_t)first * lb.lm_stride;
+    lp.lm_stride[m] = lb.lm_stride;
+  }
+  lp.hdr = h->d_hdr[l].as<TplHdr>();
+  lp.offs = h->d_offs[l].as<u32>();
+  lp.feat = h->d_feat[l].as<u32>();
+  return lp;
+}
+
+// Template side for slots [first, first+count): coarse similarity + threshold, refinement per level,
+// ordered compaction.  (Detector::matchClass.)  stop_after_coarse: debug path.
+static int run_matching(lmb200_detector* h, int first, int count, float threshold, cudaStream_t st,
+                        bool stop_after_coarse = false) {
+  const int L = h->cfg.pyramid_levels;
+  MatchParams mp = make_match_params(h, first, count, threshold);
+  CU(cudaMemsetAsync(mp.cand_count, 0, sizeof(int) * count, st));
+  CU(cudaMemsetAsync(mp.overflow, 0, sizeof(int) * count, st));
+  CU(cudaMemsetAsync(mp.stats, 0, sizeof(unsigned long long) * count, st));
+  CU(cudaMemsetAsync(h->d_out_count.as<int>() + first, 0, sizeof(int) * count, st));
+  if (mp.nsel > 0) {
+    {
+      ProfScope ps(h, LMB200_K_SIM_COARSE, st);
+      launch_similarity_coarse(mp, make_level_params(h, L - 1, first), st);
+    }
+    if (!stop_after_coarse)
+      for (int l = L - 2; l >= 0; --l) {
+        ProfScope ps(h, LMB200_K_SIM_LOCAL, st);
+        launch_similarity_local(mp, make_level_params(h, l, first), st);
+      }
+    ProfScope ps(h, LMB200_K_PACK, st);
+    launch_pack(mp, h->d_out.as<Cand>() + (size_t)first * h->out_cap, h->out_cap, h->d_out_count.as<int>() + first, st);
+  }
+  CU(cudaGetLastError());
+  for (int i = 0; i < count; ++i) h->slot_threshold[first + i] = threshold;
+  h->prof.frames += count;
+  h->prof.bytes_coarse += (long long)count * h->sel_bytes_coarse;
+  return LMB200_OK;
+}
+
+static int grow_capacity(lmb200_detector* h) {
+  CU(cudaDeviceSynchronize());
+  if (h->cand_cap > (1 << 24)) return set_error(h, LMB200_E_CUDA, "candidate buffer overflow persists after growing");
+  h->cand_cap *= 4; h->out_cap = h->cand_cap;
+  return alloc_match_buffers(h);
+}
+
+// D2H of counts + list heads, then per-frame record vectors in generation order (global template
+// index in .tsel).  Returns +1 (nothing consumed) when a device-side store overflowed: the caller
+// grows the stores (grow_capacity) and redoes the template side — linear memories stay resident.
+static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out) {
+  CU(cudaMemcpyAsync(h->h_out_count + first, h->d_out_count.as<int>() + first, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_overflow + first, h->d_overflow.as<int>() + first, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_stats + first, h->d_stats.as<unsigned long long>() + first, sizeof(unsigned long long) * count,
+                     cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpy2DAsync(h->h_out + (size_t)first * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
+                       h->d_out.as<Cand>() + (size_t)first * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
+                       (size_t)h->h_head * sizeof(Cand), count, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < count; ++i)
+    if (h->h_overflow[first + i] != 0 || h->h_out_count[first + i] > h->out_cap) return 1;
+  bool any_tail = false;
+  for (int i = 0; i < count; ++i) {
+    int n = h->h_out_count[first + i];
+    if (n > h->h_head) {
+      any_tail = true;
+      CU(cudaMemcpyAsync(h->h_out + (size_t)(first + i) * h->out_cap + h->h_head,
+                         h->d_out.as<Cand>() + (size_t)(first + i) * h->out_cap + h->h_head,
+                         (size_t)(n - h->h_head) * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  if (any_tail) CU(cudaStreamSynchronize(st));
+  out.resize(count);
+  for (int i = 0; i < count; ++i) {
+    int n = h->h_out_count[first + i];
+    const Cand* src = h->h_out + (size_t)(first + i) * h->out_cap;
+    out[i].assign(src, src + n);
+    h->prof.bytes_local += (long long)h->h_stats[first + i];
+  }
+  if (h->profiling) collect_profile(h);
+  return LMB200_OK;
+}
+
+// Single-lane fetch: on overflow grow the stores and redo the template side of [first, first+count).
+static int fetch_grow(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out) {
+  for (;;) {
+    int rc = fetch_raw(h, first, count, st, out);
+    if (rc <= 0) return rc;
+    float thr = h->slot_threshold[first];
+    rc = grow_capacity(h);
+    if (rc) return rc;
+    rc = run_matching(h, first, count, thr, st);
+    if (rc) return rc;
+  }
+}
+
+static void to_matches(lmb200_detector* h, const std::vector<Cand>& raw, std::vector<Match>& m) {
+  m.resize(raw.size());
+  for (size_t i = 0; i < raw.size(); ++i) {
+    int g = raw[i].tsel;
+    m[i] = Match{raw[i].x, raw[i].y, raw[i].sim, h->g_class[g], h->g_tid[g]};
+  }
+}
+
+static int emit(lmb200_detector* h, const std::vector<Match>& m, lmb200_match_rec* out, size_t cap, size_t base,
+                size_t* written) {
+  size_t n = m.size();
+  size_t room = cap > base ? cap - base : 0;
+  size_t w = std::min(n, room);
+  for (size_t i = 0; i < w; ++i) {
+    out[base + i].x = m[i].x; out[base + i].y = m[i].y; out[base + i].similarity = m[i].similarity;
+    out[base + i].class_index = m[i].class_index; out[base + i].template_id = m[i].template_id;
+  }
+  *written = n;
+  (void)h;
+  return w < n ? LMB200_E_TRUNCATED : LMB200_OK;
+}
+
+static int prepare(lmb200_detector* h, const lmb200_image* frames, int n_frames, int n_sources,
+                   const char* const* class_ids, int n_class_ids) {
+  if (!h || !frames || n_frames <= 0) return set_error(h, LMB200_E_INVALID, "bad arguments");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  int rows = 0, cols = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    int r, c;
+    rc = check_sources(h, frames + (size_t)f * n_sources, n_sources, &r, &c);
+    if (rc) return rc;
+    if (f == 0) { rows = r; cols = c; }
+    else if (r != rows || c != cols) return set_error(h, LMB200_E_SOURCES, "frames of one batch differ in size");
+  }
+  rc = ensure_plan(h, rows, cols);
+  if (rc) return rc;
+  return ensure_selection(h, class_ids, n_class_ids);
+}
+
+extern "C" {
+
+int lmb200_upload_frames(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, int first_slot) {
+  int rc = prepare(h, frames, n_frames, n_sources, nullptr, 0);
+  if (rc) return rc;
+  if (first_slot < 0 || first_slot + n_frames > h->slots) return set_error(h, LMB200_E_INVALID, "slot range exceeds max_batch");
+  cudaStream_t st = h->lanes[0].stream;
+  for (int f = 0; f < n_frames; ++f) {
+    ProfScope ps(h, LMB200_K_UPLOAD, st);
+    rc = upload_one(h, frames + (size_t)f * n_sources, first_slot + f, st);
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(st));
+  return LMB200_OK;
+}
+
+int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float threshold,
+                          const char* const* class_ids, int n_class_ids) {
+  if (!h || !h->device_ready || h->rows == 0) return set_error(h, LMB200_E_INVALID, "no frames uploaded");
+  if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
+  cudaSetDevice(h->device);
+  int rc = ensure_plan(h, h->rows, h->cols);
+  if (rc) return rc;
+  rc = ensure_selection(h, class_ids, n_class_ids);
+  if (rc) return rc;
+  cudaStream_t st = h->lanes[0].stream;
+  rc = run_frame_side(h, first_slot, count, st);
+  if (rc) return rc;
+  return run_matching(h, first_slot, count, threshold, st);
+}
+
+int lmb200_fetch_resident(lmb200_handle h, int first_slot, int count, lmb200_match_rec* out, size_t cap, size_t* offsets) {
+  if (!h || !h->device_ready) return set_error(h, LMB200_E_INVALID, "nothing to fetch");
+  if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
+  cudaSetDevice(h->device);
+  std::vector<std::vector<Cand>> raw;
+  int rc = fetch_grow(h, first_slot, count, h->lanes[0].stream, raw);
+  if (rc) return rc;
+  size_t base = 0;
+  int status = LMB200_OK;
+  std::vector<Match> m;
+  for (int i = 0; i < count; ++i) {
+    to_matches(h, raw[i], m);
+    h->prof.candidates += (long long)raw[i].size();
+    finalize_matches(m);
+    h->prof.matches += (long long)m.size();
+    size_t n = 0;
+    if (offsets) offsets[i] = base;
+    if (emit(h, m, out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
+    base += n;
+  }
+  if (offsets) offsets[count] = base;
+  return status;
+}
+
+int lmb200_synchronize(lmb200_handle h) {
+  if (!h || !h->device_ready) return LMB200_OK;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(h->lanes[i].stream));
+  if (h->profiling) collect_profile(h);
+  return LMB200_OK;
+}
+
+void* lmb200_stream(lmb200_handle h) { return h && h->device_ready ? (void*)h->lanes[0].stream : nullptr; }
+
+int lmb200_timer_record(lmb200_handle h, int which) {
+  if (!h || which < 0 || which > 1) return LMB200_E_INVALID;
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  if (!h->timer[which]) CU(cudaEventCreate(&h->timer[which]));
+  CU(cudaEventRecord(h->timer[which], h->lanes[0].stream));
+  return LMB200_OK;
+}
+int lmb200_timer_elapsed_ms(lmb200_handle h, float* ms) {
+  if (!h || !ms || !h->timer[0] || !h->timer[1]) return LMB200_E_INVALID;
+  CU(cudaEventSynchronize(h->timer[1]));
+  CU(cudaEventElapsedTime(ms, h->timer[0], h->timer[1]));
+  return LMB200_OK;
+}
+
+static int upload_masks(lmb200_detector* h, const lmb200_image* masks, cudaStream_t st) {
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  bool any = false;
+  for (int m = 0; m < M; ++m) any |= masks[m].data != nullptr;
+  h->masks_in_use = any;
+  if (!any) return LMB200_OK;
+  for (int m = 0; m < M; ++m) {
+    for (int l = 0; l < L; ++l) {
+      LevelBuffers& lb = h->levels[l];
+      ALLOC(lb.mask[m], lb.q_stride * h->slots);
+    }
+    LevelBuffers& l0 = h->levels[0];
+    if (!masks[m].data) {  // no mask for this modality = all ones
+      for (int l = 0; l < L; ++l) CU(cudaMemsetAsync(h->levels[l].mask[m].p, 0xFF, h->levels[l].q_stride, st));
+      continue;
+    }
+    if (masks[m].type != LMB200_8UC1 || masks[m].rows != h->rows || masks[m].cols != h->cols)
+      return set_error(h, LMB200_E_SOURCES, "mask must be 8UC1 of the source size");
+    size_t step = masks[m].step ? masks[m].step : (size_t)h->cols;
+    CU(cudaMemcpy2DAsync(l0.mask[m].p, h->cols, masks[m].data, step, h->cols, h->rows, cudaMemcpyHostToDevice, st));
+    for (int l = 1; l < L; ++l) {
+      LevelBuffers& pb = h->levels[l - 1];
+      LevelBuffers& lb = h->levels[l];
+      launch_resize_nn(pb.mask[m].as<u8>(), pb.q_stride, pb.g.rows, pb.g.cols, lb.mask[m].as<u8>(), lb.q_stride, lb.g.rows,
+                       lb.g.cols, 1, st);
+    }
+  }
+  return LMB200_OK;
+}
+
+int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, float threshold,
+                 const char* const* class_ids, int n_class_ids, lmb200_match_rec* out, size_t cap, size_t* n_out,
+                 lmb200_image* quantized_out, const lmb200_image* masks) {
+  if (n_out) *n_out = 0;
+  int rc = prepare(h, sources, 1, n_sources, class_ids, n_class_ids);
+  if (rc) return rc;
+  cudaStream_t st = h->lanes[0].stream;
+  {
+    ProfScope ps(h, LMB200_K_UPLOAD, st);
+    rc = upload_one(h, sources, 0, st);
+    if (rc) return rc;
+  }
+  if (masks) {
+    rc = upload_masks(h, masks, st);
+    if (rc) return rc;
+  } else {
+    h->masks_in_use = false;
+  }
+  rc = run_frame_side(h, 0, 1, st);
+  if (rc) return rc;
+  rc = run_matching(h, 0, 1, threshold, st);
+  if (rc) return rc;
+  std::vector<std::vector<Cand>> raw;
+  rc = fetch_grow(h, 0, 1, st, raw);
+  h->masks_in_use = false;
+  if (rc) return rc;
+  if (quantized_out) {
+    const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+    for (int l = 0; l < L; ++l)
+      for (int m = 0; m < M; ++m) {
+        lmb200_image& qi = quantized_out[l * M + m];
+        LevelBuffers& lb = h->levels[l];
+        if (!qi.data) continue;
+        if (qi.rows != lb.g.rows || qi.cols != lb.g.cols) return set_error(h, LMB200_E_INVALID, "quantized_out image has the wrong size");
+        size_t step = qi.step ? qi.step : (size_t)lb.g.cols;
+        // quantize() output is the map after masking
+        CU(cudaMemcpy2D((void*)qi.data, step, lb.q[m].p, lb.g.cols, lb.g.cols, lb.g.rows, cudaMemcpyDeviceToHost));
+        if (masks && masks[m].data) {
+          std::vector<u8> mk((size_t)lb.g.rows * lb.g.cols);
+          CU(cudaMemcpy(mk.data(), lb.mask[m].p, mk.size(), cudaMemcpyDeviceToHost));
+          u8* q = (u8*)qi.data;
+          for (int r = 0; r < lb.g.rows; ++r)
+            for (int c = 0; c < lb.g.cols; ++c)
+              if (!mk[(size_t)r * lb.g.cols + c]) q[(size_t)r * step + c] = 0;
+        }
+      }
+  }
+  std::vector<Match> m;
+  to_matches(h, raw[0], m);
+  h->prof.candidates += (long long)raw[0].size();
+  finalize_matches(m);
+  h->prof.matches += (long long)m.size();
+  size_t n = 0;
+  rc = emit(h, m, out, cap, 0, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+
+// Streaming batch: two lanes, each owning half of the slots; while lane A's chunk is being
+// post-processed on the host (sort/unique), lane B's chunk is copying/computing.
+int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
+                       const char* const* class_ids, int n_class_ids, lmb200_match_rec* out, size_t cap, size_t* offsets) {
+  int rc = prepare(h, frames, n_frames, n_sources, class_ids, n_class_ids);
+  if (rc) return rc;
+  h->masks_in_use = false;
+restart:
+  const int half = std::max(1, h->slots / 2);
+  const int chunk = std::min(half, 8);
+  struct Pending { int first_frame, count, slot0, lane; };
+  std::vector<Pending> inflight;
+  size_t base = 0;
+  int status = LMB200_OK;
+  std::vector<Match> m;
+  auto drain = [&](const Pending& p) -> int {
+    std::vector<std::vector<Cand>> raw;
+    int r = fetch_raw(h, p.slot0, p.count, h->lanes[p.lane].stream, raw);
+    if (r) return r;  // +1: stores overflowed, the whole batch is restarted with larger ones
+    for (int i = 0; i < p.count; ++i) {
+      to_matches(h, raw[i], m);
+      h->prof.candidates += (long long)raw[i].size();
+      finalize_matches(m);
+      h->prof.matches += (long long)m.size();
+      size_t n = 0;
+      if (offsets) offsets[p.first_frame + i] = base;
+      if (emit(h, m, out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
+      base += n;
+    }
+    return LMB200_OK;
+  };
+  int lane = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    int cnt = std::min(chunk, n_frames - f0);
+    if (inflight.size() == 2) {  // lane about to be reused: drain its previous chunk first
+      rc = drain(inflight.front());
+      if (rc > 0) { rc = grow_capacity(h); if (rc) return rc; goto restart; }
+      if (rc) return rc;
+      inflight.erase(inflight.begin());
+    }
+    int slot0 = lane * half;
+    cudaStream_t st = h->lanes[lane].stream;
+    {
+      ProfScope ps(h, LMB200_K_UPLOAD, st);
+      for (int i = 0; i < cnt; ++i) {
+        rc = upload_one(h, frames + (size_t)(f0 + i) * n_sources, slot0 + i, st);
+        if (rc) return rc;
+      }
+    }
+    rc = run_frame_side(h, slot0, cnt, st);
+    if (rc) return rc;
+    rc = run_matching(h, slot0, cnt, threshold, st);
+    if (rc) return rc;
+    inflight.push_back(Pending{f0, cnt, slot0, lane});
+    lane ^= 1;
+  }
+  for (auto& p : inflight) {
+    rc = drain(p);
+    if (rc > 0) { rc = grow_capacity(h); if (rc) return rc; goto restart; }
+    if (rc) return rc;
+  }
+  if (offsets) offsets[n_frames] = base;
+  return status;
+}
+
+int lmb200_host_alloc(size_t bytes, void** out) {
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return LMB200_E_CUDA; }
+  return LMB200_OK;
+}
+int lmb200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LMB200_OK : LMB200_E_CUDA; }
+
+int lmb200_set_profiling(lmb200_handle h, int enabled) {
+  if (!h) return LMB200_E_INVALID;
+  h->profiling = enabled != 0;
+  return LMB200_OK;
+}
+int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset) {
+  if (!h || !out) return LMB200_E_INVALID;
+  if (h->device_ready && h->profiling) {
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 2; ++i) cudaStreamSynchronize(h->lanes[i].stream);
+    collect_profile(h);
+  }
+  *out = h->prof;
+  if (reset) std::memset(&h->prof, 0, sizeof(h->prof));
+  return LMB200_OK;
+}
+
+int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst, size_t* n_bytes) {
+  if (!h || !h->device_ready || !n_bytes || slot < 0 || slot >= h->slots) return set_error(h, LMB200_E_INVALID, "bad debug_fetch arguments");
+  cudaSetDevice(h->device);
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  cudaStream_t st = h->lanes[0].stream;
+  CU(cudaDeviceSynchronize());
+  auto give = [&](const void* dev, size_t n) -> int {
+    size_t capb = *n_bytes;
+    *n_bytes = n;
+    if (!dst || capb < n) return LMB200_E_TRUNCATED;
+    CU(cudaMemcpy(dst, dev, n, cudaMemcpyDeviceToHost));
+    return LMB200_OK;
+  };
+  if (kind == LMB200_DBG_QUANTIZED || kind == LMB200_DBG_LINMEM) {
+    if (index < 0 || index >= L * M) return set_error(h, LMB200_E_INVALID, "bad map index");
+    LevelBuffers& lb = h->levels[index / M];
+    int m = index % M;
+    if (kind == LMB200_DBG_QUANTIZED) return give(lb.q[m].as<u8>() + (size_t)slot * lb.q_stride, (size_t)lb.g.rows * lb.g.cols);
+    return give(lb.lm[m].as<u8>() + (size_t)slot * lb.lm_stride, (size_t)8 * lb.g.rows * lb.g.cols);
+  }
+  if (kind == LMB200_DBG_COARSE || kind == LMB200_DBG_UNSORTED) {
+    int rc = run_matching(h, slot, 1, h->slot_threshold[slot], st, kind == LMB200_DBG_COARSE);
+    if (rc) return rc;
+    std::vector<std::vector<Cand>> raw;
+    rc = fetch_raw(h, slot, 1, st, raw);
+    if (rc) return rc > 0 ? set_error(h, LMB200_E_TRUNCATED, "candidate store overflow in debug fetch") : rc;
+    size_t n = raw[0].size() * sizeof(lmb200_match_rec), capb = *n_bytes;
+    *n_bytes = n;
+    if (!dst || capb < n) return LMB200_E_TRUNCATED;
+    lmb200_match_rec* o = (lmb200_match_rec*)dst;
+    for (size_t i = 0; i < raw[0].size(); ++i) {
+      int g = raw[0][i].tsel;
+      o[i].x = raw[0][i].x; o[i].y = raw[0][i].y; o[i].similarity = raw[0][i].sim;
+      o[i].class_index = h->g_class[g]; o[i].template_id = h->g_tid[g];
+    }
+    return LMB200_OK;
+  }
+  if (kind == LMB200_DBG_MAGNITUDE) {
+    if (index < 0 || index >= M || h->cfg.modalities[index].type != LMB200_COLOR_GRADIENT) return set_error(h, LMB200_E_INVALID, "not a ColorGradient modality");
+    LevelBuffers& lb = h->levels[0];
+    size_t n = (size_t)lb.g.rows * lb.g.cols;
+    ALLOC(h->d_mag, n * sizeof(float));
+    DevBuf tmpq;
+    ALLOC(tmpq, n);
+    const lmb200_modality& mod = h->cfg.modalities[index];
+    launch_cg_quantize(lb.bgr[index].as<u8>() + (size_t)slot * lb.bgr_stride, lb.bgr_stride, tmpq.as<u8>(), n,
+                       h->d_mag.as<float>(), n, lb.g.rows, lb.g.cols, mod.weak_threshold * mod.weak_threshold, 1, st);
+    CU(cudaStreamSynchronize(st));
+    int rc = give(h->d_mag.p, n * sizeof(float));
+    tmpq.release();
+    return rc;
+  }
+  if (kind == LMB200_DBG_DN_INDICES) {
+    if (index < 0 || index >= M || h->cfg.modalities[index].type != LMB200_DEPTH_NORMAL) return set_error(h, LMB200_E_INVALID, "not a DepthNormal modality");
+    LevelBuffers& lb = h->levels[0];
+    size_t n = (size_t)lb.g.rows * lb.g.cols;
+    ALLOC(h->d_dnidx, 3 * n);
+    DevBuf tmpq;
+    ALLOC(tmpq, n);
+    const lmb200_modality& mod = h->cfg.modalities[index];
+    launch_dn_quantize(h->d_depth[index].as<u16>() + (size_t)slot * h->depth_stride, h->depth_stride, tmpq.as<u8>(), n,
+                       h->d_dnidx.as<int8_t>(), lb.g.rows, lb.g.cols, mod.distance_threshold, mod.difference_threshold,
+                       h->d_normal_lut.as<u8>(), 1, st);
+    CU(cudaStreamSynchronize(st));
+    int rc = give(h->d_dnidx.p, 3 * n);
+    tmpq.release();
+    return rc;
+  }
+  return set_error(h, LMB200_E_INVALID, "unknown debug kind");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- addTemplate (GPU quantisation + host selection)
+namespace lmh {
+
+// Quantise `sources` (any size) on the GPU at every pyramid level and hand the maps to the host
+// extractor.  Uses a private single-frame workspace so the match plan is not disturbed.
+int add_template_gpu(lmb200_detector* h, const char* class_id, const lmb200_image* sources, int n_sources,
+                     const lmb200_image* object_mask, int* bb4, int* template_id) {
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  rc = upload_luts(h);
+  if (rc) return rc;
+  int rows, cols;
+  rc = check_sources(h, sources, n_sources, &rows, &cols);
+  if (rc) return rc;
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  std::vector<u8> mask0;
+  if (object_mask && object_mask->data) {
+    if (object_mask->type != LMB200_8UC1 || object_mask->rows != rows || object_mask->cols != cols)
+      return set_error(h, LMB200_E_SOURCES, "object_mask must be 8UC1 of the source size");
+    size_t step = object_mask->step ? object_mask->step : (size_t)cols;
+    mask0.resize((size_t)rows * cols);
+    for (int r = 0; r < rows; ++r) std::memcpy(&mask0[(size_t)r * cols], (const u8*)object_mask->data + (size_t)r * step, cols);
+  }
+  cudaStream_t st = h->lanes[0].stream;
+  // upstream default-inserts the class entry before extraction can fail
+  std::vector<TemplatePyramid>& tps = h->classes[class_id];
+  h->templates_dirty = true;
+  TemplatePyramid tp((size_t)M * L);
+  *template_id = -1;
+
+  size_t n0 = (size_t)rows * cols;
+  DevBuf d_src, d_src2, d_q, d_raw, d_mag;
+  auto cleanup = [&]() { d_src.release(); d_src2.release(); d_q.release(); d_raw.release(); d_mag.release(); };
+  std::vector<u8> hq(n0), hmask, hmask_next;
+  std::vector<float> hmag(n0);
+  for (int m = 0; m < M; ++m) {
+    const lmb200_modality& mod = h->cfg.modalities[m];
+    const lmb200_image& im = sources[m];
+    int r = rows, c = cols;
+    int num_features = mod.num_features, extract_threshold = mod.extract_threshold;
+    hmask = mask0;
+    if (mod.type == LMB200_COLOR_GRADIENT) {
+      ALLOC(d_src, n0 * 3); ALLOC(d_src2, n0 * 3); ALLOC(d_q, n0); ALLOC(d_mag, n0 * sizeof(float));
+      size_t rowb = (size_t)cols * 3, step = im.step ? im.step : rowb;
+      CU(cudaMemcpy2DAsync(d_src.p, rowb, im.data, step, rowb, rows, cudaMemcpyHostToDevice, st));
+      u8* cur = d_src.as<u8>();
+      u8* nxt = d_src2.as<u8>();
+      for (int l = 0; l < L; ++l) {
+        if (l > 0) {
+          launch_pyrdown_bgr(cur, 0, nxt, 0, r, c, 1, st);
+          std::swap(cur, nxt);
+          num_features /= 2;
+          int nr = r / 2, nc = c / 2;
+          if (!hmask.empty()) { hmask_next.resize((size_t)nr * nc); resize_nn_host(hmask.data(), r, c, hmask_next.data(), nr, nc); hmask.swap(hmask_next); }
+          r = nr; c = nc;
+        }
+        launch_cg_quantize(cur, 0, d_q.as<u8>(), 0, d_mag.as<float>(), 0, r, c, mod.weak_threshold * mod.weak_threshold, 1, st);
+        CU(cudaMemcpyAsync(hq.data(), d_q.p, (size_t)r * c, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hmag.data(), d_mag.p, (size_t)r * c * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!extract_color_gradient(hq.data(), hmag.data(), hmask.empty() ? nullptr : hmask.data(), r, c, num_features,
+                                    mod.strong_threshold, l, tp[(size_t)l * M + m])) { cleanup(); return LMB200_OK; }
+      }
+    } else {
+      ALLOC(d_src, n0 * 2); ALLOC(d_q, n0); ALLOC(d_raw, n0);
+      size_t rowb = (size_t)cols * 2, step = im.step ? im.step : rowb;
+      CU(cudaMemcpy2DAsync(d_src.p, rowb, im.data, step, rowb, rows, cudaMemcpyHostToDevice, st));
+      launch_dn_quantize(d_src.as<u16>(), 0, d_raw.as<u8>(), 0, nullptr, rows, cols, mod.distance_threshold,
+                         mod.difference_threshold, h->d_normal_lut.as<u8>(), 1, st);
+      launch_median5(d_raw.as<u8>(), 0, d_q.as<u8>(), 0, rows, cols, 1, st);
+      CU(cudaMemcpyAsync(hq.data(), d_q.p, n0, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      std::vector<u8> cur(hq.begin(), hq.begin() + n0), nxt;
+      for (int l = 0; l < L; ++l) {
+        if (l > 0) {
+          num_features /= 2; extract_threshold /= 2;
+          int nr = r / 2, nc = c / 2;
+          nxt.resize((size_t)nr * nc);
+          resize_nn_host(cur.data(), r, c, nxt.data(), nr, nc);
+          cur.swap(nxt);
+          if (!hmask.empty()) { hmask_next.resize((size_t)nr * nc); resize_nn_host(hmask.data(), r, c, hmask_next.data(), nr, nc); hmask.swap(hmask_next); }
+          r = nr; c = nc;
+        }
+        if (!extract_depth_normal(cur.data(), hmask.empty() ? nullptr : hmask.data(), r, c, num_features, extract_threshold, l,
+                                  tp[(size_t)l * M + m])) { cleanup(); return LMB200_OK; }
+      }
+    }
+  }
+  cleanup();
+  int bb[4];
+  crop_templates(tp, bb);
+  if (bb4) std::memcpy(bb4, bb, sizeof(bb));
+  *template_id = (int)tps.size();
+  tps.push_back(tp);
+  return LMB200_OK;
+}
+
+}  // namespace lmh
+
+// ---------------------------------------------------------------- template-sharded multi-GPU fetch
+extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, int count, lmb200_match_rec* out,
+                                                size_t cap, size_t* offsets) {
+  if (!h || !h->device_ready) return set_error(h, LMB200_E_INVALID, "nothing to fetch");
+  if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
+  if (!h->nccl_comm) return set_error(h, LMB200_E_COMM, "communicator not initialised (lmb200_comm_init)");
+  cudaSetDevice(h->device);
+  cudaStream_t st = h->lanes[0].stream;
+  const int world = h->comm_world;
+  // 1. local overflow check (a rank that overflowed redoes its own template side; no collective involved)
+  for (;;) {
+    CU(cudaMemcpyAsync(h->h_overflow + first_slot, h->d_overflow.as<int>() + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_out_count + first_slot, h->d_out_count.as<int>() + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_stats + first_slot, h->d_stats.as<unsigned long long>() + first_slot, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    bool over = false;
+    for (int i = 0; i < count; ++i) over |= h->h_overflow[first_slot + i] != 0 || h->h_out_count[first_slot + i] > h->out_cap;
+    if (!over) break;
+    float thr = h->slot_threshold[first_slot];
+    int rc = grow_capacity(h);
+    if (rc) return rc;
+    rc = run_matching(h, first_slot, count, thr, st);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < count; ++i) h->prof.bytes_local += (long long)h->h_stats[first_slot + i];
+  // 2. fixed-capacity send buffer per frame: record 0 = {count,..}, then up to gather_cap records.
+  //    Every rank sees every count after the gather, so all ranks take the same grow decision.
+  if (h->gather_cap <= 0) h->gather_cap = 2048;
+  for (;;) {
+    const size_t pitch = (size_t)(1 + h->gather_cap) * sizeof(Cand);
+    const size_t bytes = pitch * count;
+    ALLOC(h->d_gather_send, bytes);
+    ALLOC(h->d_gather_recv, bytes * world);
+    if (h->h_gather) { cudaFreeHost(h->h_gather); h->h_gather = nullptr; }
+    CU(cudaHostAlloc((void**)&h->h_gather, bytes * world, cudaHostAllocDefault));
+    CU(cudaMemsetAsync(h->d_gather_send.p, 0, bytes, st));
+    CU(cudaMemcpy2DAsync(h->d_gather_send.p, pitch, h->d_out_count.as<int>() + first_slot, sizeof(int), sizeof(int), count,
+                         cudaMemcpyDeviceToDevice, st));
+    size_t w = (size_t)std::min(h->gather_cap, h->out_cap) * sizeof(Cand);
+    CU(cudaMemcpy2DAsync((char*)h->d_gather_send.p + sizeof(Cand), pitch, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap,
+                         (size_t)h->out_cap * sizeof(Cand), w, count, cudaMemcpyDeviceToDevice, st));
+    int rc = comm_allgather(h, h->d_gather_send.p, h->d_gather_recv.p, bytes, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_gather, h->d_gather_recv.p, bytes * world, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int maxc = 0;
+    for (int r = 0; r < world; ++r)
+      for (int i = 0; i < count; ++i) maxc = std::max(maxc, h->h_gather[((size_t)r * count + i) * (1 + h->gather_cap)].tsel);
+    if (maxc <= h->gather_cap) break;
+    while (h->gather_cap < maxc) h->gather_cap *= 2;
+  }
+  if (h->profiling) collect_profile(h);
+  // 3. rank-ordered concatenation == reference generation order; same epilogue as the 1-GPU path
+  size_t base = 0;
+  int status = LMB200_OK;
+  std::vector<Cand> all;
+  std::vector<Match> m;
+  for (int i = 0; i < count; ++i) {
+    all.clear();
+    for (int r = 0; r < world; ++r) {
+      const Cand* rec = h->h_gather + ((size_t)r * count + i) * (1 + h->gather_cap);
+      all.insert(all.end(), rec + 1, rec + 1 + rec[0].tsel);
+    }
+    to_matches(h, all, m);
+    h->prof.candidates += (long long)all.size();
+    finalize_matches(m);
+    h->prof.matches += (long long)m.size();
+    size_t n = 0;
+    if (offsets) offsets[i] = base;
+    if (emit(h, m, out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
+    base += n;
+  }
+  if (offsets) offsets[count] = base;
+  return status;
+}

@@ -1,0 +1,151 @@
+// detector.h — host-side state of one lmb200 handle (internal; the public surface is include/lmb200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lmb200.h"
+#include "kernels.cuh"
+
+namespace lmh {
+
+struct Feature { int x, y, label; };
+struct Template {
+  int width = 0, height = 0, pyramid_level = 0;
+  std::vector<Feature> features;
+};
+typedef std::vector<Template> TemplatePyramid;  // index = level * num_modalities + modality
+
+struct Match {  // cv::linemod::Match with class_id as index into the sorted class list
+  int x, y;
+  float similarity;
+  int class_index;
+  int template_id;
+  bool operator<(const Match& r) const {
+    if (similarity != r.similarity) return similarity > r.similarity;
+    return template_id < r.template_id;
+  }
+  bool operator==(const Match& r) const {
+    return x == r.x && y == r.y && similarity == r.similarity && class_index == r.class_index;
+  }
+};
+
+// sort + unique, exactly upstream's epilogue of Detector::match
+void finalize_matches(std::vector<Match>& m);
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n);  // returns cudaError
+  void release();
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct LevelBuffers {
+  lmk::LevelGeom g;
+  size_t q_stride = 0, lm_stride = 0, bgr_stride = 0;
+  DevBuf bgr[LMB200_MAX_MODALITIES];   // CG source at this level (level 0 = uploaded frame)
+  DevBuf q[LMB200_MAX_MODALITIES];     // quantized map
+  DevBuf mask[LMB200_MAX_MODALITIES];  // optional mask pyramid
+  DevBuf lm[LMB200_MAX_MODALITIES];    // linear memories [slots][8*rows*cols + pad]
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+
+struct ProfRec { int family; cudaEvent_t a, b; };
+
+}  // namespace lmh
+
+struct lmb200_detector {
+  lmb200_config cfg;
+  std::string err;
+  uint8_t sim_lut[256];
+  uint8_t normal_lut[8000];
+
+  // ---- template store (host truth) ----
+  std::map<std::string, std::vector<lmh::TemplatePyramid>> classes;
+  bool templates_dirty = true;  // device tables stale
+  bool plan_dirty = true;       // offsets stale
+
+  // ---- device ----
+  bool device_ready = false;
+  int device = -1;
+  lmh::Lane lanes[2];
+  lmh::DevBuf d_table, d_normal_lut;
+  bool luts_dirty = true;
+
+  // template tables (per level)
+  int ntpl = 0;
+  std::vector<int> g_class, g_tid;                 // global template index -> (class index, template id)
+  std::vector<std::string> class_list;             // sorted class ids (index = class_index)
+  lmh::DevBuf d_hdr[LMB200_MAX_LEVELS], d_feat[LMB200_MAX_LEVELS], d_offs[LMB200_MAX_LEVELS];
+  std::vector<double> tpl_cost;                    // coarse bytes per template for the current plan
+
+  // selection
+  std::string sel_key;
+  std::vector<int> h_sel;                          // global indices scored by this handle (after sharding)
+  lmh::DevBuf d_sel;
+  long long sel_bytes_coarse = 0;
+  int shard_rank = 0, shard_world = 1;
+
+  // frame plan
+  int rows = 0, cols = 0, slots = 0;
+  int cand_cap = 0, out_cap = 0;
+  bool masks_in_use = false;
+  std::vector<lmh::LevelBuffers> levels;
+  lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
+  size_t depth_stride = 0;
+  lmh::DevBuf d_cand, d_cand_count, d_tpl_start, d_tpl_cnt, d_overflow, d_stats, d_out, d_out_count;
+  int nsel_stride = 0;
+  // pinned host mirrors
+  int* h_out_count = nullptr; int* h_overflow = nullptr; unsigned long long* h_stats = nullptr;
+  lmk::Cand* h_out = nullptr; int h_head = 0;      // first h_head records of every slot
+  void* h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for pageable/strided inputs
+  std::vector<float> slot_threshold;
+
+  // profiling
+  bool profiling = false;
+  std::vector<lmh::ProfRec> prof_pending;
+  std::vector<cudaEvent_t> event_pool;
+  lmb200_profile prof;
+  cudaEvent_t timer[2] = {nullptr, nullptr};
+
+  // comm
+  void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+  lmh::DevBuf d_gather_send, d_gather_recv; int gather_cap = 0;
+  lmk::Cand* h_gather = nullptr;
+
+  // scratch for lmb200_get_template
+  std::vector<lmb200_feature> tmp_features;
+};
+
+namespace lmh {
+// detector.cu
+int ensure_device(lmb200_detector* h);
+int set_error(lmb200_detector* h, int code, const std::string& msg);
+int cuda_fail(lmb200_detector* h, cudaError_t e, const char* what);
+// extract.cpp (host feature selection; images are level-sized row-major arrays)
+bool extract_color_gradient(const uint8_t* quant, const float* magnitude, const uint8_t* mask /*nullable*/,
+                            int rows, int cols, int num_features, float strong_threshold, int level, Template& out);
+bool extract_depth_normal(const uint8_t* quant, const uint8_t* mask /*nullable*/, int rows, int cols,
+                          int num_features, int extract_threshold, int level, Template& out);
+void crop_templates(TemplatePyramid& tp, int bb[4]);
+void resize_nn_host(const uint8_t* src, int rows, int cols, uint8_t* dst, int drows, int dcols);
+// persistence.cpp
+int write_detector_file(lmb200_detector* h, const char* path);
+int read_detector_file(const char* path, int device, lmb200_handle* out, std::string& err);
+int write_class_file(lmb200_detector* h, const std::string& class_id, const char* path);
+int read_class_file(lmb200_detector* h, const char* path, std::string& err);
+// comm.cpp
+int comm_unique_id(uint8_t* id128, std::string& err);
+int comm_init(lmb200_detector* h, const uint8_t* id128, int rank, int world);
+int comm_destroy(lmb200_detector* h);
+int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st);
+void default_normal_lut(uint8_t* out8000);
+void default_similarity_lut(uint8_t* out256);
+}  // namespace lmh

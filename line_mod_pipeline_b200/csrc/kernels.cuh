@@ -1,0 +1,118 @@
+// kernels.cuh — device data layout and kernel launch interface (sm_100a).
+// One launcher per upstream function group: every launcher takes a frame
+// count and per-frame strides so a whole batch is one launch (grid.z / grid.y = frame).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lmk {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+
+constexpr int MAX_MOD = 4;
+constexpr int FEAT_SLOTS = 64;        // per modality per template (upstream asserts <= 63 features)
+constexpr u32 OFF_INVALID = 0xFFFFFFFFu;
+constexpr int LM_PAD = 256;           // zero slack after each linear-memory block (realigned 16 B loads overrun)
+
+// Packed feature: x[0:14) y[14:28) label[28:31) valid[31].  Invalid = coordinate negative / > 16383
+// (upstream skips features outside the image; negative ones can never be inside).
+__host__ __device__ inline u32 pack_feature(int x, int y, int label) {
+  if (x < 0 || y < 0 || x > 16383 || y > 16383) return 0u;
+  return (u32)x | ((u32)y << 14) | ((u32)(label & 7) << 28) | 0x80000000u;
+}
+
+// Per (level, template) header.  width/height are per modality (cropTemplates makes them equal,
+// synthetic templates may differ; upstream's refinement clamp uses modality 0).
+struct alignas(8) TplHdr {
+  short width[MAX_MOD];
+  short height[MAX_MOD];
+  u8 nf[MAX_MOD];
+  u32 flags;                          // bit0: local-safe, bit1: coarse-safe (set by the plan kernel)
+};
+
+// Register-resident view of a TplHdr (dynamic modality index without local memory).
+struct HdrR {
+  unsigned long long w, h;
+  u32 nfs, flags;
+  __device__ __forceinline__ int width(int m) const { return (int)(short)(w >> (16 * m)); }
+  __device__ __forceinline__ int height(int m) const { return (int)(short)(h >> (16 * m)); }
+  __device__ __forceinline__ int nf(int m) const { return (int)((nfs >> (8 * m)) & 0xFFu); }
+  __device__ __forceinline__ int nf_total() const {
+    return (int)((nfs & 0xFF) + ((nfs >> 8) & 0xFF) + ((nfs >> 16) & 0xFF) + (nfs >> 24));
+  }
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ HdrR load_hdr(const TplHdr* p) {
+  const unsigned long long* q = reinterpret_cast<const unsigned long long*>(p);
+  HdrR r;
+  r.w = __ldg(q); r.h = __ldg(q + 1);
+  unsigned long long t = __ldg(q + 2);
+  r.nfs = (u32)t; r.flags = (u32)(t >> 32);
+  return r;
+}
+#endif
+
+// Candidate / match record kept on the device (16 B).  tsel = index into the selection list.
+struct Cand {
+  int tsel;
+  int x, y;
+  float sim;                          // < 0 : filtered out
+};
+
+struct LevelGeom {
+  int T, rows, cols, W, H;            // quantized image size; W=cols/T, H=rows/T
+  u32 per_label;                      // T*T*W*H
+};
+
+// ------------------------------------------------------------------ frame side
+void launch_pyrdown_bgr(const u8* src, size_t src_stride, u8* dst, size_t dst_stride,
+                        int rows, int cols, int frames, cudaStream_t st);
+void launch_cg_quantize(const u8* bgr, size_t bgr_stride, u8* q, size_t q_stride,
+                        float* mag, size_t mag_stride /*elements; mag nullable*/,
+                        int rows, int cols, float weak_sq, int frames, cudaStream_t st);
+void launch_dn_quantize(const u16* depth, size_t depth_stride /*elements*/, u8* out, size_t out_stride,
+                        int8_t* idx_out /*nullable [frames][3][rows*cols]*/,
+                        int rows, int cols, int dist_thr, int diff_thr, const u8* lut_dev,
+                        int frames, cudaStream_t st);
+void launch_median5(const u8* src, size_t src_stride, u8* dst, size_t dst_stride, int rows, int cols,
+                    int frames, cudaStream_t st);
+void launch_resize_nn(const u8* src, size_t src_stride, int rows, int cols,
+                      u8* dst, size_t dst_stride, int drows, int dcols, int frames, cudaStream_t st);
+// spread (T x T OR) + response LUT + linearize, fused.  table: 256 x uint2 (8 orientation bytes per
+// spread byte).  lm: per frame [8][T*T*W*H] (+LM_PAD).  mask nullable (quantize() through mask).
+void launch_spread_linearize(const u8* q, size_t q_stride, const u8* mask, size_t mask_stride,
+                             u8* lm, size_t lm_stride, LevelGeom g, const uint2* table,
+                             int frames, cudaStream_t st);
+
+// ------------------------------------------------------------------ template side
+// Plan: flat linear-memory offsets of every feature for one level's geometry + safe flags.
+void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g,
+                          cudaStream_t st);
+
+struct MatchParams {
+  int M, nsel, frames;
+  const int* sel;                     // selection list: global template indices, generation order
+  float threshold;
+  // candidate store, per frame
+  Cand* cand; int cand_cap;
+  int* cand_count;                    // [frames]
+  int* tpl_start; int* tpl_cnt;       // [frames][nsel_stride]
+  int nsel_stride;
+  int* overflow;                      // [frames]
+  unsigned long long* stats;          // [frames]: algorithmic bytes gathered by similarityLocal (nullable)
+};
+
+struct LevelParams {
+  LevelGeom g;
+  const u8* lm[MAX_MOD]; size_t lm_stride[MAX_MOD];   // this level's linear memories per modality
+  const TplHdr* hdr; const u32* offs; const u32* feat; // this level's template tables
+};
+
+void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
+void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
+// Ordered compaction: out[frame][0..n) in generation order, count[frame] = n (may exceed cap -> overflow).
+void launch_pack(const MatchParams& mp, Cand* out, int out_cap, int* out_count, cudaStream_t st);
+
+}  // namespace lmk

@@ -1,0 +1,454 @@
+// kernels_frame.cu — frame-side kernels (sm_100a): everything `Detector::match` does per frame
+// before template scoring.  Each kernel restates one upstream function group bit-exactly
+// (opencv_contrib rgbd/linemod.cpp):
+//   pyrdown_bgr_kernel        ColorGradientPyramid::pyrDown -> cv::pyrDown            (a4)
+//   cg_quantize_kernel        quantizedOrientations + hysteresisGradient, fused       (a2,a3)
+//   dn_quantize_kernel        quantizedNormals body                                   (a6)
+//   median5_kernel            medianBlur(5) on one-hot bytes                          (a6)
+//   resize_nn_kernel          DepthNormalPyramid::pyrDown / mask pyramids             (a7)
+//   spread_linearize_kernel   spread + computeResponseMaps + linearize, fused         (a8-a10)
+// All are HBM-bound byte kernels: no tensor cores.  Compiled with -fmad=false; float ops that must
+// match the CPU bit for bit use explicit round-to-nearest intrinsics.
+#include "kernels.cuh"
+
+namespace lmk {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv::pyrDown 5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum+128)>>8, dst = (rows/2, cols/2)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyrdown_bgr_kernel(const u8* __restrict__ src, size_t src_stride,
+                                                          u8* __restrict__ dst, size_t dst_stride,
+                                                          int rows, int cols, int drows, int dcols) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= dcols || y >= drows) return;
+  const u8* s = src + (size_t)blockIdx.z * src_stride;
+  const int w[5] = {1, 4, 6, 4, 1};
+  int xs[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) xs[j] = reflect101(2 * x + j - 2, cols) * 3;
+  int acc0 = 0, acc1 = 0, acc2 = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const u8* row = s + (size_t)reflect101(2 * y + i - 2, rows) * cols * 3;
+    int r0 = 0, r1 = 0, r2 = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      r0 += w[j] * row[xs[j]];
+      r1 += w[j] * row[xs[j] + 1];
+      r2 += w[j] * row[xs[j] + 2];
+    }
+    acc0 += w[i] * r0; acc1 += w[i] * r1; acc2 += w[i] * r2;
+  }
+  u8* d = dst + (size_t)blockIdx.z * dst_stride + ((size_t)y * dcols + x) * 3;
+  d[0] = (u8)((acc0 + 128) >> 8);
+  d[1] = (u8)((acc1 + 128) >> 8);
+  d[2] = (u8)((acc2 + 128) >> 8);
+}
+
+void launch_pyrdown_bgr(const u8* src, size_t src_stride, u8* dst, size_t dst_stride, int rows, int cols,
+                        int frames, cudaStream_t st) {
+  int drows = rows / 2, dcols = cols / 2;
+  dim3 grid((dcols + 31) / 32, (drows + 7) / 8, frames), block(32, 8);
+  pyrdown_bgr_kernel<<<grid, block, 0, st>>>(src, src_stride, dst, dst_stride, rows, cols, drows, dcols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ColorGradient quantisation, one fused pass per pyramid level.
+//   Gaussian 7x7 fixed point ([8,28,56,72,56,28,8], single (sum+2^15)>>16 rounding, replicate)
+//   -> Sobel 3x3 on the blurred image (replicate border ON THE BLURRED IMAGE)
+//   -> channel with max dx^2+dy^2 (ties: B, then G) -> fastAtan2 degrees -> *16/360 round-half-even
+//   -> border zero, &7 -> 3x3 vote (>=5 of 9, first max), magnitude > weak^2 (strict).
+// Tile 64x16 output pixels, 256 threads, halo 5 (3 blur + 1 Sobel + 1 vote), planar smem staging.
+// ---------------------------------------------------------------------------------------------
+constexpr int CG_TW = 64, CG_TH = 16;
+constexpr int CG_SR = CG_TH + 10, CG_SC = CG_TW + 10, CG_SCP = CG_SC + 2;  // source tile (halo 5)
+constexpr int CG_HC = CG_TW + 4, CG_BR = CG_TH + 4;                        // blurred region R2 (halo 2)
+constexpr int CG_QR = CG_TH + 2, CG_QC = CG_TW + 2, CG_QCP = CG_QC + 2;    // orientation region R1 (halo 1)
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  // OpenCV hal::fastAtan32f, fused polynomial (bit-exact with the cv2 wheel)
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+  const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  float ax = fabsf(x), ay = fabsf(y);
+  float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float c = __fdiv_rn(mn, __fadd_rn(mx, (float)2.2204460492503131e-16));
+  float c2 = __fmul_rn(c, c);
+  float a = __fmaf_rn(p7, c2, p5);
+  a = __fmaf_rn(a, c2, p3);
+  a = __fmaf_rn(a, c2, p1);
+  a = __fmul_rn(a, c);
+  if (!(ax >= ay)) a = __fsub_rn(90.f, a);
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__ bgr, size_t bgr_stride,
+                                                          u8* __restrict__ qout, size_t q_stride,
+                                                          float* __restrict__ mag_out, size_t mag_stride,
+                                                          int rows, int cols, float weak_sq) {
+  __shared__ u8 s_src[3][CG_SR][CG_SCP];
+  __shared__ u16 s_h[3][CG_SR][CG_HC];
+  __shared__ u8 s_b[3][CG_BR][CG_HC];
+  __shared__ u8 s_q[CG_QR][CG_QCP];
+  __shared__ int s_m[CG_QR][CG_QCP];
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * CG_TW, y0 = blockIdx.y * CG_TH;
+  const u8* src = bgr + (size_t)blockIdx.z * bgr_stride;
+
+  // 1. source tile, replicate-clamped (the blur's border mode acts on the source)
+  for (int idx = tid; idx < CG_SR * CG_SC; idx += 256) {
+    int ty = idx / CG_SC, tx = idx - ty * CG_SC;
+    int gy = clampi(y0 - 5 + ty, 0, rows - 1), gx = clampi(x0 - 5 + tx, 0, cols - 1);
+    const u8* p = src + ((size_t)gy * cols + gx) * 3;
+    s_src[0][ty][tx] = p[0]; s_src[1][ty][tx] = p[1]; s_src[2][ty][tx] = p[2];
+  }
+  __syncthreads();
+
+  // 2. horizontal blur sums at the CLAMPED centre column (so out-of-image R2 columns replicate the
+  //    blurred border column, which is what Sobel's BORDER_REPLICATE sees)
+  for (int idx = tid; idx < CG_SR * CG_HC; idx += 256) {
+    int ty = idx / CG_HC, tx2 = idx - ty * CG_HC;
+    int cx = clampi(x0 - 2 + tx2, 0, cols - 1);
+    int tc = cx - (x0 - 5);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const u8* r = &s_src[ch][ty][tc - 3];
+      int s = 8 * (r[0] + r[6]) + 28 * (r[1] + r[5]) + 56 * (r[2] + r[4]) + 72 * r[3];
+      s_h[ch][ty][tx2] = (u16)s;
+    }
+  }
+  __syncthreads();
+
+  // 3. vertical pass at the clamped centre row -> blurred u8 on R2
+  for (int idx = tid; idx < CG_BR * CG_HC; idx += 256) {
+    int ty2 = idx / CG_HC, tx2 = idx - ty2 * CG_HC;
+    int cy = clampi(y0 - 2 + ty2, 0, rows - 1);
+    int tr = cy - (y0 - 5);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      int s = 8 * ((int)s_h[ch][tr - 3][tx2] + s_h[ch][tr + 3][tx2]) + 28 * ((int)s_h[ch][tr - 2][tx2] + s_h[ch][tr + 2][tx2]) +
+              56 * ((int)s_h[ch][tr - 1][tx2] + s_h[ch][tr + 1][tx2]) + 72 * (int)s_h[ch][tr][tx2];
+      s_b[ch][ty2][tx2] = (u8)((s + 32768) >> 16);
+    }
+  }
+  __syncthreads();
+
+  // 4. Sobel + channel select + orientation code on R1
+  for (int idx = tid; idx < CG_QR * CG_QC; idx += 256) {
+    int ty1 = idx / CG_QC, tx1 = idx - ty1 * CG_QC;
+    int gy = y0 - 1 + ty1, gx = x0 - 1 + tx1;
+    u8 q = 0;
+    int mag = 0;
+    if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+      int by = ty1 + 1, bx = tx1 + 1;  // R2 index of this pixel
+      int best_dx = 0, best_dy = 0, best_m = -1;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        int a00 = s_b[ch][by - 1][bx - 1], a01 = s_b[ch][by - 1][bx], a02 = s_b[ch][by - 1][bx + 1];
+        int a10 = s_b[ch][by][bx - 1], a12 = s_b[ch][by][bx + 1];
+        int a20 = s_b[ch][by + 1][bx - 1], a21 = s_b[ch][by + 1][bx], a22 = s_b[ch][by + 1][bx + 1];
+        int dx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
+        int dy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
+        int m = dx * dx + dy * dy;
+        if (m > best_m) { best_m = m; best_dx = dx; best_dy = dy; }  // strict >: earlier channel wins ties (B, G, R)
+      }
+      mag = best_m;
+      if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1) {
+        float ang = fast_atan2_deg((float)best_dy, (float)best_dx);
+        int r = __float2int_rn(__fmul_rn(ang, (float)(16.0 / 360.0)));
+        r = r < 0 ? 0 : (r > 255 ? 255 : r);
+        q = (u8)(r & 7);
+      }
+    }
+    s_q[ty1][tx1] = q;
+    s_m[ty1][tx1] = mag;
+  }
+  __syncthreads();
+
+  // 5. 3x3 vote
+  u8* qo = qout + (size_t)blockIdx.z * q_stride;
+  for (int idx = tid; idx < CG_TH * CG_TW; idx += 256) {
+    int ty = idx / CG_TW, tx = idx - ty * CG_TW;
+    int gy = y0 + ty, gx = x0 + tx;
+    if (gy >= rows || gx >= cols) continue;
+    int mag = s_m[ty + 1][tx + 1];
+    u8 out = 0;
+    if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1 && (float)mag > weak_sq) {
+      u32 hist = 0;  // 8 x 4-bit counters
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) hist += 1u << (4 * s_q[ty + i][tx + j]);
+      int max_votes = 0, index = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        int v = (hist >> (4 * b)) & 15;
+        if (max_votes < v) { max_votes = v; index = b; }
+      }
+      if (max_votes >= 5) out = (u8)(1u << index);
+    }
+    qo[(size_t)gy * cols + gx] = out;
+    if (mag_out) mag_out[(size_t)blockIdx.z * mag_stride + (size_t)gy * cols + gx] = (float)mag;
+  }
+}
+
+void launch_cg_quantize(const u8* bgr, size_t bgr_stride, u8* q, size_t q_stride, float* mag, size_t mag_stride,
+                        int rows, int cols, float weak_sq, int frames, cudaStream_t st) {
+  dim3 grid((cols + CG_TW - 1) / CG_TW, (rows + CG_TH - 1) / CG_TH, frames);
+  cg_quantize_kernel<<<grid, 256, 0, st>>>(bgr, bgr_stride, q, q_stride, mag, mag_stride, rows, cols, weak_sq);
+}
+
+// ---------------------------------------------------------------------------------------------
+// DepthNormal: quantizedNormals body.  64-bit integer accumulators like upstream's `long`;
+// float normalisation with explicit rn intrinsics (no FMA); C truncation; LUT indices clamped
+// to 19 (upstream reads out of bounds there — N4).  Writes every pixel (0 on border/failure).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dn_quantize_kernel(const u16* __restrict__ depth, size_t depth_stride,
+                                                          u8* __restrict__ out, size_t out_stride,
+                                                          int8_t* __restrict__ idx_out, int rows, int cols,
+                                                          int dist_thr, int diff_thr, const u8* __restrict__ lut) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  const u16* d = depth + (size_t)blockIdx.z * depth_stride;
+  const size_t n = (size_t)rows * cols, pix = (size_t)y * cols + x;
+  u8 res = 0;
+  int v1 = -1, v2 = -1, v3 = -1;
+  const int r = 5;
+  if (y >= r && y < rows - r - 1 && x >= r && x < cols - r - 1) {
+    long long dc = d[pix];
+    if (dc < dist_thr) {
+      long long A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
+      const int oi[8] = {-5, 0, 5, -5, 5, -5, 0, 5};
+      const int oj[8] = {-5, -5, -5, 0, 0, 5, 5, 5};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        long long i = oi[k], j = oj[k];
+        long long delta = (long long)d[(size_t)(y + oj[k]) * cols + (x + oi[k])] - dc;
+        long long f = (delta < 0 ? -delta : delta) < diff_thr ? 1 : 0;
+        long long fi = f * i, fj = f * j;
+        A0 += fi * i; A1 += fi * j; A3 += fj * j;
+        b0 += fi * delta; b1 += fj * delta;
+      }
+      long long det = A0 * A3 - A1 * A1;
+      long long ddx = A3 * b0 - A1 * b1;
+      long long ddy = -A1 * b0 + A0 * b1;
+      float nx = (float)(1150 * ddx), ny = (float)(1150 * ddy), nz = (float)(-det * dc);
+      float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+      if (s > 0) {
+        float inv = __fdiv_rn(1.0f, s);
+        nx = __fmul_rn(nx, inv); ny = __fmul_rn(ny, inv); nz = __fmul_rn(nz, inv);
+        v1 = (int)__fadd_rn(__fmul_rn(nx, 10.f), 10.f);
+        v2 = (int)__fadd_rn(__fmul_rn(ny, 10.f), 10.f);
+        v3 = (int)__fadd_rn(__fmul_rn(nz, 20.f), 20.f);
+        v1 = clampi(v1, 0, 19); v2 = clampi(v2, 0, 19); v3 = clampi(v3, 0, 19);
+        res = lut[(v3 * 20 + v2) * 20 + v1];
+      }
+    }
+  }
+  out[(size_t)blockIdx.z * out_stride + pix] = res;
+  if (idx_out) {
+    int8_t* io = idx_out + (size_t)blockIdx.z * 3 * n;
+    io[pix] = (int8_t)v1; io[n + pix] = (int8_t)v2; io[2 * n + pix] = (int8_t)v3;
+  }
+}
+
+void launch_dn_quantize(const u16* depth, size_t depth_stride, u8* out, size_t out_stride, int8_t* idx_out,
+                        int rows, int cols, int dist_thr, int diff_thr, const u8* lut_dev, int frames,
+                        cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 7) / 8, frames), block(32, 8);
+  dn_quantize_kernel<<<grid, block, 0, st>>>(depth, depth_stride, out, out_stride, idx_out, rows, cols, dist_thr,
+                                             diff_thr, lut_dev);
+}
+
+// ---------------------------------------------------------------------------------------------
+// medianBlur(5), replicate border, on bytes that are 0 or one-hot: the sorted order is
+// 0 < 1 < 2 < 4 < ... < 128, so the 13th of 25 falls out of nine 5-bit counters.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) median5_kernel(const u8* __restrict__ src, size_t src_stride,
+                                                      u8* __restrict__ dst, size_t dst_stride, int rows, int cols) {
+  __shared__ u8 tile[8 + 4][32 + 4 + 4];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const u8* s = src + (size_t)blockIdx.z * src_stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int idx = tid; idx < 12 * 36; idx += 256) {
+    int ty = idx / 36, tx = idx - ty * 36;
+    tile[ty][tx] = s[(size_t)clampi(y0 - 2 + ty, 0, rows - 1) * cols + clampi(x0 - 2 + tx, 0, cols - 1)];
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  unsigned long long cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) cnt += 1ull << (5 * __ffs((int)tile[threadIdx.y + i][threadIdx.x + j]));
+  int acc = 0, k = 0;
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    int c = (int)((cnt >> (5 * b)) & 31);
+    if (acc < 13) k = b;
+    acc += c;
+  }
+  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * cols + x] = k ? (u8)(1u << (k - 1)) : (u8)0;
+}
+
+void launch_median5(const u8* src, size_t src_stride, u8* dst, size_t dst_stride, int rows, int cols, int frames,
+                    cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 7) / 8, frames), block(32, 8);
+  median5_kernel<<<grid, block, 0, st>>>(src, src_stride, dst, dst_stride, rows, cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv::resize(INTER_NEAREST): sx = min(floor(x * (1/(dcols/cols))), cols-1)  (double, like OpenCV)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_nn_kernel(const u8* __restrict__ src, size_t src_stride, int rows, int cols,
+                                                        u8* __restrict__ dst, size_t dst_stride, int drows, int dcols,
+                                                        double ifx, double ify) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= dcols || y >= drows) return;
+  int sx = min((int)floor(x * ifx), cols - 1), sy = min((int)floor(y * ify), rows - 1);
+  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dcols + x] = src[(size_t)blockIdx.z * src_stride + (size_t)sy * cols + sx];
+}
+
+void launch_resize_nn(const u8* src, size_t src_stride, int rows, int cols, u8* dst, size_t dst_stride, int drows,
+                      int dcols, int frames, cudaStream_t st) {
+  dim3 grid((dcols + 31) / 32, (drows + 7) / 8, frames), block(32, 8);
+  double ifx = 1.0 / ((double)dcols / cols), ify = 1.0 / ((double)drows / rows);
+  resize_nn_kernel<<<grid, block, 0, st>>>(src, src_stride, rows, cols, dst, dst_stride, drows, dcols, ifx, ify);
+}
+
+// ---------------------------------------------------------------------------------------------
+// spread + response maps + linearize, fused.  One CTA = one decimated row i (image rows
+// [iT, iT+2T-1)) x SL_CW decimated columns.  The band is staged in shared memory with its
+// (T-1) right/bottom halo (zero outside the image: OR identity), OR-reduced vertically then
+// horizontally, looked up in a 256 x 8-byte table (all 8 orientations of one spread byte at once)
+// and written straight into the T-strided linear memories:
+//     LM[ori][ (y%T*T + x%T) * W*H + (y/T)*W + x/T ]
+// Each thread produces 4 consecutive decimated positions of one grid cell for all 8 orientations,
+// i.e. eight 32-bit stores; a warp writes contiguous 128 B runs per (ori, grid cell).
+// ---------------------------------------------------------------------------------------------
+constexpr int SL_CW = 64;
+
+__global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restrict__ q, size_t q_stride,
+                                                               const u8* __restrict__ mask, size_t mask_stride,
+                                                               u8* __restrict__ lm, size_t lm_stride, LevelGeom g,
+                                                               const uint2* __restrict__ table) {
+  extern __shared__ __align__(16) u8 sl_smem[];
+  const int T = g.T, W = g.W;
+  const int i = blockIdx.x;            // decimated row
+  const int c0 = blockIdx.y * SL_CW;   // first decimated column of this chunk
+  const int cw = min(SL_CW, W - c0);
+  const int pw = cw * T;               // pixel columns produced
+  const int lw = pw + T - 1;           // pixel columns loaded
+  const int lwp = (lw + 3) & ~3;
+  const int nr = 2 * T - 1;
+  u8* qb = sl_smem;                                      // [nr][lwp]   raw band, later horizontal result [T][lwp]
+  u8* vb = qb + (size_t)nr * lwp;                        // [T][lwp]    vertical OR
+  uint2* tab = (uint2*)(sl_smem + (((size_t)(nr + T) * lwp + 15) & ~(size_t)15));
+  const int tid = threadIdx.x;
+  const u8* qf = q + (size_t)blockIdx.z * q_stride;
+  const u8* mf = mask ? mask + (size_t)blockIdx.z * mask_stride : nullptr;
+
+  tab[tid] = table[tid];  // 256 threads, 256 entries
+  const int y0 = i * T, x0 = c0 * T;
+  for (int idx = tid; idx < nr * lw; idx += 256) {
+    int r = idx / lw, x = idx - r * lw;
+    int gy = y0 + r, gx = x0 + x;
+    u8 v = 0;
+    if (gy < g.rows && gx < g.cols) {
+      v = qf[(size_t)gy * g.cols + gx];
+      if (mf && !mf[(size_t)gy * g.cols + gx]) v = 0;
+    }
+    qb[r * lwp + x] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < T * lw; idx += 256) {
+    int r = idx / lw, x = idx - r * lw;
+    u8 v = 0;
+    for (int k = 0; k < T; ++k) v |= qb[(r + k) * lwp + x];
+    vb[r * lwp + x] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < T * pw; idx += 256) {
+    int r = idx / pw, x = idx - r * pw;
+    u8 v = 0;
+    for (int k = 0; k < T; ++k) v |= vb[r * lwp + x + k];
+    qb[r * lwp + x] = v;  // qb rows [0,T) now hold the spread band
+  }
+  __syncthreads();
+
+  u8* lmf = lm + (size_t)blockIdx.z * lm_stride;
+  const u32 per = g.per_label;
+  const u32 plane = (u32)W * g.H;
+  const int quads = (cw + 3) >> 2;
+  const bool vec = ((W & 3) == 0);
+  for (int idx = tid; idx < T * T * quads; idx += 256) {
+    int cell = idx / quads, k = idx - cell * quads;
+    int gy = cell / T, gx = cell - gy * T;
+    u32 lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int p = 4 * k + j;
+      uint2 e = make_uint2(0u, 0u);
+      if (p < cw) e = tab[qb[gy * lwp + p * T + gx]];
+      lo[j] = e.x; hi[j] = e.y;
+    }
+    u32 dstoff = (u32)cell * plane + (u32)i * W + c0 + 4 * k;
+    if (vec && 4 * k + 3 < cw) {
+      // transpose 4 positions x 8 orientations -> one u32 (4 positions) per orientation
+      u32 t01 = __byte_perm(lo[0], lo[1], 0x5140), t23 = __byte_perm(lo[2], lo[3], 0x5140);  // ori0: b0,b0' ; ori1: b1,b1'
+      u32 u01 = __byte_perm(lo[0], lo[1], 0x7362), u23 = __byte_perm(lo[2], lo[3], 0x7362);  // ori2, ori3
+      *(u32*)(lmf + 0 * (size_t)per + dstoff) = __byte_perm(t01, t23, 0x5410);
+      *(u32*)(lmf + 1 * (size_t)per + dstoff) = __byte_perm(t01, t23, 0x7632);
+      *(u32*)(lmf + 2 * (size_t)per + dstoff) = __byte_perm(u01, u23, 0x5410);
+      *(u32*)(lmf + 3 * (size_t)per + dstoff) = __byte_perm(u01, u23, 0x7632);
+      t01 = __byte_perm(hi[0], hi[1], 0x5140); t23 = __byte_perm(hi[2], hi[3], 0x5140);
+      u01 = __byte_perm(hi[0], hi[1], 0x7362); u23 = __byte_perm(hi[2], hi[3], 0x7362);
+      *(u32*)(lmf + 4 * (size_t)per + dstoff) = __byte_perm(t01, t23, 0x5410);
+      *(u32*)(lmf + 5 * (size_t)per + dstoff) = __byte_perm(t01, t23, 0x7632);
+      *(u32*)(lmf + 6 * (size_t)per + dstoff) = __byte_perm(u01, u23, 0x5410);
+      *(u32*)(lmf + 7 * (size_t)per + dstoff) = __byte_perm(u01, u23, 0x7632);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (4 * k + j < cw) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            lmf[(size_t)o * per + dstoff + j] = (u8)(lo[j] >> (8 * o));
+            lmf[(size_t)(o + 4) * per + dstoff + j] = (u8)(hi[j] >> (8 * o));
+          }
+        }
+      }
+    }
+  }
+}
+
+static size_t sl_smem_bytes(int T, int cw) {
+  int lw = cw * T + T - 1, lwp = (lw + 3) & ~3;
+  size_t b = ((size_t)(3 * T - 1) * lwp + 15) & ~(size_t)15;
+  return b + 256 * sizeof(uint2);
+}
+
+void launch_spread_linearize(const u8* q, size_t q_stride, const u8* mask, size_t mask_stride, u8* lm,
+                             size_t lm_stride, LevelGeom g, const uint2* table, int frames, cudaStream_t st) {
+  static size_t configured = 0;
+  size_t smem = sl_smem_bytes(g.T, g.W < SL_CW ? g.W : SL_CW);
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(spread_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid(g.H, (g.W + SL_CW - 1) / SL_CW, frames);
+  spread_linearize_kernel<<<grid, 256, smem, st>>>(q, q_stride, mask, mask_stride, lm, lm_stride, g, table);
+}
+
+}  // namespace lmk

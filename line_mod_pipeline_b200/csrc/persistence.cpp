@@ -1,0 +1,380 @@
+// persistence.cpp — OpenCV FileStorage (YAML 1.0, optional gzip) read/write of the detector and its
+// template classes.  File layout = what the reference writes/reads in
+// HighLevelLineMOD::writeLinemod / readLinemod (src/HighLevelLinemod.cpp:256-270, :288-300):
+//   Detector::write at the root (pyramid_levels, T, modalities) + "classes": [ {writeClass}, ... ]
+// and what Detector::writeClasses/readClasses produce per class (SURVEY.md §8c "Template file layout",
+// verified loadable by real cv2.FileStorage in tests/test_persistence.py).
+// The reader is a streaming, schema-directed line parser: a 20 000-template file is ~4 M lines and
+// a DOM would cost gigabytes.
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "detector.h"
+
+namespace lmh {
+
+namespace {
+
+struct Writer {
+  gzFile gz = nullptr;
+  FILE* fp = nullptr;
+  std::string buf;
+  bool open(const char* path) {
+    size_t n = std::strlen(path);
+    if (n > 3 && std::strcmp(path + n - 3, ".gz") == 0) gz = gzopen(path, "wb6");
+    else fp = std::fopen(path, "wb");
+    return gz || fp;
+  }
+  void flush() {
+    if (buf.empty()) return;
+    if (gz) gzwrite(gz, buf.data(), (unsigned)buf.size());
+    else std::fwrite(buf.data(), 1, buf.size(), fp);
+    buf.clear();
+  }
+  void put(const std::string& s) {
+    buf += s;
+    if (buf.size() > (1u << 20)) flush();
+  }
+  void close() {
+    flush();
+    if (gz) gzclose(gz);
+    if (fp) std::fclose(fp);
+    gz = nullptr; fp = nullptr;
+  }
+};
+
+std::string fmt_float(float v) {  // OpenCV style: "10." for integral values, shortest round-trip otherwise
+  char b[64];
+  if (v == (float)(long long)v && std::fabs(v) < 1e15f) { std::snprintf(b, sizeof b, "%lld.", (long long)v); return b; }
+  std::snprintf(b, sizeof b, "%.8e", (double)v);
+  return b;
+}
+std::string quote(const std::string& s) {
+  std::string o = "\"";
+  for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); }
+  return o + "\"";
+}
+std::string ind(int n) { return std::string((size_t)n, ' '); }
+
+void write_header(Writer& w, const lmb200_detector* h) {
+  w.put("%YAML:1.0\n---\n");
+  w.put("pyramid_levels: " + std::to_string(h->cfg.pyramid_levels) + "\n");
+  std::string t = "T: [ ";
+  for (int l = 0; l < h->cfg.pyramid_levels; ++l) t += std::to_string(h->cfg.T[l]) + (l + 1 < h->cfg.pyramid_levels ? ", " : "");
+  w.put(t + " ]\n");
+  w.put("modalities:\n");
+  for (int m = 0; m < h->cfg.num_modalities; ++m) {
+    const lmb200_modality& mo = h->cfg.modalities[m];
+    w.put("   -\n");
+    if (mo.type == LMB200_COLOR_GRADIENT) {
+      w.put("      type: ColorGradient\n");
+      w.put("      weak_threshold: " + fmt_float(mo.weak_threshold) + "\n");
+      w.put("      num_features: " + std::to_string(mo.num_features) + "\n");
+      w.put("      strong_threshold: " + fmt_float(mo.strong_threshold) + "\n");
+    } else {
+      w.put("      type: DepthNormal\n");
+      w.put("      distance_threshold: " + std::to_string(mo.distance_threshold) + "\n");
+      w.put("      difference_threshold: " + std::to_string(mo.difference_threshold) + "\n");
+      w.put("      num_features: " + std::to_string(mo.num_features) + "\n");
+      w.put("      extract_threshold: " + std::to_string(mo.extract_threshold) + "\n");
+    }
+  }
+}
+
+const char* mod_name(int type) { return type == LMB200_COLOR_GRADIENT ? "ColorGradient" : "DepthNormal"; }
+
+// writeClass body at indentation `in`
+void write_class(Writer& w, const lmb200_detector* h, const std::string& id, const std::vector<TemplatePyramid>& tps, int in) {
+  w.put(ind(in) + "class_id: " + quote(id) + "\n");
+  std::string m = ind(in) + "modalities: [ ";
+  for (int i = 0; i < h->cfg.num_modalities; ++i) m += std::string(mod_name(h->cfg.modalities[i].type)) + (i + 1 < h->cfg.num_modalities ? ", " : "");
+  w.put(m + " ]\n");
+  w.put(ind(in) + "pyramid_levels: " + std::to_string(h->cfg.pyramid_levels) + "\n");
+  w.put(ind(in) + "template_pyramids:\n");
+  char line[96];
+  for (size_t t = 0; t < tps.size(); ++t) {
+    w.put(ind(in + 3) + "-\n");
+    w.put(ind(in + 6) + "template_id: " + std::to_string(t) + "\n");
+    w.put(ind(in + 6) + "templates:\n");
+    for (const Template& tp : tps[t]) {
+      w.put(ind(in + 9) + "-\n");
+      w.put(ind(in + 12) + "width: " + std::to_string(tp.width) + "\n");
+      w.put(ind(in + 12) + "height: " + std::to_string(tp.height) + "\n");
+      w.put(ind(in + 12) + "pyramid_level: " + std::to_string(tp.pyramid_level) + "\n");
+      w.put(ind(in + 12) + "features:\n");
+      std::string pre = ind(in + 15);
+      for (const Feature& f : tp.features) {
+        std::snprintf(line, sizeof line, "- [ %d, %d, %d ]\n", f.x, f.y, f.label);
+        w.put(pre + line);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ reader
+struct Reader {
+  gzFile gz = nullptr;
+  std::string line;
+  bool open(const char* path) { gz = gzopen(path, "rb"); if (gz) gzbuffer(gz, 1 << 18); return gz != nullptr; }
+  bool next(std::string& out) {
+    char buf[4096];
+    out.clear();
+    for (;;) {
+      if (!gzgets(gz, buf, sizeof buf)) return !out.empty();
+      out += buf;
+      if (!out.empty() && out.back() == '\n') { out.pop_back(); if (!out.empty() && out.back() == '\r') out.pop_back(); return true; }
+    }
+  }
+  void close() { if (gz) gzclose(gz); gz = nullptr; }
+};
+
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t"), b = s.find_last_not_of(" \t");
+  return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+std::string unquote(const std::string& s0) {
+  std::string s = trim(s0);
+  if (s.size() >= 2 && (s.front() == '"' || s.front() == '\'') && s.back() == s.front()) {
+    std::string o;
+    for (size_t i = 1; i + 1 < s.size(); ++i) {
+      if (s[i] == '\\' && s.front() == '"' && i + 2 < s.size()) ++i;
+      o.push_back(s[i]);
+    }
+    return o;
+  }
+  return s;
+}
+// "[ a, b, c ]" -> items (handles "[:" too)
+std::vector<std::string> flow_items(const std::string& s) {
+  std::vector<std::string> out;
+  size_t a = s.find('['), b = s.rfind(']');
+  if (a == std::string::npos || b == std::string::npos || b < a) return out;
+  std::string body = s.substr(a + 1, b - a - 1);
+  if (!body.empty() && body[0] == ':') body.erase(0, 1);
+  size_t p = 0;
+  while (p <= body.size()) {
+    size_t q = body.find(',', p);
+    if (q == std::string::npos) q = body.size();
+    std::string it = trim(body.substr(p, q - p));
+    if (!it.empty()) out.push_back(unquote(it));
+    p = q + 1;
+  }
+  return out;
+}
+
+struct ParseState {
+  // detector-level (root) config
+  bool have_levels = false, have_T = false;
+  int pyramid_levels = 0;
+  std::vector<int> T;
+  std::vector<lmb200_modality> mods;
+  // classes
+  struct Cls { std::string id; std::vector<std::string> mod_names; int pyramid_levels = -1; std::vector<TemplatePyramid> tps; };
+  std::vector<Cls> classes;
+};
+
+int parse_file(const char* path, ParseState& S, std::string& err) {
+  Reader rd;
+  if (!rd.open(path)) { err = std::string("cannot open ") + path; return LMB200_E_IO; }
+  std::string raw;
+  bool in_classes = false;         // past "classes:" (or the file is a bare writeClass file)
+  bool in_root_modalities = false;
+  ParseState::Cls* cls = nullptr;
+  Template* tpl = nullptr;
+  long lineno = 0;
+  auto fail = [&](const std::string& m) { err = std::string(path) + ":" + std::to_string(lineno) + ": " + m; rd.close(); return LMB200_E_IO; };
+  while (rd.next(raw)) {
+    ++lineno;
+    std::string s = trim(raw);
+    if (s.empty() || s[0] == '%' || s == "---" || s == "..." || s[0] == '#') continue;
+    // feature line (hot path): "- [ x, y, label ]"
+    if (s[0] == '-' && s.find('[') != std::string::npos && tpl) {
+      const char* p = s.c_str() + s.find('[') + 1;
+      if (*p == ':') ++p;
+      char* e;
+      long x = std::strtol(p, &e, 10); while (*e == ' ' || *e == ',') ++e;
+      long y = std::strtol(e, &e, 10); while (*e == ' ' || *e == ',') ++e;
+      long l = std::strtol(e, &e, 10);
+      tpl->features.push_back(Feature{(int)x, (int)y, (int)l});
+      continue;
+    }
+    if (s[0] == '-') {  // "-" alone or "- key: value"
+      s = trim(s.substr(1));
+      if (s.empty()) continue;
+    }
+    // flow sequences may wrap over several lines
+    if (s.find('[') != std::string::npos && s.find(']') == std::string::npos) {
+      std::string more;
+      while (s.find(']') == std::string::npos && rd.next(more)) { ++lineno; s += " " + trim(more); }
+    }
+    size_t colon = s.find(':');
+    if (colon == std::string::npos) continue;
+    std::string key = trim(s.substr(0, colon)), val = trim(s.substr(colon + 1));
+    if (key == "classes") { in_classes = true; in_root_modalities = false; continue; }
+    if (key == "class_id") {
+      in_classes = true; in_root_modalities = false;
+      S.classes.emplace_back();
+      cls = &S.classes.back(); tpl = nullptr;
+      cls->id = unquote(val);
+      continue;
+    }
+    if (key == "modalities") {
+      if (!val.empty()) {  // class-level flow list of names
+        auto names = flow_items(val);
+        if (cls) cls->mod_names = names;
+        else {  // bare class file may list modalities before class_id: remember for the next class
+          S.classes.emplace_back(); cls = &S.classes.back(); cls->mod_names = names; in_classes = true;
+        }
+      } else if (!in_classes) in_root_modalities = true;
+      continue;
+    }
+    if (key == "pyramid_levels") {
+      int v = std::atoi(val.c_str());
+      if (cls) cls->pyramid_levels = v; else { S.pyramid_levels = v; S.have_levels = true; }
+      continue;
+    }
+    if (key == "T" && !in_classes) {
+      for (auto& it : flow_items(val)) S.T.push_back(std::atoi(it.c_str()));
+      S.have_T = true;
+      continue;
+    }
+    if (in_root_modalities) {
+      if (key == "type") {
+        lmb200_modality mo;
+        std::string t = unquote(val);
+        if (t == "ColorGradient") lmb200_default_modality(LMB200_COLOR_GRADIENT, &mo);
+        else if (t == "DepthNormal") lmb200_default_modality(LMB200_DEPTH_NORMAL, &mo);
+        else return fail("unknown modality type '" + t + "'");
+        S.mods.push_back(mo);
+      } else if (!S.mods.empty()) {
+        lmb200_modality& mo = S.mods.back();
+        if (key == "weak_threshold") mo.weak_threshold = (float)std::atof(val.c_str());
+        else if (key == "strong_threshold") mo.strong_threshold = (float)std::atof(val.c_str());
+        else if (key == "num_features") mo.num_features = std::atoi(val.c_str());
+        else if (key == "distance_threshold") mo.distance_threshold = std::atoi(val.c_str());
+        else if (key == "difference_threshold") mo.difference_threshold = std::atoi(val.c_str());
+        else if (key == "extract_threshold") mo.extract_threshold = std::atoi(val.c_str());
+      }
+      continue;
+    }
+    if (!cls) continue;
+    if (key == "template_pyramids") continue;
+    if (key == "template_id") {
+      int id = std::atoi(val.c_str());
+      if (id != (int)cls->tps.size()) return fail("template_id " + std::to_string(id) + " is not consecutive (upstream CV_Assert)");
+      cls->tps.emplace_back();
+      tpl = nullptr;
+      continue;
+    }
+    if (key == "templates") continue;
+    if (key == "width") {
+      if (cls->tps.empty()) return fail("template outside a template pyramid");
+      cls->tps.back().emplace_back();
+      tpl = &cls->tps.back().back();
+      tpl->width = std::atoi(val.c_str());
+      continue;
+    }
+    if (key == "height" && tpl) { tpl->height = std::atoi(val.c_str()); continue; }
+    if (key == "pyramid_level" && tpl) { tpl->pyramid_level = std::atoi(val.c_str()); continue; }
+    if (key == "features") {
+      if (!val.empty() && tpl) {  // everything in one (wrapped) flow sequence: [ [x,y,l], ... ] or empty "[]"
+        const char* p = val.c_str();
+        std::vector<long> nums;
+        while (*p) {
+          if ((*p >= '0' && *p <= '9') || *p == '-') { char* e; nums.push_back(std::strtol(p, &e, 10)); p = e; }
+          else ++p;
+        }
+        for (size_t i = 0; i + 2 < nums.size(); i += 3) tpl->features.push_back(Feature{(int)nums[i], (int)nums[i + 1], (int)nums[i + 2]});
+      }
+      continue;
+    }
+  }
+  rd.close();
+  return LMB200_OK;
+}
+
+int add_parsed_class(lmb200_detector* h, ParseState::Cls& c, const char* override_id, std::string& err) {
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  if ((int)c.mod_names.size() != M) { err = "class '" + c.id + "': modality count differs from the detector's (upstream CV_Assert)"; return LMB200_E_CLASS; }
+  for (int m = 0; m < M; ++m)
+    if (c.mod_names[m] != mod_name(h->cfg.modalities[m].type)) { err = "class '" + c.id + "': modality names differ from the detector's"; return LMB200_E_CLASS; }
+  if (c.pyramid_levels != L) { err = "class '" + c.id + "': pyramid_levels differs from the detector's"; return LMB200_E_CLASS; }
+  std::string id = (override_id && *override_id) ? override_id : c.id;
+  if (!(override_id && *override_id) && h->classes.count(id)) { err = "class '" + id + "' already present (upstream CV_Assert)"; return LMB200_E_CLASS; }
+  for (auto& tp : c.tps)
+    if ((int)tp.size() != M * L) { err = "class '" + id + "': template pyramid has " + std::to_string(tp.size()) + " templates, expected " + std::to_string(M * L); return LMB200_E_IO; }
+  if (!h->classes.count(id)) h->classes[id] = std::move(c.tps);  // std::map::insert semantics: existing entry wins
+  h->templates_dirty = true;
+  return LMB200_OK;
+}
+
+}  // namespace
+
+int write_detector_file(lmb200_detector* h, const char* path) {
+  Writer w;
+  if (!w.open(path)) return set_error(h, LMB200_E_IO, std::string("cannot open ") + path + " for writing");
+  write_header(w, h);
+  w.put("classes:\n");
+  for (auto& kv : h->classes) {
+    w.put("   -\n");
+    write_class(w, h, kv.first, kv.second, 6);
+  }
+  w.close();
+  return LMB200_OK;
+}
+
+int write_class_file(lmb200_detector* h, const std::string& class_id, const char* path) {
+  auto it = h->classes.find(class_id);
+  if (it == h->classes.end()) return set_error(h, LMB200_E_CLASS, "unknown class " + class_id);
+  Writer w;
+  if (!w.open(path)) return set_error(h, LMB200_E_IO, std::string("cannot open ") + path + " for writing");
+  w.put("%YAML:1.0\n---\n");
+  write_class(w, h, it->first, it->second, 0);
+  w.close();
+  return LMB200_OK;
+}
+
+int read_detector_file(const char* path, int device, lmb200_handle* out, std::string& err) {
+  ParseState S;
+  int rc = parse_file(path, S, err);
+  if (rc) return rc;
+  if (!S.have_levels || !S.have_T || S.mods.empty() || (int)S.T.size() != S.pyramid_levels) {
+    err = std::string(path) + ": missing pyramid_levels / T / modalities at the root";
+    return LMB200_E_IO;
+  }
+  if (S.pyramid_levels > LMB200_MAX_LEVELS || (int)S.mods.size() > LMB200_MAX_MODALITIES) { err = "too many levels/modalities"; return LMB200_E_INVALID; }
+  lmb200_config cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.num_modalities = (int)S.mods.size();
+  for (int m = 0; m < cfg.num_modalities; ++m) cfg.modalities[m] = S.mods[m];
+  cfg.pyramid_levels = S.pyramid_levels;
+  for (int l = 0; l < cfg.pyramid_levels; ++l) cfg.T[l] = S.T[l];
+  cfg.device = device;
+  lmb200_handle h = nullptr;
+  rc = lmb200_create(&cfg, &h);
+  if (rc) { err = lmb200_last_error(nullptr); return rc; }
+  for (auto& c : S.classes) {
+    rc = add_parsed_class(h, c, nullptr, err);
+    if (rc) { lmb200_destroy(h); return rc; }
+  }
+  *out = h;
+  return LMB200_OK;
+}
+
+int read_class_file(lmb200_detector* h, const char* path, std::string& err) {
+  ParseState S;
+  int rc = parse_file(path, S, err);
+  if (rc) return rc;
+  if (S.classes.empty()) { err = std::string(path) + ": no class found"; return LMB200_E_IO; }
+  for (auto& c : S.classes) {
+    rc = add_parsed_class(h, c, nullptr, err);
+    if (rc) return rc;
+  }
+  return LMB200_OK;
+}
+
+}  // namespace lmh

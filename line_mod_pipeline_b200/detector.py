@@ -1,0 +1,377 @@
+"""Python mirror of the reference-facing Detector surface, a thin layer over the C ABI.
+
+Method names and argument meaning follow cv::linemod::Detector as the reference calls it
+(/root/reference/src/HighLevelLinemod.cpp:26-43 ctor, :93 addTemplate, :152 match, :115 getTemplates,
+:55 classIds, :65 numTemplates, :184 getT, :256-320 read/write), so parity tests read like the
+reference's own call sites.  All compute happens in liblmb200.so (CUDA); nothing here has a CPU path.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _capi as K
+
+
+class LinemodError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lmb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+MATCH_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("similarity", np.float32),
+                        ("class_index", np.int32), ("template_id", np.int32)])
+assert MATCH_DTYPE.itemsize == C.sizeof(K.MatchRec)
+
+
+def ColorGradient(weak_threshold=10.0, num_features=63, strong_threshold=55.0):
+    return dict(type=K.COLOR_GRADIENT, weak_threshold=weak_threshold, num_features=num_features,
+                strong_threshold=strong_threshold)
+
+
+def DepthNormal(distance_threshold=2000, difference_threshold=50, num_features=63, extract_threshold=2):
+    return dict(type=K.DEPTH_NORMAL, distance_threshold=distance_threshold, difference_threshold=difference_threshold,
+                num_features=num_features, extract_threshold=extract_threshold)
+
+
+def _image(a):
+    """numpy array -> (lmb200_image, keepalive)."""
+    if a is None:
+        return K.Image(None, 0, 0, K.T_8UC1, 0), None
+    if a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3:
+        t = K.T_8UC3
+    elif a.dtype == np.uint16 and a.ndim == 2:
+        t = K.T_16UC1
+    elif a.dtype == np.uint8 and a.ndim == 2:
+        t = K.T_8UC1
+    else:
+        raise TypeError("image must be uint8 HxWx3 (BGR), uint16 HxW (depth mm) or uint8 HxW (mask)")
+    if a.strides[-1] != a.itemsize or (a.ndim == 3 and a.strides[1] != 3):
+        a = np.ascontiguousarray(a)
+    return K.Image(a.ctypes.data, a.shape[0], a.shape[1], t, a.strides[0]), a
+
+
+def _cstr_array(ids):
+    ids = list(ids or [])
+    arr = (C.c_char_p * max(1, len(ids)))(*[s.encode() for s in ids])
+    return arr, len(ids)
+
+
+class Detector:
+    """Detector(modalities, T_pyramid) — see getDefaultLINE / getDefaultLINEMOD for the reference's two wirings."""
+
+    def __init__(self, modalities=None, T_pyramid=(5, 8), device=-1, max_batch=0, candidate_capacity=0, _handle=None):
+        self._L = K.lib()
+        self._h = K._H()
+        if _handle is not None:
+            self._h = _handle
+            return
+        cfg = K.Config()
+        cfg.num_modalities = len(modalities)
+        for i, m in enumerate(modalities):
+            self._L.lmb200_default_modality(m["type"], C.byref(cfg.modalities[i]))
+            for k, v in m.items():
+                setattr(cfg.modalities[i], k, v)
+        cfg.pyramid_levels = len(T_pyramid)
+        for i, t in enumerate(T_pyramid):
+            cfg.T[i] = int(t)
+        cfg.device = device
+        cfg.max_batch = max_batch
+        cfg.candidate_capacity = candidate_capacity
+        rc = self._L.lmb200_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise LinemodError(rc, (self._L.lmb200_last_error(None) or b"").decode())
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, allow=()):
+        if rc and rc not in allow:
+            raise LinemodError(rc, (self._L.lmb200_last_error(self._h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lmb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ------------------------------------------------------------------ introspection
+    def getModalities(self):
+        return [self._L.lmb200_modality_name(self._h, i).decode() for i in range(self._L.lmb200_num_modalities(self._h))]
+
+    def pyramidLevels(self):
+        return self._L.lmb200_pyramid_levels(self._h)
+
+    def getT(self, level):
+        return self._check_nonneg(self._L.lmb200_get_T(self._h, level))
+
+    def _check_nonneg(self, v):
+        if v < 0:
+            raise LinemodError(v, "bad argument")
+        return v
+
+    def numClasses(self):
+        return self._L.lmb200_num_classes(self._h)
+
+    def classIds(self):
+        return [self._L.lmb200_class_id(self._h, i).decode() for i in range(self.numClasses())]
+
+    def numTemplates(self, class_id=None):
+        return self._L.lmb200_num_templates(self._h, class_id.encode() if class_id is not None else None)
+
+    def getTemplates(self, class_id, template_id):
+        """-> list (level*M+modality) of dict(width,height,pyramid_level,features=int32[n,3])."""
+        n = self.pyramidLevels() * len(self.getModalities())
+        out = []
+        for i in range(n):
+            t = K.Template()
+            self._check(self._L.lmb200_get_template(self._h, class_id.encode(), template_id, i, C.byref(t)))
+            f = np.zeros((t.num_features, 3), np.int32)
+            if t.num_features:
+                f[:] = np.ctypeslib.as_array(C.cast(t.features, C.POINTER(C.c_int)), shape=(t.num_features, 3))
+            out.append(dict(width=t.width, height=t.height, pyramid_level=t.pyramid_level, features=f))
+        return out
+
+    # ------------------------------------------------------------------ templates
+    def addTemplate(self, sources, class_id, object_mask=None):
+        """-> (template_id, (x, y, w, h)); template_id == -1 when extraction fails (reference: HighLevelLinemod.cpp:97)."""
+        imgs = [_image(s) for s in sources]
+        arr = (K.Image * len(imgs))(*[i[0] for i in imgs])
+        mimg, mkeep = _image(object_mask)
+        bb = (C.c_int * 4)()
+        tid = C.c_int(-1)
+        self._check(self._L.lmb200_add_template(self._h, class_id.encode(), arr, len(imgs),
+                                                C.byref(mimg) if object_mask is not None else None, bb, C.byref(tid)))
+        return tid.value, tuple(bb)
+
+    def addSyntheticTemplate(self, templates, class_id):
+        arr = (K.Template * len(templates))()
+        keep = []
+        for i, t in enumerate(templates):
+            f = np.ascontiguousarray(np.asarray(t["features"], np.int32).reshape(-1, 3))
+            keep.append(f)
+            arr[i] = K.Template(t["width"], t["height"], t["pyramid_level"], len(f), C.cast(f.ctypes.data, C.POINTER(K.Feature)))
+        tid = C.c_int(-1)
+        self._check(self._L.lmb200_add_synthetic_template(self._h, class_id.encode(), arr, len(templates), C.byref(tid)))
+        return tid.value
+
+    def clearTemplates(self):
+        self._check(self._L.lmb200_clear_templates(self._h))
+
+    # ------------------------------------------------------------------ persistence
+    def write(self, path):
+        self._check(self._L.lmb200_write(self._h, str(path).encode()))
+
+    @classmethod
+    def read(cls, path, device=-1):
+        L = K.lib()
+        h = K._H()
+        rc = L.lmb200_read(str(path).encode(), device, C.byref(h))
+        if rc:
+            raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode())
+        return cls(_handle=h)
+
+    def writeClasses(self, fmt="templates_%s.yml.gz"):
+        self._check(self._L.lmb200_write_classes(self._h, fmt.encode()))
+
+    def readClasses(self, class_ids, fmt="templates_%s.yml.gz"):
+        arr, n = _cstr_array(class_ids)
+        self._check(self._L.lmb200_read_classes(self._h, arr, n, fmt.encode()))
+
+    # ------------------------------------------------------------------ matching
+    def match(self, sources, threshold, class_ids=(), quantized_images=False, masks=None):
+        """-> structured array (x,y,similarity,class_index,template_id) in the reference's order;
+        with quantized_images=True also returns the list of quantized maps (index level*M+modality)."""
+        imgs = [_image(s) for s in sources]
+        arr = (K.Image * len(imgs))(*[i[0] for i in imgs])
+        ids, nids = _cstr_array(class_ids)
+        qarr, qimgs = None, None
+        if quantized_images:
+            r, c = sources[0].shape[:2]
+            M, L = len(self.getModalities()), self.pyramidLevels()
+            qimgs = []
+            for l in range(L):
+                for m in range(M):
+                    qimgs.append(np.zeros((r, c), np.uint8))
+                r //= 2; c //= 2
+            qarr = (K.Image * len(qimgs))(*[_image(q)[0] for q in qimgs])
+        marr, mkeep = None, None
+        if masks is not None:
+            mkeep = [_image(m) for m in masks]
+            marr = (K.Image * len(mkeep))(*[i[0] for i in mkeep])
+        cap = 4096
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            n = C.c_size_t(0)
+            rc = self._check(self._L.lmb200_match(self._h, arr, len(imgs), C.c_float(threshold), ids, nids,
+                                                  out.ctypes.data_as(C.POINTER(K.MatchRec)), cap, C.byref(n), qarr, marr),
+                             allow=(K.E_TRUNCATED,))
+            if rc == K.E_TRUNCATED:
+                cap = int(n.value)
+                continue
+            res = out[:n.value].view(np.recarray)
+            return (res, qimgs) if quantized_images else res
+
+    def _frames(self, frames):
+        keep, flat = [], []
+        for fr in frames:
+            for s in fr:
+                im, k = _image(s)
+                flat.append(im); keep.append(k)
+        return (K.Image * len(flat))(*flat), keep, len(frames[0])
+
+    def matchBatch(self, frames, threshold, class_ids=(), cap=None):
+        """frames: list of [source per modality].  -> list of per-frame match arrays."""
+        arr, keep, nsrc = self._frames(frames)
+        ids, nids = _cstr_array(class_ids)
+        cap = cap or 4096 * len(frames)
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            offs = (C.c_size_t * (len(frames) + 1))()
+            rc = self._check(self._L.lmb200_match_batch(self._h, arr, len(frames), nsrc, C.c_float(threshold), ids, nids,
+                                                        out.ctypes.data_as(C.POINTER(K.MatchRec)), cap, offs),
+                             allow=(K.E_TRUNCATED,))
+            if rc == K.E_TRUNCATED:
+                cap = int(offs[len(frames)])
+                continue
+            return [out[offs[i]:offs[i + 1]].view(np.recarray) for i in range(len(frames))]
+
+    def uploadFrames(self, frames, first_slot=0):
+        arr, keep, nsrc = self._frames(frames)
+        self._check(self._L.lmb200_upload_frames(self._h, arr, len(frames), nsrc, first_slot))
+
+    def matchResident(self, first_slot, count, threshold, class_ids=()):
+        ids, nids = _cstr_array(class_ids)
+        self._check(self._L.lmb200_match_resident(self._h, first_slot, count, C.c_float(threshold), ids, nids))
+
+    def fetchResident(self, first_slot, count, allgather=False, cap=None):
+        cap = cap or 4096 * count
+        fn = self._L.lmb200_fetch_resident_allgather if allgather else self._L.lmb200_fetch_resident
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            offs = (C.c_size_t * (count + 1))()
+            rc = self._check(fn(self._h, first_slot, count, out.ctypes.data_as(C.POINTER(K.MatchRec)), cap, offs),
+                             allow=(K.E_TRUNCATED,))
+            if rc == K.E_TRUNCATED:
+                cap = int(offs[count])
+                if allgather:
+                    raise LinemodError(rc, "output capacity too small for a collective fetch; pass cap=")
+                continue
+            return [out[offs[i]:offs[i + 1]].view(np.recarray) for i in range(count)]
+
+    def synchronize(self):
+        self._check(self._L.lmb200_synchronize(self._h))
+
+    def stream(self):
+        return self._L.lmb200_stream(self._h)
+
+    def timerRecord(self, which):
+        self._check(self._L.lmb200_timer_record(self._h, which))
+
+    def timerElapsedMs(self):
+        ms = C.c_float(0)
+        self._check(self._L.lmb200_timer_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    # ------------------------------------------------------------------ tables / sharding / profile / debug
+    def setSimilarityLut(self, lut):
+        lut = np.ascontiguousarray(lut, np.uint8); assert lut.size == 256
+        self._check(self._L.lmb200_set_similarity_lut(self._h, lut.ctypes.data))
+
+    def getSimilarityLut(self):
+        out = np.zeros(256, np.uint8)
+        self._check(self._L.lmb200_get_similarity_lut(self._h, out.ctypes.data))
+        return out
+
+    def setNormalLut(self, lut):
+        lut = np.ascontiguousarray(lut, np.uint8); assert lut.size == 8000
+        self._check(self._L.lmb200_set_normal_lut(self._h, lut.ctypes.data))
+
+    def getNormalLut(self):
+        out = np.zeros(8000, np.uint8)
+        self._check(self._L.lmb200_get_normal_lut(self._h, out.ctypes.data))
+        return out
+
+    def setTemplateShard(self, rank, world):
+        self._check(self._L.lmb200_set_template_shard(self._h, rank, world))
+
+    def commInit(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, np.uint8); assert uid.size == 128
+        self._check(self._L.lmb200_comm_init(self._h, uid.ctypes.data, rank, world))
+
+    def setProfiling(self, on):
+        self._check(self._L.lmb200_set_profiling(self._h, int(on)))
+
+    def getProfile(self, reset=False):
+        p = K.Profile()
+        self._check(self._L.lmb200_get_profile(self._h, C.byref(p), int(reset)))
+        d = dict(ms={K.K_NAMES[i]: p.ms[i] for i in range(10)}, launches={K.K_NAMES[i]: p.launches[i] for i in range(10)},
+                 bytes_coarse=p.bytes_coarse, bytes_local=p.bytes_local, frames=p.frames, candidates=p.candidates,
+                 matches=p.matches)
+        return d
+
+    def debugFetch(self, kind, slot=0, index=0):
+        n = C.c_size_t(0)
+        rc = self._L.lmb200_debug_fetch(self._h, kind, slot, index, None, C.byref(n))
+        if rc not in (K.OK, K.E_TRUNCATED):
+            self._check(rc)
+        buf = np.zeros(max(1, n.value), np.uint8)
+        n2 = C.c_size_t(buf.size)
+        self._check(self._L.lmb200_debug_fetch(self._h, kind, slot, index, buf.ctypes.data, C.byref(n2)))
+        buf = buf[:n2.value]
+        if kind in (K.DBG_COARSE, K.DBG_UNSORTED):
+            return buf.view(MATCH_DTYPE).view(np.recarray)
+        if kind == K.DBG_MAGNITUDE:
+            return buf.view(np.float32)
+        if kind == K.DBG_DN_INDICES:
+            return buf.view(np.int8)
+        return buf
+
+
+def getDefaultLINE(**kw):
+    """cv::linemod::getDefaultLINE(): ColorGradient, T={5,8}."""
+    return Detector([ColorGradient()], (5, 8), **kw)
+
+
+def getDefaultLINEMOD(**kw):
+    """cv::linemod::getDefaultLINEMOD(): ColorGradient + DepthNormal, T={5,8} (reference: HighLevelLinemod.cpp:26-35)."""
+    return Detector([ColorGradient(), DepthNormal()], (5, 8), **kw)
+
+
+def comm_unique_id():
+    uid = np.zeros(128, np.uint8)
+    rc = K.lib().lmb200_comm_unique_id(uid.ctypes.data)
+    if rc:
+        raise LinemodError(rc, (K.lib().lmb200_last_error(None) or b"").decode())
+    return uid
+
+
+def merge_matches(parts):
+    """Host merge of per-rank generation-ordered match arrays (rank order) -> reference-ordered list."""
+    L = K.lib()
+    parts = [np.ascontiguousarray(p, MATCH_DTYPE) for p in parts]
+    ptrs = (C.POINTER(K.MatchRec) * len(parts))(*[p.ctypes.data_as(C.POINTER(K.MatchRec)) for p in parts])
+    counts = (C.c_size_t * len(parts))(*[len(p) for p in parts])
+    total = sum(len(p) for p in parts)
+    out = np.zeros(max(1, total), MATCH_DTYPE)
+    n = C.c_size_t(0)
+    rc = L.lmb200_merge_matches(ptrs, counts, len(parts), out.ctypes.data_as(C.POINTER(K.MatchRec)), len(out), C.byref(n))
+    if rc:
+        raise LinemodError(rc, "merge failed")
+    return out[:n.value].view(np.recarray)
+
+
+def shard_plan(costs, world):
+    L = K.lib()
+    costs = np.ascontiguousarray(costs, np.float64)
+    begin = (C.c_int * (world + 1))()
+    rc = L.lmb200_shard_plan(costs.ctypes.data_as(C.POINTER(C.c_double)), len(costs), world, begin)
+    if rc:
+        raise LinemodError(rc, "shard_plan failed")
+    return list(begin)

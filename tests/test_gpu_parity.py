@@ -1,0 +1,255 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) vs the CPU oracle, bit-exact.
+
+Everything here needs a B200 (`-m gpu`).  Sizes are the BASELINE.json configs where the oracle
+finishes in seconds, plus edge cases (ragged geometry, empty sets, malformed templates, masks).
+"""
+import hashlib
+import numpy as np
+import pytest
+
+import line_mod_pipeline_b200 as lm
+from line_mod_pipeline_b200 import synth, capi as K
+from oracle import oracle as O
+from helpers import make_pair, sources, add_random, add_planted_from_oracle, assert_same_matches
+
+pytestmark = pytest.mark.gpu
+sha = lambda a: hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _check_frame_side(det, ora, srcs, threshold=80.0, n_maps=4, masks=None):
+    got, qimgs = det.match(srcs, threshold, quantized_images=True, masks=masks)
+    ref = ora.match(srcs, threshold, masks=masks, debug=True)
+    for i in range(n_maps):
+        q = ref.quantized(i)
+        assert qimgs[i].shape == q.shape
+        bad = np.argwhere(qimgs[i] != q)
+        assert bad.size == 0, "quantized map %d differs at %d px, first %r: got %d want %d" % (
+            i, len(bad), tuple(bad[0]), qimgs[i][tuple(bad[0])], q[tuple(bad[0])])
+        if masks is None:
+            assert np.array_equal(det.debugFetch(K.DBG_QUANTIZED, 0, i).reshape(q.shape), q)
+        lmg, lmo = det.debugFetch(K.DBG_LINMEM, 0, i), ref.linmem(i)
+        assert lmg.shape == lmo.shape
+        bad = np.flatnonzero(lmg != lmo)
+        assert bad.size == 0, "linear memory %d differs at %d bytes, first %d" % (i, bad.size, bad[0])
+    return got, ref
+
+
+def test_frame_side_fixture_golden(fixture_frame, golden):
+    """Quantized maps + linear memories on the reference's own frame, vs oracle AND the golden hashes."""
+    bgr, depth = fixture_frame
+    det, ora = make_pair()
+    _check_frame_side(det, ora, [bgr, depth])
+    q0 = det.debugFetch(K.DBG_QUANTIZED, 0, 0)
+    q1 = det.debugFetch(K.DBG_QUANTIZED, 0, 2)
+    assert sha(q0) == golden["G2G3_L0_T5"]["quantized_sha1"] == "f45507458cb4ef60bbf11099074023f5ddf0bc5d"
+    assert sha(q1) == golden["G4_L1_T8"]["quantized_sha1"]
+    assert sha(det.debugFetch(K.DBG_LINMEM, 0, 0)) == golden["G2G3_L0_T5"]["lut0"]["linmem_sha1"]
+    assert sha(det.debugFetch(K.DBG_LINMEM, 0, 2)) == golden["G4_L1_T8"]["lut0"]["linmem_sha1"]
+    assert sha(det.debugFetch(K.DBG_MAGNITUDE, 0, 0)) == golden["G2G3_L0_T5"]["magnitude_sha1"]
+    assert sha(det.debugFetch(K.DBG_DN_INDICES, 0, 1)) == golden["G5_dn_indices"]["sha1"]
+    # the survey hashed linear memories under the circular LUT: reproduce those too
+    det2, ora2 = make_pair(sim_lut=O.similarity_lut(1))
+    det2.match([bgr, depth], 80.0)
+    assert sha(det2.debugFetch(K.DBG_LINMEM, 0, 0)) == "89d3edac27207763163c79a2eb205f6f0750ca75"
+    assert sha(det2.debugFetch(K.DBG_LINMEM, 0, 2)) == "b3fd1e4644625c962aa0d22da8a22f751270e4f6"
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_frame_side_synthetic(idx):
+    bgr, depth = synth.make_frame(idx)
+    det, ora = make_pair()
+    _check_frame_side(det, ora, [bgr, depth])
+
+
+@pytest.mark.parametrize("rows,cols,T", [(240, 320, (4, 8)), (256, 384, (4, 8, 16)), (120, 160, (5, 8)), (96, 112, (2, 8)), (400, 600, (5, 4))])
+def test_frame_side_ragged_geometry(rows, cols, T):
+    """Sizes that are not multiples of the kernel tiles; W%4 != 0 linear memories (scalar store path)."""
+    bgr, depth = synth.make_frame(3, rows, cols, n_shapes=15)
+    det, ora = make_pair(T=T)
+    _check_frame_side(det, ora, [bgr, depth], n_maps=2 * len(T))
+
+
+def test_size_not_divisible_is_rejected():
+    det, ora = make_pair()
+    bgr, depth = synth.make_frame(0, 480, 636)
+    with pytest.raises(lm.LinemodError) as e:
+        det.match([bgr, depth], 80.0)
+    assert e.value.code == K.E_SIZE
+    with pytest.raises(ValueError):
+        ora.match([bgr, depth], 80.0)
+    with pytest.raises(lm.LinemodError) as e:
+        det.match([bgr], 80.0)
+    assert e.value.code == K.E_SOURCES
+
+
+def test_masks_in_match():
+    bgr, depth = synth.make_frame(4)
+    det, ora = make_pair()
+    m0 = synth.planted_masks(1, seed=3)[0]
+    m1 = synth.planted_masks(1, seed=4)[0]
+    add_random(det, ora, 50)
+    got, ref = _check_frame_side(det, ora, [bgr, depth], masks=[m0, m1])
+    assert_same_matches(got, ref.matches(0), "masked")
+
+
+@pytest.fixture(scope="module")
+def cfg2_small():
+    """Config-2-shaped workload at 400 templates: 40 planted (oracle-extracted) + 360 random."""
+    bgr, depth = synth.make_frame(0)
+    det, ora = make_pair()
+    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(40))
+    assert n >= 20
+    add_random(det, ora, 360)
+    return det, ora, bgr, depth
+
+
+@pytest.mark.parametrize("threshold", [80.0, 55.0, 91.5, 30.0])
+def test_match_parity(cfg2_small, threshold):
+    det, ora, bgr, depth = cfg2_small
+    got = det.match([bgr, depth], threshold)
+    ref = ora.match([bgr, depth], threshold, threads=8, debug=True)
+    assert_same_matches(det.debugFetch(K.DBG_COARSE, 0), ref.matches(2), "coarse candidates thr=%g" % threshold)
+    assert_same_matches(det.debugFetch(K.DBG_UNSORTED, 0), ref.matches(1), "generation order thr=%g" % threshold)
+    assert_same_matches(got, ref.matches(0), "final thr=%g" % threshold)
+    if threshold <= 80:
+        assert len(got) > 0
+
+
+def test_match_other_frame_and_class_filter(cfg2_small):
+    det, ora, _, _ = cfg2_small
+    bgr, depth = synth.make_frame(5)
+    for ids in ((), ("rand",), ("planted",), ("rand", "planted"), ("nope", "planted")):
+        got = det.match([bgr, depth], 60.0, class_ids=ids)
+        ref = ora.match([bgr, depth], 60.0, class_ids=ids, threads=8)
+        assert_same_matches(got, ref.matches(0), "class filter %r" % (ids,))
+
+
+def test_batch_and_resident_equal_single(cfg2_small):
+    det, ora, _, _ = cfg2_small
+    frames = [list(synth.make_frame(i)) for i in range(11)]
+    singles = [det.match(f, 70.0) for f in frames]
+    batch = det.matchBatch(frames, 70.0)
+    for i, (a, b) in enumerate(zip(batch, singles)):
+        assert_same_matches(a, b, "batch frame %d" % i)
+    assert_same_matches(batch[3], ora.match(frames[3], 70.0, threads=8).matches(0), "batch vs oracle")
+    det.uploadFrames(frames[:6], first_slot=2)
+    det.matchResident(2, 6, 70.0)
+    res = det.fetchResident(2, 6)
+    for i in range(6):
+        assert_same_matches(res[i], singles[i], "resident frame %d" % i)
+
+
+def test_candidate_overflow_grows():
+    """A tiny candidate store must grow transparently and still give the oracle's list."""
+    bgr, depth = synth.make_frame(0)
+    det, ora = make_pair(candidate_capacity=64, max_batch=4)
+    add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(12))
+    add_random(det, ora, 100)
+    got = det.match([bgr, depth], 20.0)
+    ref = ora.match([bgr, depth], 20.0, threads=8)
+    assert len(got) > 64
+    assert_same_matches(got, ref.matches(0), "overflow")
+    frames = [list(synth.make_frame(i)) for i in range(5)]
+    det2, ora2 = make_pair(candidate_capacity=64, max_batch=4)
+    add_planted_from_oracle(det2, ora2, [bgr, depth], synth.planted_masks(12))
+    add_random(det2, ora2, 100)
+    for i, b in enumerate(det2.matchBatch(frames, 20.0)):
+        assert_same_matches(b, ora2.match(frames[i], 20.0, threads=8).matches(0), "overflow batch %d" % i)
+
+
+def test_color_only_T2_8(fixture_frame):
+    """The reference's shipped default wiring: {ColorGradient}, T={2,8} (HighLevelLinemod.cpp:36-43)."""
+    bgr, depth = fixture_frame
+    det, ora = make_pair(modalities=("cg",), T=(2, 8))
+    add_planted_from_oracle(det, ora, [bgr], synth.planted_masks(30, seed=11))
+    add_random(det, ora, 150, n_modalities=1)
+    for thr in (80.0, 50.0):
+        got, ref = _check_frame_side(det, ora, [bgr], thr, n_maps=2)
+        assert_same_matches(got, ref.matches(0), "CG-only thr=%g" % thr)
+
+
+def test_three_level_pyramid():
+    """Config-5-shaped pyramid (T={4,8,16}, features 63/31/15) at a size the oracle does quickly."""
+    bgr, depth = synth.make_frame(6, 512, 768)
+    det, ora = make_pair(T=(4, 8, 16))
+    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(30, 512, 768, seed=5, size_range=(60, 120)))
+    assert n > 5
+    add_random(det, ora, 200, levels=3, wh_range=(40, 120))
+    for thr in (80.0, 50.0):
+        got, ref = _check_frame_side(det, ora, [bgr, depth], thr, n_maps=6)
+        assert_same_matches(det.debugFetch(K.DBG_UNSORTED, 0), ref.matches(1), "3-level generation order")
+        assert_same_matches(got, ref.matches(0), "3-level thr=%g" % thr)
+
+
+def test_empty_and_degenerate_templates():
+    bgr, depth = synth.make_frame(0)
+    det, ora = make_pair()
+    assert len(det.match([bgr, depth], 50.0)) == 0          # no templates at all
+    rng = np.random.default_rng(5)
+    weird = []
+    for k in range(40):
+        tp = synth.random_template_pyramid(rng, 2, 2)
+        kind = k % 5
+        for t in tp:
+            f = t["features"]
+            if kind == 0:      # features far outside the bbox (guarded rows)
+                f[:, 0] += 300 >> t["pyramid_level"]
+            elif kind == 1:    # template wider than the image minus 16T (N4: clamp makes max_x < border)
+                t["width"] = 600 >> t["pyramid_level"]; t["height"] = 440 >> t["pyramid_level"]
+            elif kind == 2:    # negative coordinates and an empty feature list at the coarse level
+                f[0, 0] = -3
+                if t["pyramid_level"] == 1:
+                    t["features"] = f[:0]
+            elif kind == 3:    # bbox larger than the whole image (P <= 0)
+                t["width"] = 700 >> t["pyramid_level"]; t["height"] = 500 >> t["pyramid_level"]
+            else:              # features beyond the image
+                f[:, 1] += 470 >> t["pyramid_level"]
+        weird.append(tp)
+    for tp in weird:
+        det.addSyntheticTemplate(tp, "weird"); ora.add_synthetic(tp, "weird")
+    add_random(det, ora, 20)
+    for thr in (10.0, 40.0):
+        got = det.match([bgr, depth], thr)
+        ref = ora.match([bgr, depth], thr, debug=True)
+        assert_same_matches(det.debugFetch(K.DBG_COARSE, 0), ref.matches(2), "degenerate coarse thr=%g" % thr)
+        assert_same_matches(got, ref.matches(0), "degenerate thr=%g" % thr)
+
+
+def test_add_template_parity(fixture_frame):
+    """Product addTemplate (GPU quantisation + host selection) == oracle addTemplate, incl. failures."""
+    for name, (bgr, depth) in (("fixture", fixture_frame), ("synthetic", synth.make_frame(2))):
+        det, ora = make_pair()
+        masks = synth.planted_masks(24, seed=21) + [None, np.zeros((480, 640), np.uint8)]
+        ok = 0
+        for i, m in enumerate(masks):
+            tid, bb = det.addTemplate([bgr, depth], "obj", m)
+            otid, obb = ora.add_template([bgr, depth], "obj", m)
+            assert tid == otid, "%s mask %d: template id %d vs oracle %d" % (name, i, tid, otid)
+            if tid >= 0:
+                ok += 1
+                assert tuple(bb) == tuple(obb)
+                got = det.getTemplates("obj", tid)
+                want = O.decode_pyramid(ora.get_template_flat("obj", tid))
+                for a, b in zip(got, want):
+                    assert (a["width"], a["height"], a["pyramid_level"]) == (b["width"], b["height"], b["pyramid_level"])
+                    assert np.array_equal(a["features"], b["features"])
+        assert ok >= 10 and det.numTemplates("obj") == ora.num_templates("obj") == ok
+        assert_same_matches(det.match([bgr, depth], 75.0), ora.match([bgr, depth], 75.0).matches(0), "after addTemplate")
+
+
+def test_config2_full_size():
+    """BASELINE config 2: one 640x480 frame vs 3 000 templates (300 planted + 2 700 random), thresholds 80 and 57."""
+    bgr, depth = synth.make_frame(0)
+    det, ora = make_pair()
+    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(300, seed=17))
+    add_random(det, ora, 3000 - n)
+    assert det.numTemplates() == 3000
+    for thr in (80.0, 57.0):
+        got = det.match([bgr, depth], thr)
+        ref = ora.match([bgr, depth], thr, threads=8)
+        assert_same_matches(got, ref.matches(0), "config 2 thr=%g" % thr)
+    # size-independent properties: idempotence and order
+    again = det.match([bgr, depth], 57.0)
+    assert_same_matches(again, got, "idempotence")
+    s = got.similarity
+    assert np.all(s[:-1] >= s[1:]) and np.all(s >= 57.0)
