@@ -94,12 +94,18 @@ def build_templates_product(det, n_templates, bgr, depth):
     """configs[1] template set through the PRODUCT's own addTemplate: ~10 % planted on frame 0, rest random (seed 99)."""
     from line_mod_pipeline_b200 import synth
     planted = 0
-    for m in synth.planted_masks(n_templates // 10, seed=17):
+    for m in planted_mask_list(n_templates):
         tid, _ = det.addTemplate([bgr, depth], "planted", m)
         planted += tid >= 0
     for tp in synth.random_templates(n_templates - planted):
         det.addSyntheticTemplate(tp, "rand")
     return planted
+
+
+def planted_mask_list(n_templates):
+    """Masks for the planted ~10 %: frame 0's object silhouettes + random rectangles/ellipses on frame 0."""
+    from line_mod_pipeline_b200 import synth
+    return synth.object_masks(0) + synth.planted_masks(n_templates // 10, seed=17)
 
 
 def copy_templates_to_oracle(det, ora):
@@ -135,7 +141,7 @@ def run_reference(args):
     ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], normal_lut=lut)
     bgr0, depth0 = synth.make_frame(0)
     planted = 0
-    for m in synth.planted_masks(args.templates // 10, seed=17):
+    for m in planted_mask_list(args.templates):
         tid, _ = ora.add_template([bgr0, depth0], "planted", m)
         planted += tid >= 0
     for tp in synth.random_templates(args.templates - planted):
@@ -240,9 +246,9 @@ def main():
     barrier()
     ms = det.timerElapsedMs()
     clocks = sampler.summary()
+    res = det.fetchResident(0, B) if not allg else step()   # outside the timed region (also collects device-side counters)
     prof = det.getProfile(reset=True)
     det.setProfiling(False)
-    res = det.fetchResident(0, B) if not allg else step()
     n_matches = int(sum(len(r) for r in res))
     if dist is not None:
         t = torch.tensor([ms], device="cuda")
@@ -282,6 +288,8 @@ def main():
         if launches[k]:
             kernels[k] = {"ms_total": round(prof["ms"][k], 4), "launches": launches[k], "ms_per_launch": round(prof["ms"][k] / launches[k], 5)}
     bytes_frame_side = K * B * (FRAME_BYTES + 2 * 8 * (ROWS * COLS + ROWS * COLS // 4))
+    # similarityLocal bytes are counted on the device per step; the fetch above read one step's counters
+    prof["bytes_local"] = prof["bytes_local"] * (K if not allg else 1)
     alg = {"sim_coarse": prof["bytes_coarse"], "sim_local": prof["bytes_local"], "linearize": K * B * 2 * 9 * (ROWS * COLS + ROWS * COLS // 4)}
     for k, b in alg.items():
         if k in kernels and prof["ms"][k] > 0:

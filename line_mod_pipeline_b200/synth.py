@@ -10,12 +10,13 @@ Random templates (seed 99): bbox w,h even in [60,200]; per modality nf features 
 import numpy as np
 
 
-def make_frame(idx=0, rows=480, cols=640, n_shapes=40):
+def make_frame(idx=0, rows=480, cols=640, n_shapes=40, return_owner=False):
     rng = np.random.default_rng(1234 + idx)
     yy, xx = np.mgrid[0:rows, 0:cols].astype(np.float32)
     color = np.full((rows, cols, 3), 128.0, np.float32)
     depth = np.full((rows, cols), 1200.0, np.float32)
-    for _ in range(n_shapes):
+    owner = np.full((rows, cols), -1, np.int32)      # index of the topmost shape per pixel
+    for k in range(n_shapes):
         cx, cy = rng.uniform(0, cols), rng.uniform(0, rows)
         a, b = rng.uniform(10, 100), rng.uniform(10, 100)
         th = rng.uniform(0, np.pi)
@@ -27,6 +28,7 @@ def make_frame(idx=0, rows=480, cols=640, n_shapes=40):
             m = (np.abs(u) <= a) & (np.abs(v) <= b)
         col = rng.uniform(20, 235, 3)
         color[m] = col
+        owner[m] = k
         d0 = rng.uniform(500, 1100)
         sx, sy = rng.uniform(-0.5, 0.5, 2)
         depth[m] = (d0 + sx * (xx - cx) + sy * (yy - cy))[m]
@@ -39,7 +41,25 @@ def make_frame(idx=0, rows=480, cols=640, n_shapes=40):
     depth = np.clip(depth, 400, 1999)
     holes = rng.random(((rows + 7) // 8, (cols + 7) // 8)) < 0.05
     depth[np.kron(holes, np.ones((8, 8), bool))[:rows, :cols]] = 0
+    if return_owner:
+        return bgr, np.rint(depth).astype(np.uint16), owner
     return bgr, np.rint(depth).astype(np.uint16)
+
+
+def object_masks(idx=0, rows=480, cols=640, n_shapes=40, min_px=1500, margin=12):
+    """Object masks for planting templates: the visible region of every shape of frame `idx` that is large
+    enough and away from the image border (uint8 0/255), i.e. silhouettes that coincide with real edges."""
+    _, _, owner = make_frame(idx, rows, cols, n_shapes, return_owner=True)
+    out = []
+    for k in range(n_shapes):
+        m = owner == k
+        if m.sum() < min_px:
+            continue
+        ys, xs = np.nonzero(m)
+        if ys.min() < margin or xs.min() < margin or ys.max() >= rows - margin or xs.max() >= cols - margin:
+            continue
+        out.append(m.astype(np.uint8) * 255)
+    return out
 
 
 def random_template_pyramid(rng, n_modalities, levels, nf0=63, wh_range=(60, 200)):

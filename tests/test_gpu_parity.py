@@ -61,7 +61,7 @@ def test_frame_side_synthetic(idx):
     _check_frame_side(det, ora, [bgr, depth])
 
 
-@pytest.mark.parametrize("rows,cols,T", [(240, 320, (4, 8)), (256, 384, (4, 8, 16)), (120, 160, (5, 8)), (96, 112, (2, 8)), (400, 600, (5, 4))])
+@pytest.mark.parametrize("rows,cols,T", [(240, 320, (4, 8)), (256, 384, (4, 8, 16)), (160, 240, (5, 8)), (96, 112, (2, 8)), (400, 600, (5, 4))])
 def test_frame_side_ragged_geometry(rows, cols, T):
     """Sizes that are not multiples of the kernel tiles; W%4 != 0 linear memories (scalar store path)."""
     bgr, depth = synth.make_frame(3, rows, cols, n_shapes=15)
@@ -97,9 +97,9 @@ def cfg2_small():
     """Config-2-shaped workload at 400 templates: 40 planted (oracle-extracted) + 360 random."""
     bgr, depth = synth.make_frame(0)
     det, ora = make_pair()
-    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(40))
+    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(0) + synth.planted_masks(40))
     assert n >= 20
-    add_random(det, ora, 360)
+    add_random(det, ora, 400 - n)
     return det, ora, bgr, depth
 
 
@@ -172,7 +172,7 @@ def test_three_level_pyramid():
     """Config-5-shaped pyramid (T={4,8,16}, features 63/31/15) at a size the oracle does quickly."""
     bgr, depth = synth.make_frame(6, 512, 768)
     det, ora = make_pair(T=(4, 8, 16))
-    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(30, 512, 768, seed=5, size_range=(60, 120)))
+    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(6, 512, 768))
     assert n > 5
     add_random(det, ora, 200, levels=3, wh_range=(40, 120))
     for thr in (80.0, 50.0):
@@ -241,7 +241,9 @@ def test_config2_full_size():
     """BASELINE config 2: one 640x480 frame vs 3 000 templates (300 planted + 2 700 random), thresholds 80 and 57."""
     bgr, depth = synth.make_frame(0)
     det, ora = make_pair()
-    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.planted_masks(300, seed=17))
+    masks = synth.object_masks(0) + synth.planted_masks(300, seed=17)
+    n = add_planted_from_oracle(det, ora, [bgr, depth], masks)
+    assert n >= 100
     add_random(det, ora, 3000 - n)
     assert det.numTemplates() == 3000
     for thr in (80.0, 57.0):
