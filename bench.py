@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--threshold", type=float, default=80.0)
     ap.add_argument("--shard", default="frames", choices=["frames", "templates"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--template-cache", default="", help="YAML(.gz) written/read through the product's persistence; skips addTemplate when present")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -189,9 +190,20 @@ def main():
 
     B, K, W = args.frames, args.steps, max(args.warmup, 3)
     n_tpl = args.templates * (world if args.shard == "templates" else 1)
-    det = lm.getDefaultLINEMOD(device=local, max_batch=B)
     bgr0, depth0 = synth.make_frame(0)
-    planted = build_templates_product(det, n_tpl, bgr0, depth0)
+    if args.template_cache and os.path.exists(args.template_cache):
+        det0 = lm.Detector.read(args.template_cache)
+        det = lm.getDefaultLINEMOD(device=local, max_batch=B)
+        for cid in det0.classIds():
+            for t in range(det0.numTemplates(cid)):
+                det.addSyntheticTemplate(det0.getTemplates(cid, t), cid)
+        planted = det.numTemplates("planted")
+        det0.close()
+    else:
+        det = lm.getDefaultLINEMOD(device=local, max_batch=B)
+        planted = build_templates_product(det, n_tpl, bgr0, depth0)
+        if args.template_cache and rank == 0:
+            det.write(args.template_cache)
     if args.shard == "templates" and world > 1:
         det.setTemplateShard(rank, world)
         uid = torch.zeros(128, dtype=torch.uint8)
@@ -222,7 +234,7 @@ def main():
     def step():
         det.matchResident(0, B, args.threshold)
         if allg:
-            return det.fetchResident(0, B, allgather=True, cap=16384 * B)
+            return det.fetchResident(0, B, allgather=True, cap=2048 * B)
         return None
 
     def barrier():
@@ -261,11 +273,11 @@ def main():
     e2e = None
     if not args.no_e2e and not allg:
         for _ in range(2):
-            det.matchBatch(frames, args.threshold, cap=16384 * B)
+            det.matchBatch(frames, args.threshold, cap=2048 * B)
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
-            det.matchBatch(frames, args.threshold, cap=16384 * B)
+            det.matchBatch(frames, args.threshold, cap=2048 * B)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:

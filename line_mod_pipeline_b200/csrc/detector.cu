@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 using namespace lmk;
@@ -751,7 +752,8 @@ int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames
   h->masks_in_use = false;
 restart:
   const int half = std::max(1, h->slots / 2);
-  const int chunk = std::min(half, 8);
+  int chunk = std::min(half, 8);
+  if (const char* e = std::getenv("LMB200_CHUNK")) chunk = std::max(1, std::min(half, std::atoi(e)));
   struct Pending { int first_frame, count, slot0, lane; };
   std::vector<Pending> inflight;
   size_t base = 0;

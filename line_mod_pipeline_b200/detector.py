@@ -230,9 +230,9 @@ class Detector:
         """frames: list of [source per modality].  -> list of per-frame match arrays."""
         arr, keep, nsrc = self._frames(frames)
         ids, nids = _cstr_array(class_ids)
-        cap = cap or 4096 * len(frames)
+        cap = cap or 1024 * len(frames)
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = self._outbuf(cap)
             offs = (C.c_size_t * (len(frames) + 1))()
             rc = self._check(self._L.lmb200_match_batch(self._h, arr, len(frames), nsrc, C.c_float(threshold), ids, nids,
                                                         out.ctypes.data_as(C.POINTER(K.MatchRec)), cap, offs),
@@ -240,7 +240,15 @@ class Detector:
             if rc == K.E_TRUNCATED:
                 cap = int(offs[len(frames)])
                 continue
-            return [out[offs[i]:offs[i + 1]].view(np.recarray) for i in range(len(frames))]
+            return [out[offs[i]:offs[i + 1]].copy().view(np.recarray) for i in range(len(frames))]
+
+    def _outbuf(self, cap):
+        """Reusable (uninitialised) result buffer: zero-filling tens of MB per call would dominate a batch call."""
+        buf = getattr(self, "_out_cache", None)
+        if buf is None or len(buf) < cap:
+            buf = np.empty(cap, MATCH_DTYPE)
+            self._out_cache = buf
+        return buf
 
     def uploadFrames(self, frames, first_slot=0):
         arr, keep, nsrc = self._frames(frames)
@@ -251,10 +259,10 @@ class Detector:
         self._check(self._L.lmb200_match_resident(self._h, first_slot, count, C.c_float(threshold), ids, nids))
 
     def fetchResident(self, first_slot, count, allgather=False, cap=None):
-        cap = cap or 4096 * count
+        cap = cap or 1024 * count
         fn = self._L.lmb200_fetch_resident_allgather if allgather else self._L.lmb200_fetch_resident
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = self._outbuf(cap)
             offs = (C.c_size_t * (count + 1))()
             rc = self._check(fn(self._h, first_slot, count, out.ctypes.data_as(C.POINTER(K.MatchRec)), cap, offs),
                              allow=(K.E_TRUNCATED,))
@@ -263,7 +271,7 @@ class Detector:
                 if allgather:
                     raise LinemodError(rc, "output capacity too small for a collective fetch; pass cap=")
                 continue
-            return [out[offs[i]:offs[i + 1]].view(np.recarray) for i in range(count)]
+            return [out[offs[i]:offs[i + 1]].copy().view(np.recarray) for i in range(count)]
 
     def synchronize(self):
         self._check(self._L.lmb200_synchronize(self._h))

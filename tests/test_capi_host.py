@@ -1,0 +1,106 @@
+"""CPU-side checks of the product library: it loads without a GPU, exports every symbol the header
+declares, its host logic (template store, tables, shard plan, merge) works, and every compute entry
+point fails LOUDLY without a CUDA device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+
+import line_mod_pipeline_b200 as lm
+from line_mod_pipeline_b200 import capi as K, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_header_symbols_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "lmb200.h")).read()
+    declared = set(re.findall(r"\b(lmb200_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    out = subprocess.run(["nm", "-D", "--defined-only", K.SO_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lmb200_[a-zA-Z0-9_]+)", out))
+    assert declared <= exported, "declared but not exported: %r" % sorted(declared - exported)
+    assert declared == set(K.SIGNATURES), "ctypes table out of sync: %r" % sorted(declared ^ set(K.SIGNATURES))
+    L = K.lib()
+    assert L.lmb200_version().startswith(b"lmb200")
+    assert C.sizeof(K.MatchRec) == 20 and C.sizeof(K.Feature) == 12
+
+
+def test_detector_surface_host_side():
+    d = lm.getDefaultLINEMOD()
+    assert d.getModalities() == ["ColorGradient", "DepthNormal"] and d.pyramidLevels() == 2
+    assert (d.getT(0), d.getT(1)) == (5, 8) and d.numClasses() == 0 and d.numTemplates() == 0
+    line = lm.getDefaultLINE()
+    assert line.getModalities() == ["ColorGradient"]
+    tps = synth.random_templates(5)
+    for i, tp in enumerate(tps):
+        assert d.addSyntheticTemplate(tp, "b_obj") == i
+    assert d.addSyntheticTemplate(tps[0], "a_obj") == 0
+    assert d.classIds() == ["a_obj", "b_obj"]            # std::map key order
+    assert d.numTemplates() == 6 and d.numTemplates("b_obj") == 5 and d.numTemplates("zzz") == 0
+    got = d.getTemplates("b_obj", 3)
+    for a, b in zip(got, tps[3]):
+        assert (a["width"], a["height"], a["pyramid_level"]) == (b["width"], b["height"], b["pyramid_level"])
+        assert np.array_equal(a["features"], b["features"])
+    with pytest.raises(lm.LinemodError) as e:
+        d.getTemplates("b_obj", 99)
+    assert e.value.code == K.E_CLASS
+    bad = [dict(t, features=np.zeros((64, 3), np.int32)) for t in tps[0]]
+    with pytest.raises(lm.LinemodError) as e:
+        d.addSyntheticTemplate(bad, "x")                 # upstream CV_Assert(features.size() <= 63)
+    assert e.value.code == K.E_FEATURES
+    with pytest.raises(lm.LinemodError):
+        d.addSyntheticTemplate(tps[0][:3], "x")          # wrong pyramid size
+
+
+def test_tables():
+    d = lm.getDefaultLINEMOD()
+    lut = d.getSimilarityLut()
+    assert lut[:16].tolist() == [0, 4, 3, 4, 2, 4, 3, 4, 1, 4, 3, 4, 2, 4, 3, 4] and int(lut.sum()) == 528
+    assert np.array_equal(d.getNormalLut(), synth.default_normal_lut())
+    with pytest.raises(lm.LinemodError):
+        d.setNormalLut(np.full(8000, 3, np.uint8))       # not one-hot
+    with pytest.raises(lm.LinemodError):
+        d.setSimilarityLut(np.full(256, 5, np.uint8))    # 63 * 5 would overflow a byte
+    from oracle import oracle as O
+    d.setSimilarityLut(O.similarity_lut(1))
+    assert np.array_equal(d.getSimilarityLut(), O.similarity_lut(1))
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    d = lm.getDefaultLINEMOD()
+    bgr, depth = synth.make_frame(0, 96, 160, n_shapes=4)
+    for call in (lambda: d.match([bgr, depth], 80.0),
+                 lambda: d.addTemplate([bgr, depth], "x", None),
+                 lambda: d.uploadFrames([[bgr, depth]]),
+                 lambda: d.matchBatch([[bgr, depth]], 80.0)):
+        with pytest.raises(lm.LinemodError) as e:
+            call()
+        assert e.value.code == K.E_NODEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_shard_plan_and_merge():
+    assert lm.shard_plan([1, 1, 1, 1], 2) == [0, 2, 4]
+    assert lm.shard_plan([], 3) == [0, 0, 0, 0]
+    plan = lm.shard_plan(np.r_[np.ones(10), 100, np.ones(10)], 4)
+    assert plan[0] == 0 and plan[-1] == 21 and all(a <= b for a, b in zip(plan, plan[1:]))
+    rng = np.random.default_rng(0)
+    costs = rng.uniform(1, 3, 1000)
+    p = lm.shard_plan(costs, 8)
+    sums = [costs[p[i]:p[i + 1]].sum() for i in range(8)]
+    assert max(sums) / min(sums) < 1.05
+    # merge == sort+unique of the concatenation (Match::operator< / operator== of upstream)
+    a = np.array([(10, 10, 90.0, 0, 1), (20, 10, 95.0, 0, 1), (10, 10, 90.0, 0, 2)], lm.MATCH_DTYPE)
+    b = np.array([(10, 10, 90.0, 0, 3), (5, 5, 99.0, 1, 0), (10, 10, 90.0, 0, 3)], lm.MATCH_DTYPE)
+    m = lm.merge_matches([a, b])
+    assert [tuple(x) for x in m.tolist()] == [(5, 5, 99.0, 1, 0), (20, 10, 95.0, 0, 1), (10, 10, 90.0, 0, 1)]

@@ -1,0 +1,137 @@
+"""Template-file persistence (OpenCV FileStorage YAML 1.0 / .gz) — the on-disk contract of
+HighLevelLineMOD::writeLinemod / readLinemod (reference: src/HighLevelLinemod.cpp:256-300)."""
+import os
+import numpy as np
+import pytest
+
+import line_mod_pipeline_b200 as lm
+from line_mod_pipeline_b200 import capi as K, synth
+
+
+def _fill(d, n=7):
+    tps = synth.random_templates(n, seed=5)
+    for i, tp in enumerate(tps):
+        d.addSyntheticTemplate(tp, "lagergehaeuse.ply" if i % 2 else "other obj")
+    return tps
+
+
+def _same(a, b):
+    assert a.classIds() == b.classIds() and a.numTemplates() == b.numTemplates()
+    assert a.getModalities() == b.getModalities() and a.pyramidLevels() == b.pyramidLevels()
+    assert [a.getT(l) for l in range(a.pyramidLevels())] == [b.getT(l) for l in range(b.pyramidLevels())]
+    for cid in a.classIds():
+        assert a.numTemplates(cid) == b.numTemplates(cid)
+        for t in range(a.numTemplates(cid)):
+            for x, y in zip(a.getTemplates(cid, t), b.getTemplates(cid, t)):
+                assert (x["width"], x["height"], x["pyramid_level"]) == (y["width"], y["height"], y["pyramid_level"])
+                assert np.array_equal(x["features"], y["features"])
+
+
+@pytest.mark.parametrize("name", ["linemod_templates.yml.gz", "linemod_templates.yml"])
+def test_round_trip(tmp_path, name):
+    d = lm.getDefaultLINEMOD()
+    _fill(d)
+    path = str(tmp_path / name)
+    d.write(path)
+    _same(d, lm.Detector.read(path))
+
+
+def test_three_level_color_only_round_trip(tmp_path):
+    d = lm.Detector([lm.ColorGradient(weak_threshold=12.5, num_features=40, strong_threshold=60.0)], (4, 8, 16))
+    for tp in synth.random_templates(3, n_modalities=1, levels=3, nf0=40):
+        d.addSyntheticTemplate(tp, "c")
+    path = str(tmp_path / "t.yml.gz")
+    d.write(path)
+    _same(d, lm.Detector.read(path))
+
+
+def test_real_opencv_reads_our_file(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    d = lm.getDefaultLINEMOD()
+    tps = _fill(d)
+    path = str(tmp_path / "linemod_templates.yml.gz")
+    d.write(path)
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+    assert fs.isOpened() and int(fs.getNode("pyramid_levels").real()) == 2
+    T = fs.getNode("T")
+    assert [int(T.at(i).real()) for i in range(T.size())] == [5, 8]
+    mods = fs.getNode("modalities")
+    assert mods.at(0).getNode("type").string() == "ColorGradient" and mods.at(0).getNode("weak_threshold").real() == 10.0
+    assert mods.at(1).getNode("type").string() == "DepthNormal" and int(mods.at(1).getNode("distance_threshold").real()) == 2000
+    classes = fs.getNode("classes")
+    assert classes.size() == 2 and classes.at(0).getNode("class_id").string() == "lagergehaeuse.ply"
+    tp0 = classes.at(0).getNode("template_pyramids").at(0)
+    assert int(tp0.getNode("template_id").real()) == 0
+    t = tp0.getNode("templates").at(3)
+    want = tps[1][3]
+    assert int(t.getNode("width").real()) == want["width"] and int(t.getNode("pyramid_level").real()) == 1
+    f = t.getNode("features")
+    got = np.array([[int(f.at(i).at(j).real()) for j in range(3)] for i in range(f.size())])
+    assert np.array_equal(got, want["features"])
+
+
+def test_we_read_a_file_written_by_real_opencv(tmp_path):
+    """Emit the layout with cv2.FileStorage itself (its own indentation/quoting/wrapping) and load it."""
+    cv2 = pytest.importorskip("cv2")
+    tps = synth.random_templates(3, seed=8)
+    path = str(tmp_path / "cv_written.yml.gz")
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_WRITE)
+    fs.write("pyramid_levels", 2)
+    fs.startWriteStruct("T", cv2.FileNode_SEQ | cv2.FileNode_FLOW); fs.write("", 5); fs.write("", 8); fs.endWriteStruct()
+    fs.startWriteStruct("modalities", cv2.FileNode_SEQ)
+    fs.startWriteStruct("", cv2.FileNode_MAP); fs.write("type", "ColorGradient"); fs.write("weak_threshold", 10.0)
+    fs.write("num_features", 63); fs.write("strong_threshold", 55.0); fs.endWriteStruct()
+    fs.startWriteStruct("", cv2.FileNode_MAP); fs.write("type", "DepthNormal"); fs.write("distance_threshold", 2000)
+    fs.write("difference_threshold", 50); fs.write("num_features", 63); fs.write("extract_threshold", 2); fs.endWriteStruct()
+    fs.endWriteStruct()
+    fs.startWriteStruct("classes", cv2.FileNode_SEQ)
+    fs.startWriteStruct("", cv2.FileNode_MAP)
+    fs.write("class_id", "lagergehaeuse.ply")
+    fs.startWriteStruct("modalities", cv2.FileNode_SEQ | cv2.FileNode_FLOW); fs.write("", "ColorGradient"); fs.write("", "DepthNormal"); fs.endWriteStruct()
+    fs.write("pyramid_levels", 2)
+    fs.startWriteStruct("template_pyramids", cv2.FileNode_SEQ)
+    for i, tp in enumerate(tps):
+        fs.startWriteStruct("", cv2.FileNode_MAP)
+        fs.write("template_id", i)
+        fs.startWriteStruct("templates", cv2.FileNode_SEQ)
+        for t in tp:
+            fs.startWriteStruct("", cv2.FileNode_MAP)
+            fs.write("width", int(t["width"])); fs.write("height", int(t["height"])); fs.write("pyramid_level", int(t["pyramid_level"]))
+            fs.startWriteStruct("features", cv2.FileNode_SEQ)
+            for x, y, l in t["features"]:
+                fs.startWriteStruct("", cv2.FileNode_SEQ | cv2.FileNode_FLOW); fs.write("", int(x)); fs.write("", int(y)); fs.write("", int(l)); fs.endWriteStruct()
+            fs.endWriteStruct()
+            fs.endWriteStruct()
+        fs.endWriteStruct()
+        fs.endWriteStruct()
+    fs.endWriteStruct()
+    fs.endWriteStruct()
+    fs.endWriteStruct()
+    fs.release()
+    d = lm.Detector.read(path)
+    assert d.classIds() == ["lagergehaeuse.ply"] and d.numTemplates() == 3 and d.getModalities() == ["ColorGradient", "DepthNormal"]
+    for i, tp in enumerate(tps):
+        for a, b in zip(d.getTemplates("lagergehaeuse.ply", i), tp):
+            assert (a["width"], a["height"], a["pyramid_level"]) == (b["width"], b["height"], b["pyramid_level"])
+            assert np.array_equal(a["features"], b["features"])
+
+
+def test_write_read_classes(tmp_path):
+    d = lm.getDefaultLINEMOD()
+    _fill(d)
+    fmt = str(tmp_path / "templates_%s.yml.gz")
+    d.writeClasses(fmt)
+    assert sorted(os.listdir(tmp_path)) == ["templates_lagergehaeuse.ply.yml.gz", "templates_other obj.yml.gz"]
+    e = lm.getDefaultLINEMOD()
+    e.readClasses(["other obj", "lagergehaeuse.ply"], fmt)
+    _same(d, e)
+    with pytest.raises(lm.LinemodError) as err:      # upstream: CV_Assert(class not already present)
+        e.readClasses(["other obj"], fmt)
+    assert err.value.code == K.E_CLASS
+    line = lm.getDefaultLINE()
+    with pytest.raises(lm.LinemodError) as err:      # upstream: CV_Assert(modalities match)
+        line.readClasses(["other obj"], fmt)
+    assert err.value.code == K.E_CLASS
+    with pytest.raises(lm.LinemodError) as err:
+        lm.Detector.read(str(tmp_path / "missing.yml.gz"))
+    assert err.value.code == K.E_IO
