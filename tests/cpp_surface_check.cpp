@@ -1,0 +1,35 @@
+// Compile-and-run check of include/lmb200_detector.hpp against liblmb200.so (host-only calls: no GPU needed).
+#include <cstdio>
+#include <cstring>
+#include "lmb200_detector.hpp"
+
+int main(int argc, char** argv) {
+  auto det = lm::getDefaultLINEMOD();
+  if (det->getModalities().size() != 2 || det->getT(0) != 5 || det->getT(1) != 8 || det->pyramidLevels() != 2) return 1;
+  std::vector<lm::Template> tp(4);
+  for (int i = 0; i < 4; ++i) {
+    tp[i].width = 100 >> (i / 2); tp[i].height = 80 >> (i / 2); tp[i].pyramid_level = i / 2;
+    for (int k = 0; k < 10; ++k) tp[i].features.push_back(lm::Feature(k, 2 * k, k % 8));
+  }
+  if (det->addSyntheticTemplate(tp, "lagergehaeuse.ply") != 0 || det->addSyntheticTemplate(tp, "lagergehaeuse.ply") != 1) return 2;
+  if (det->numTemplates() != 2 || det->numClasses() != 1 || det->classIds()[0] != "lagergehaeuse.ply") return 3;
+  std::string path = std::string(argc > 1 ? argv[1] : "/tmp") + "/cpp_surface.yml.gz";
+  det->write(path);
+  auto back = lm::Detector::read(path);
+  auto t = back->getTemplates("lagergehaeuse.ply", 1);
+  if (t.size() != 4 || t[3].features.size() != 10 || t[3].features[9].y != 18 || t[2].width != 50) return 4;
+  // match without a GPU must throw the loud no-device error; with a GPU it must return an (empty-ish) list
+  std::vector<unsigned char> bgr(480 * 640 * 3, 0);
+  std::vector<unsigned short> depth(480 * 640, 0);
+  std::vector<lm::Match> matches;
+  try {
+    det->match({lm::ImageView(bgr.data(), 480, 640, LMB200_8UC3), lm::ImageView(depth.data(), 480, 640, LMB200_16UC1)}, 80.f, matches,
+               {"lagergehaeuse.ply"});
+    std::printf("match ran on a GPU: %zu matches\n", matches.size());
+  } catch (const lm::Error& e) {
+    if (e.code != LMB200_E_NODEVICE) { std::printf("unexpected: %s\n", e.what()); return 5; }
+    std::printf("no GPU: %s\n", e.what());
+  }
+  std::printf("CPP_SURFACE_OK\n");
+  return 0;
+}

@@ -104,3 +104,15 @@ def test_shard_plan_and_merge():
     b = np.array([(10, 10, 90.0, 0, 3), (5, 5, 99.0, 1, 0), (10, 10, 90.0, 0, 3)], lm.MATCH_DTYPE)
     m = lm.merge_matches([a, b])
     assert [tuple(x) for x in m.tolist()] == [(5, 5, 99.0, 1, 0), (20, 10, 95.0, 0, 1), (10, 10, 90.0, 0, 1)]
+
+
+def test_cpp_surface_header_compiles_and_runs(tmp_path):
+    """include/lmb200_detector.hpp (the cv::linemod::Detector-shaped C++ surface) against liblmb200.so."""
+    exe = str(tmp_path / "cpp_surface_check")
+    so_dir = os.path.dirname(K.SO_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_surface_check.cpp"),
+           "-o", exe, "-L", so_dir, "-llmb200", "-Wl,-rpath," + so_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "CPP_SURFACE_OK" in r.stdout, r.stdout + r.stderr
