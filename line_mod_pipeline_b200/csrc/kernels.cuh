@@ -30,12 +30,14 @@ struct alignas(8) TplHdr {
   short height[MAX_MOD];
   u8 nf[MAX_MOD];
   u32 flags;                          // bit0: local-safe, bit1: coarse-safe (set by the plan kernel)
+  u32 bkt[MAX_MOD];                   // plan: per modality, 4 x u8 counts of valid offsets per word shift (off>>2)&3
 };
 
 // Register-resident view of a TplHdr (dynamic modality index without local memory).
 struct HdrR {
-  unsigned long long w, h;
+  unsigned long long w, h, b01, b23;
   u32 nfs, flags;
+  __device__ __forceinline__ u32 bkt(int m) const { unsigned long long v = (m & 2) ? b23 : b01; return (u32)(v >> (32 * (m & 1))); }
   __device__ __forceinline__ int width(int m) const { return (int)(short)(w >> (16 * m)); }
   __device__ __forceinline__ int height(int m) const { return (int)(short)(h >> (16 * m)); }
   __device__ __forceinline__ int nf(int m) const { return (int)((nfs >> (8 * m)) & 0xFFu); }
@@ -50,6 +52,7 @@ __device__ __forceinline__ HdrR load_hdr(const TplHdr* p) {
   r.w = __ldg(q); r.h = __ldg(q + 1);
   unsigned long long t = __ldg(q + 2);
   r.nfs = (u32)t; r.flags = (u32)(t >> 32);
+  r.b01 = __ldg(q + 3); r.b23 = __ldg(q + 4);
   return r;
 }
 #endif

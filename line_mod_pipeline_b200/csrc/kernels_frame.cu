@@ -213,6 +213,9 @@ void launch_cg_quantize(const u8* bgr, size_t bgr_stride, u8* q, size_t q_stride
 // float normalisation with explicit rn intrinsics (no FMA); C truncation; LUT indices clamped
 // to 19 (upstream reads out of bounds there — N4).  Writes every pixel (0 on border/failure).
 // ---------------------------------------------------------------------------------------------
+// ACC = int when every intermediate provably fits 32 bits (difference_threshold <= 200, distance_threshold
+// <= 65535: |1150*ddx| <= 1150*(150+100)*30*199 < 2^31, det*d <= 22500*65535 < 2^31), else long long.
+template <typename ACC>
 __global__ void __launch_bounds__(256) dn_quantize_kernel(const u16* __restrict__ depth, size_t depth_stride,
                                                           u8* __restrict__ out, size_t out_stride,
                                                           int8_t* __restrict__ idx_out, int rows, int cols,
@@ -225,23 +228,22 @@ __global__ void __launch_bounds__(256) dn_quantize_kernel(const u16* __restrict_
   int v1 = -1, v2 = -1, v3 = -1;
   const int r = 5;
   if (y >= r && y < rows - r - 1 && x >= r && x < cols - r - 1) {
-    long long dc = d[pix];
+    const ACC dc = d[pix];
     if (dc < dist_thr) {
-      long long A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
+      ACC A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
       const int oi[8] = {-5, 0, 5, -5, 5, -5, 0, 5};
       const int oj[8] = {-5, -5, -5, 0, 0, 5, 5, 5};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        long long i = oi[k], j = oj[k];
-        long long delta = (long long)d[(size_t)(y + oj[k]) * cols + (x + oi[k])] - dc;
-        long long f = (delta < 0 ? -delta : delta) < diff_thr ? 1 : 0;
-        long long fi = f * i, fj = f * j;
-        A0 += fi * i; A1 += fi * j; A3 += fj * j;
-        b0 += fi * delta; b1 += fj * delta;
+        const ACC delta = (ACC)d[(size_t)(y + oj[k]) * cols + (x + oi[k])] - dc;
+        if ((delta < 0 ? -delta : delta) < diff_thr) {  // f = 1
+          A0 += oi[k] * oi[k]; A1 += oi[k] * oj[k]; A3 += oj[k] * oj[k];
+          b0 += oi[k] * delta; b1 += oj[k] * delta;
+        }
       }
-      long long det = A0 * A3 - A1 * A1;
-      long long ddx = A3 * b0 - A1 * b1;
-      long long ddy = -A1 * b0 + A0 * b1;
+      const ACC det = A0 * A3 - A1 * A1;
+      const ACC ddx = A3 * b0 - A1 * b1;
+      const ACC ddy = -A1 * b0 + A0 * b1;
       float nx = (float)(1150 * ddx), ny = (float)(1150 * ddy), nz = (float)(-det * dc);
       float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
       if (s > 0) {
@@ -266,17 +268,23 @@ void launch_dn_quantize(const u16* depth, size_t depth_stride, u8* out, size_t o
                         int rows, int cols, int dist_thr, int diff_thr, const u8* lut_dev, int frames,
                         cudaStream_t st) {
   dim3 grid((cols + 31) / 32, (rows + 7) / 8, frames), block(32, 8);
-  dn_quantize_kernel<<<grid, block, 0, st>>>(depth, depth_stride, out, out_stride, idx_out, rows, cols, dist_thr,
-                                             diff_thr, lut_dev);
+  if (diff_thr <= 200 && dist_thr <= 65535)
+    dn_quantize_kernel<int><<<grid, block, 0, st>>>(depth, depth_stride, out, out_stride, idx_out, rows, cols, dist_thr, diff_thr, lut_dev);
+  else
+    dn_quantize_kernel<long long><<<grid, block, 0, st>>>(depth, depth_stride, out, out_stride, idx_out, rows, cols, dist_thr, diff_thr, lut_dev);
 }
 
 // ---------------------------------------------------------------------------------------------
 // medianBlur(5), replicate border, on bytes that are 0 or one-hot: the sorted order is
 // 0 < 1 < 2 < 4 < ... < 128, so the 13th of 25 falls out of nine 5-bit counters.
 // ---------------------------------------------------------------------------------------------
+// Separable: per column the 5-row window is folded into eight byte-wide label counters (two u32; a
+// one-hot byte's nibble n becomes (n*0x204081)&0x01010101, one counter byte per set bit), then every
+// output adds five neighbouring column counters and walks the cumulative count to the 13th element.
 __global__ void __launch_bounds__(256) median5_kernel(const u8* __restrict__ src, size_t src_stride,
                                                       u8* __restrict__ dst, size_t dst_stride, int rows, int cols) {
   __shared__ u8 tile[8 + 4][32 + 4 + 4];
+  __shared__ uint2 colcnt[8][32 + 4];
   const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
   const u8* s = src + (size_t)blockIdx.z * src_stride;
   const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -285,21 +293,39 @@ __global__ void __launch_bounds__(256) median5_kernel(const u8* __restrict__ src
     tile[ty][tx] = s[(size_t)clampi(y0 - 2 + ty, 0, rows - 1) * cols + clampi(x0 - 2 + tx, 0, cols - 1)];
   }
   __syncthreads();
+  for (int idx = tid; idx < 8 * 36; idx += 256) {
+    int ty = idx / 36, tx = idx - ty * 36;
+    u32 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      u32 v = tile[ty + i][tx];
+      lo += ((v & 15u) * 0x00204081u) & 0x01010101u;
+      hi += ((v >> 4) * 0x00204081u) & 0x01010101u;
+    }
+    colcnt[ty][tx] = make_uint2(lo, hi);
+  }
+  __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
   if (x >= cols || y >= rows) return;
-  unsigned long long cnt = 0;
+  u32 lo = 0, hi = 0;
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) cnt += 1ull << (5 * __ffs((int)tile[threadIdx.y + i][threadIdx.x + j]));
-  int acc = 0, k = 0;
-#pragma unroll
-  for (int b = 0; b < 9; ++b) {
-    int c = (int)((cnt >> (5 * b)) & 31);
-    if (acc < 13) k = b;
-    acc += c;
+  for (int j = 0; j < 5; ++j) {
+    uint2 c = colcnt[threadIdx.y][threadIdx.x + j];
+    lo += c.x; hi += c.y;
   }
-  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * cols + x] = k ? (u8)(1u << (k - 1)) : (u8)0;
+  // sorted order 0 < 1 < 2 < ... < 128: zeros first, then labels 0..7
+  u32 s4 = (lo & 0x00FF00FFu) + ((lo >> 8) & 0x00FF00FFu) + (hi & 0x00FF00FFu) + ((hi >> 8) & 0x00FF00FFu);
+  int acc = 25 - (int)((s4 & 0xFFFFu) + (s4 >> 16));
+  u8 res = 0;
+  if (acc < 13) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      int c = (int)(((b < 4 ? lo : hi) >> (8 * (b & 3))) & 0xFFu);
+      if (acc < 13 && acc + c >= 13) res = (u8)(1u << b);
+      acc += c;
+    }
+  }
+  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * cols + x] = res;
 }
 
 void launch_median5(const u8* src, size_t src_stride, u8* dst, size_t dst_stride, int rows, int cols, int frames,
@@ -339,6 +365,13 @@ void launch_resize_nn(const u8* src, size_t src_stride, int rows, int cols, u8* 
 // ---------------------------------------------------------------------------------------------
 constexpr int SL_CW = 64;
 
+__device__ __forceinline__ u32 bytes_nonzero_mask(u32 m) {  // 0xFF in every byte of m that is non-zero
+  u32 nz = (((m & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | m) & 0x80808080u;
+  return (nz >> 7) * 0xFFu;
+}
+
+// Shared memory holds the band as 32-bit words (4 pixels): the T x T OR is T word-ORs vertically and
+// T funnel-shift+ORs horizontally per 4 pixels.
 __global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restrict__ q, size_t q_stride,
                                                                const u8* __restrict__ mask, size_t mask_stride,
                                                                u8* __restrict__ lm, size_t lm_stride, LevelGeom g,
@@ -349,44 +382,61 @@ __global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restr
   const int c0 = blockIdx.y * SL_CW;   // first decimated column of this chunk
   const int cw = min(SL_CW, W - c0);
   const int pw = cw * T;               // pixel columns produced
-  const int lw = pw + T - 1;           // pixel columns loaded
-  const int lwp = (lw + 3) & ~3;
+  const int pww = (pw + 3) >> 2;       // ... in words
+  const int wpr = pww + 5;             // words per staged row: T-1 halo bytes + slack for the 5-word window
   const int nr = 2 * T - 1;
-  u8* qb = sl_smem;                                      // [nr][lwp]   raw band, later horizontal result [T][lwp]
-  u8* vb = qb + (size_t)nr * lwp;                        // [T][lwp]    vertical OR
-  uint2* tab = (uint2*)(sl_smem + (((size_t)(nr + T) * lwp + 15) & ~(size_t)15));
+  u32* qb = reinterpret_cast<u32*>(sl_smem);                 // [nr][wpr] raw band; later the spread band [T][wpr]
+  u32* vb = qb + nr * wpr;                                   // [T][wpr]  vertical OR
+  uint2* tab = reinterpret_cast<uint2*>(sl_smem + (((size_t)(nr + T) * wpr * 4 + 15) & ~(size_t)15));
   const int tid = threadIdx.x;
   const u8* qf = q + (size_t)blockIdx.z * q_stride;
   const u8* mf = mask ? mask + (size_t)blockIdx.z * mask_stride : nullptr;
 
   tab[tid] = table[tid];  // 256 threads, 256 entries
   const int y0 = i * T, x0 = c0 * T;
-  for (int idx = tid; idx < nr * lw; idx += 256) {
-    int r = idx / lw, x = idx - r * lw;
-    int gy = y0 + r, gx = x0 + x;
-    u8 v = 0;
+  const bool vec_in = ((g.cols & 3) == 0) && ((x0 & 3) == 0);
+  for (int idx = tid; idx < nr * wpr; idx += 256) {
+    const int r = idx / wpr, xw = idx - r * wpr;
+    const int gy = y0 + r, gx = x0 + 4 * xw;
+    u32 v = 0;
     if (gy < g.rows && gx < g.cols) {
-      v = qf[(size_t)gy * g.cols + gx];
-      if (mf && !mf[(size_t)gy * g.cols + gx]) v = 0;
+      const size_t o = (size_t)gy * g.cols + gx;
+      if (vec_in && gx + 3 < g.cols) {
+        v = *reinterpret_cast<const u32*>(qf + o);
+        if (mf) v &= bytes_nonzero_mask(*reinterpret_cast<const u32*>(mf + o));
+      } else {
+        for (int b = 0; b < 4 && gx + b < g.cols; ++b) {
+          u32 px = qf[o + b];
+          if (mf && !mf[o + b]) px = 0;
+          v |= px << (8 * b);
+        }
+      }
     }
-    qb[r * lwp + x] = v;
+    qb[idx] = v;
   }
   __syncthreads();
-  for (int idx = tid; idx < T * lw; idx += 256) {
-    int r = idx / lw, x = idx - r * lw;
-    u8 v = 0;
-    for (int k = 0; k < T; ++k) v |= qb[(r + k) * lwp + x];
-    vb[r * lwp + x] = v;
+  for (int idx = tid; idx < T * wpr; idx += 256) {
+    const int r = idx / wpr, xw = idx - r * wpr;
+    u32 v = 0;
+    for (int k = 0; k < T; ++k) v |= qb[(r + k) * wpr + xw];
+    vb[idx] = v;
   }
   __syncthreads();
-  for (int idx = tid; idx < T * pw; idx += 256) {
-    int r = idx / pw, x = idx - r * pw;
-    u8 v = 0;
-    for (int k = 0; k < T; ++k) v |= vb[r * lwp + x + k];
-    qb[r * lwp + x] = v;  // qb rows [0,T) now hold the spread band
+  for (int idx = tid; idx < T * pww; idx += 256) {
+    const int r = idx / pww, xw = idx - r * pww;
+    const u32* wp = vb + r * wpr + xw;
+    const u32 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    const u32 ww[6] = {w0, w1, w2, w3, w4, 0u};
+    u32 v = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < T) v |= __funnelshift_r(ww[k >> 2], ww[(k >> 2) + 1], (k & 3) * 8);
+    qb[r * wpr + xw] = v;  // qb rows [0,T) now hold the spread band
   }
   __syncthreads();
 
+  const u8* sb = reinterpret_cast<const u8*>(qb);
+  const int rowb = wpr * 4;
   u8* lmf = lm + (size_t)blockIdx.z * lm_stride;
   const u32 per = g.per_label;
   const u32 plane = (u32)W * g.H;
@@ -400,14 +450,14 @@ __global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restr
     for (int j = 0; j < 4; ++j) {
       int p = 4 * k + j;
       uint2 e = make_uint2(0u, 0u);
-      if (p < cw) e = tab[qb[gy * lwp + p * T + gx]];
+      if (p < cw) e = tab[sb[gy * rowb + p * T + gx]];
       lo[j] = e.x; hi[j] = e.y;
     }
     u32 dstoff = (u32)cell * plane + (u32)i * W + c0 + 4 * k;
     if (vec && 4 * k + 3 < cw) {
       // transpose 4 positions x 8 orientations -> one u32 (4 positions) per orientation
-      u32 t01 = __byte_perm(lo[0], lo[1], 0x5140), t23 = __byte_perm(lo[2], lo[3], 0x5140);  // ori0: b0,b0' ; ori1: b1,b1'
-      u32 u01 = __byte_perm(lo[0], lo[1], 0x7362), u23 = __byte_perm(lo[2], lo[3], 0x7362);  // ori2, ori3
+      u32 t01 = __byte_perm(lo[0], lo[1], 0x5140), t23 = __byte_perm(lo[2], lo[3], 0x5140);
+      u32 u01 = __byte_perm(lo[0], lo[1], 0x7362), u23 = __byte_perm(lo[2], lo[3], 0x7362);
       *(u32*)(lmf + 0 * (size_t)per + dstoff) = __byte_perm(t01, t23, 0x5410);
       *(u32*)(lmf + 1 * (size_t)per + dstoff) = __byte_perm(t01, t23, 0x7632);
       *(u32*)(lmf + 2 * (size_t)per + dstoff) = __byte_perm(u01, u23, 0x5410);
@@ -434,8 +484,8 @@ __global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restr
 }
 
 static size_t sl_smem_bytes(int T, int cw) {
-  int lw = cw * T + T - 1, lwp = (lw + 3) & ~3;
-  size_t b = ((size_t)(3 * T - 1) * lwp + 15) & ~(size_t)15;
+  int pww = (cw * T + 3) >> 2, wpr = pww + 5;
+  size_t b = ((size_t)(3 * T - 1) * wpr * 4 + 15) & ~(size_t)15;
   return b + 256 * sizeof(uint2);
 }
 

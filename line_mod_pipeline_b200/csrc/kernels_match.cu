@@ -13,10 +13,12 @@
 namespace lmk {
 
 // ---------------------------------------------------------------------------------------------
-// Plan kernel: one warp per template.  offs[g][m*64+k] = label*per_label + grid_index*W*H + lm_index
-// (OFF_INVALID when upstream's similarity() would skip the feature).  hdr.flags:
-//   bit0  local-safe : similarityLocal can never skip a feature or leave its plane (see below)
-//   bit1  coarse-safe: every feature row + template_positions stays inside its label's block
+// Plan kernel: one warp per template.  For every modality the valid feature offsets
+//   off = label*per_label + grid_index*W*H + lm_index            (accessLinearMemory)
+// are written contiguously, SORTED by their word shift (off>>2)&3 (warp-level counting sort), with the
+// four bucket sizes in hdr.bkt[m]; features upstream's similarity() would skip are dropped.
+// hdr.flags: bit0 local-safe  : similarityLocal can never skip a feature or leave its plane
+//            bit1 coarse-safe : every feature row + template_positions stays inside its label's block
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restrict__ feat, u32* __restrict__ offs,
                                                             TplHdr* __restrict__ hdr, int ntpl, int M, LevelGeom g) {
@@ -25,26 +27,51 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
   TplHdr h = hdr[warp];
   const int T = g.T, W = g.W, H = g.H;
   const u32 plane = (u32)W * H;
+  const u32 lt = (1u << lane) - 1u;
   bool local_safe = h.width[0] >= 0 && h.height[0] >= 0 && h.width[0] <= g.cols - 16 * T && h.height[0] <= g.rows - 16 * T;
   bool coarse_safe = true;
-  for (int s = lane; s < M * FEAT_SLOTS; s += 32) {
-    int m = s / FEAT_SLOTS, k = s - m * FEAT_SLOTS;
-    u32 off = OFF_INVALID;
-    if (k < h.nf[m]) {
-      u32 f = feat[(size_t)warp * M * FEAT_SLOTS + s];
-      int x = f & 0x3FFF, y = (f >> 14) & 0x3FFF, label = (f >> 28) & 7;
-      bool valid = (f >> 31) && x < g.cols && y < g.rows;
-      if (valid) {
-        u32 base = (u32)((y % T) * T + (x % T)) * plane + (u32)(y / T) * W + (u32)(x / T);
-        off = (u32)label * g.per_label + base;
-        int wf = (h.width[m] - 1) / T + 1, hf = (h.height[m] - 1) / T + 1;
-        long long P = (long long)(H - hf) * W + (W - wf) + 1;
-        if (P > (long long)plane) P = plane;
-        if (P > 0 && (long long)base + P > (long long)g.per_label) coarse_safe = false;
+  for (int m = 0; m < M; ++m) {
+    u32 off2[2];
+    int key2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = lane + 32 * j;
+      u32 off = OFF_INVALID;
+      if (k < (int)hdr[warp].nf[m]) {
+        u32 f = feat[((size_t)warp * M + m) * FEAT_SLOTS + k];
+        int x = f & 0x3FFF, y = (f >> 14) & 0x3FFF, label = (f >> 28) & 7;
+        bool valid = (f >> 31) && x < g.cols && y < g.rows;
+        if (valid) {
+          u32 base = (u32)((y % T) * T + (x % T)) * plane + (u32)(y / T) * W + (u32)(x / T);
+          off = (u32)label * g.per_label + base;
+          int wf = (hdr[warp].width[m] - 1) / T + 1, hf = (hdr[warp].height[m] - 1) / T + 1;
+          long long P = (long long)(H - hf) * W + (W - wf) + 1;
+          if (P > (long long)plane) P = plane;
+          if (P > 0 && (long long)base + P > (long long)g.per_label) coarse_safe = false;
+        }
+        if (!(f >> 31) || x > h.width[0] || y > h.height[0]) local_safe = false;
       }
-      if (!(f >> 31) || x > h.width[0] || y > h.height[0]) local_safe = false;
+      off2[j] = off;
+      key2[j] = off == OFF_INVALID ? 4 : (int)((off >> 2) & 3);
     }
-    offs[(size_t)warp * M * FEAT_SLOTS + s] = off;
+    // counting sort by key (0..3 valid buckets, 4 = dropped)
+    u32 start = 0, packed = 0;
+    u32 dst[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      u32 b0 = __ballot_sync(0xffffffffu, key2[0] == w), b1 = __ballot_sync(0xffffffffu, key2[1] == w);
+      u32 c0 = __popc(b0), c1 = __popc(b1);
+      if (key2[0] == w) dst[0] = start + __popc(b0 & lt);
+      if (key2[1] == w) dst[1] = start + c0 + __popc(b1 & lt);
+      packed |= (c0 + c1) << (8 * w);
+      start += c0 + c1;
+    }
+    u32* o = offs + ((size_t)warp * M + m) * FEAT_SLOTS;
+    o[lane] = OFF_INVALID; o[lane + 32] = OFF_INVALID;
+    __syncwarp();
+    if (dst[0] != 0xFFFFFFFFu) o[dst[0]] = off2[0];
+    if (dst[1] != 0xFFFFFFFFu) o[dst[1]] = off2[1];
+    if (lane == 0) hdr[warp].bkt[m] = packed;
   }
   local_safe = __all_sync(0xffffffffu, local_safe);
   coarse_safe = __all_sync(0xffffffffu, coarse_safe);
@@ -60,8 +87,6 @@ void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 ld_nc_u32(const u32* p) { return __ldg(p); }
-
 // zero the bytes at index >= nv (nv in [0,16]) of a 16-byte value held in 4 little-endian words
 __device__ __forceinline__ void mask16(u32& w0, u32& w1, u32& w2, u32& w3, int nv) {
   u32 w[4] = {w0, w1, w2, w3};
@@ -80,215 +105,218 @@ __device__ __forceinline__ int raw_threshold(int nf, float threshold) {
   return (int)__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f);
 }
 
-// Accumulate one (modality, word-shift) bucket of feature rows into 16 packed byte sums.
-// lmb: this modality's linear memories + 16*chunk (16 B aligned).  WS = (off>>2)&3 is uniform per bucket,
-// so the realignment is straight-line code: two aligned LDG.128 + four funnel shifts per feature.
+// Accumulate the features [k0, k0+n) of one word-shift bucket into 16 packed byte sums.
+// lst = the modality's sorted offsets staged in shared memory (LDS broadcast);
+// lmb = modality's linear memories + 16*chunk (16 B aligned).  WS is a
+// compile-time constant per bucket, so the realignment is straight-line: two aligned LDG.128 + four
+// funnel shifts per feature; a 32-bit IADD then adds four responses (bytes never carry: <= 63*4).
 template <int WS, bool SAFE>
-__device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u32* __restrict__ lst,
-                                             const u32* __restrict__ lim, int n, int pos0, int P,
-                                             u32& a0, u32& a1, u32& a2, u32& a3) {
+__device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u32* __restrict__ lst, int k0, int n, bool active,
+                                             int pos0, int P, u32 per_label, u32& a0, u32& a1, u32& a2, u32& a3) {
 #pragma unroll 4
-  for (int k = 0; k < n; ++k) {
+  for (int k = k0; k < k0 + n; ++k) {
     const u32 off = lst[k];
     int nv = 16;
+    bool go = active;
     if (!SAFE) {
-      nv = min(P, (int)lim[k]) - pos0;  // positions past the label block contribute 0 (oracle semantics)
-      if (nv <= 0) continue;            // ... and are never loaded
+      int lim = (int)(per_label - off % per_label);   // positions past the label block contribute 0 (oracle semantics)
+      nv = min(P, lim) - pos0;
+      go = go && nv > 0;                              // ... and are never loaded
     }
-    const uint4* p = reinterpret_cast<const uint4*>(lmb + (off & ~15u));
-    const uint4 A = __ldg(p), B = __ldg(p + 1);
-    const u32 sh = (off & 3u) * 8u;
-    u32 w0, w1, w2, w3;
-    if (WS == 0) {
-      w0 = __funnelshift_r(A.x, A.y, sh); w1 = __funnelshift_r(A.y, A.z, sh);
-      w2 = __funnelshift_r(A.z, A.w, sh); w3 = __funnelshift_r(A.w, B.x, sh);
-    } else if (WS == 1) {
-      w0 = __funnelshift_r(A.y, A.z, sh); w1 = __funnelshift_r(A.z, A.w, sh);
-      w2 = __funnelshift_r(A.w, B.x, sh); w3 = __funnelshift_r(B.x, B.y, sh);
-    } else if (WS == 2) {
-      w0 = __funnelshift_r(A.z, A.w, sh); w1 = __funnelshift_r(A.w, B.x, sh);
-      w2 = __funnelshift_r(B.x, B.y, sh); w3 = __funnelshift_r(B.y, B.z, sh);
-    } else {
-      w0 = __funnelshift_r(A.w, B.x, sh); w1 = __funnelshift_r(B.x, B.y, sh);
-      w2 = __funnelshift_r(B.y, B.z, sh); w3 = __funnelshift_r(B.z, B.w, sh);
+    if (go) {
+      const uint4* p = reinterpret_cast<const uint4*>(lmb + (off & ~15u));
+      const uint4 A = __ldg(p), B = __ldg(p + 1);
+      const u32 sh = (off & 3u) * 8u;
+      u32 w0, w1, w2, w3;
+      if (WS == 0) {
+        w0 = __funnelshift_r(A.x, A.y, sh); w1 = __funnelshift_r(A.y, A.z, sh);
+        w2 = __funnelshift_r(A.z, A.w, sh); w3 = __funnelshift_r(A.w, B.x, sh);
+      } else if (WS == 1) {
+        w0 = __funnelshift_r(A.y, A.z, sh); w1 = __funnelshift_r(A.z, A.w, sh);
+        w2 = __funnelshift_r(A.w, B.x, sh); w3 = __funnelshift_r(B.x, B.y, sh);
+      } else if (WS == 2) {
+        w0 = __funnelshift_r(A.z, A.w, sh); w1 = __funnelshift_r(A.w, B.x, sh);
+        w2 = __funnelshift_r(B.x, B.y, sh); w3 = __funnelshift_r(B.y, B.z, sh);
+      } else {
+        w0 = __funnelshift_r(A.w, B.x, sh); w1 = __funnelshift_r(B.x, B.y, sh);
+        w2 = __funnelshift_r(B.y, B.z, sh); w3 = __funnelshift_r(B.z, B.w, sh);
+      }
+      if (!SAFE && nv < 16) mask16(w0, w1, w2, w3, nv);
+      a0 += w0; a1 += w1; a2 += w2; a3 += w3;
     }
-    if (!SAFE && nv < 16) mask16(w0, w1, w2, w3, nv);
-    a0 += w0; a1 += w1; a2 += w2; a3 += w3;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Coarse similarity: grid (template, frame); each thread owns chunks of 16 contiguous positions.
+// Coarse similarity: one WARP per (template, frame) — no block barriers.  The warp sweeps the
+// H*W positions in passes of 32 lanes x 16 positions; hits are appended in raster order to a small
+// per-warp queue (lane order = position order, passes are sequential).  One atomicAdd per template
+// with hits reserves a contiguous block of the frame's candidate store; if a template has more hits
+// than the queue holds (low thresholds) the warp re-sweeps and writes directly into its block.
 // ---------------------------------------------------------------------------------------------
-template <bool SAFE>
-__device__ __forceinline__ void coarse_body(const MatchParams& mp, const LevelParams& lp, const HdrR& hdr,
-                                            const u32* lst, const u32* lim, const int* cnt, u16* bm, int NC,
-                                            const u8* const* s_lm, int raw_thr) {
-  const int M = mp.M, T = lp.g.T, W = lp.g.W, H = lp.g.H, HW = W * H;
-  for (int c = threadIdx.x; c < NC; c += blockDim.x) {
-    const int pos0 = 16 * c;
+constexpr int CW_WARPS = 4;          // warps (templates) per CTA
+constexpr int CW_QCAP = 96;          // queued hits per warp
+
+struct CoarseCtx {
+  HdrR hdr;
+  const u32* lst;                    // this warp's staged offsets [M][FEAT_SLOTS] (shared memory)
+  int M, T, W, H, HW, NC, raw_thr, nf_total;
+  u32 per_label;
+  __device__ __forceinline__ int P(int m) const {  // upstream's template_positions
+    int wf = (hdr.width(m) - 1) / T + 1, hf = (hdr.height(m) - 1) / T + 1;
+    int p = (H - hf) * W + (W - wf) + 1;
+    return p > HW ? HW : p;
+  }
+};
+
+// DIRECT=false: count hits and queue them (queue entries beyond CW_QCAP are dropped, count continues)
+// DIRECT=true : write Cand records at out[0..) in raster order
+template <bool SAFE, bool DIRECT>
+__device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const* s_lm, u32* queue, Cand* out, int isel, int lane) {
+  int nhit = 0;
+  int Pmax = 0;
+  for (int m = 0; m < cx.M; ++m) Pmax = max(Pmax, cx.P(m));
+  const int offset = cx.T / 2 + (cx.T % 2 - 1);
+  const float denom = (float)(4 * cx.nf_total);
+  for (int c0 = 0; c0 < cx.NC && 16 * c0 < Pmax; c0 += 32) {
+    const int c = c0 + lane, pos0 = 16 * c;
     u32 tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, th0 = 0, th1 = 0, th2 = 0, th3 = 0;  // u16 pairs: (4w,4w+2) / (4w+1,4w+3)
-    for (int m = 0; m < M; ++m) {
-      int wf = (hdr.width(m) - 1) / T + 1, hf = (hdr.height(m) - 1) / T + 1;
-      int P = (H - hf) * W + (W - wf) + 1;
-      if (P > HW) P = HW;
+    for (int m = 0; m < cx.M; ++m) {
+      const int P = cx.P(m);
+      if (16 * c0 >= P) continue;  // warp-uniform
       const int rem = P - pos0;
-      if (rem <= 0) continue;
+      const bool active = rem > 0;
       u32 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const u8* lmb = s_lm[m] + pos0;
-      const u32* l = lst + m * 4 * FEAT_SLOTS;
-      const u32* li = lim + m * 4 * FEAT_SLOTS;
-      accum_bucket<0, SAFE>(lmb, l, li, cnt[m * 4 + 0], pos0, P, a0, a1, a2, a3);
-      accum_bucket<1, SAFE>(lmb, l + FEAT_SLOTS, li + FEAT_SLOTS, cnt[m * 4 + 1], pos0, P, a0, a1, a2, a3);
-      accum_bucket<2, SAFE>(lmb, l + 2 * FEAT_SLOTS, li + 2 * FEAT_SLOTS, cnt[m * 4 + 2], pos0, P, a0, a1, a2, a3);
-      accum_bucket<3, SAFE>(lmb, l + 3 * FEAT_SLOTS, li + 3 * FEAT_SLOTS, cnt[m * 4 + 3], pos0, P, a0, a1, a2, a3);
-      if (SAFE && rem < 16) mask16(a0, a1, a2, a3, rem);
+      const u32 b = cx.hdr.bkt(m);
+      const int n0 = b & 255, n1 = (b >> 8) & 255, n2 = (b >> 16) & 255, n3 = b >> 24;
+      const u32* lst = cx.lst + m * FEAT_SLOTS;
+      accum_bucket<0, SAFE>(lmb, lst, 0, n0, active, pos0, P, cx.per_label, a0, a1, a2, a3);
+      accum_bucket<1, SAFE>(lmb, lst, n0, n1, active, pos0, P, cx.per_label, a0, a1, a2, a3);
+      accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, active, pos0, P, cx.per_label, a0, a1, a2, a3);
+      accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, active, pos0, P, cx.per_label, a0, a1, a2, a3);
+      if (SAFE && rem < 16) mask16(a0, a1, a2, a3, rem < 0 ? 0 : rem);
       tl0 += a0 & 0x00FF00FFu; th0 += (a0 >> 8) & 0x00FF00FFu;
       tl1 += a1 & 0x00FF00FFu; th1 += (a1 >> 8) & 0x00FF00FFu;
       tl2 += a2 & 0x00FF00FFu; th2 += (a2 >> 8) & 0x00FF00FFu;
       tl3 += a3 & 0x00FF00FFu; th3 += (a3 >> 8) & 0x00FF00FFu;
     }
-    u32 mask = 0;
     const u32 tl[4] = {tl0, tl1, tl2, tl3}, th[4] = {th0, th1, th2, th3};
+    u32 mask = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      mask |= ((int)(tl[w] & 0xFFFFu) > raw_thr ? 1u : 0u) << (4 * w);
-      mask |= ((int)(th[w] & 0xFFFFu) > raw_thr ? 1u : 0u) << (4 * w + 1);
-      mask |= ((int)(tl[w] >> 16) > raw_thr ? 1u : 0u) << (4 * w + 2);
-      mask |= ((int)(th[w] >> 16) > raw_thr ? 1u : 0u) << (4 * w + 3);
+      mask |= ((int)(tl[w] & 0xFFFFu) > cx.raw_thr ? 1u : 0u) << (4 * w);
+      mask |= ((int)(th[w] & 0xFFFFu) > cx.raw_thr ? 1u : 0u) << (4 * w + 1);
+      mask |= ((int)(tl[w] >> 16) > cx.raw_thr ? 1u : 0u) << (4 * w + 2);
+      mask |= ((int)(th[w] >> 16) > cx.raw_thr ? 1u : 0u) << (4 * w + 3);
     }
-    // raw scores of the hits are needed again at emission: stash them next to the bitmap
-    bm[c] = (u16)mask;
-    if (mask) {
-      u16* raw = bm + ((NC + 1) & ~1) + 16 * c;  // raw[NC][16], only touched for chunks with hits
+    if (!__any_sync(0xffffffffu, mask != 0)) continue;
+    // raster-ordered slots: exclusive prefix of per-lane hit counts
+    const int mine = __popc(mask);
+    int incl = mine;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        raw[4 * w + 0] = (u16)(tl[w] & 0xFFFFu); raw[4 * w + 1] = (u16)(th[w] & 0xFFFFu);
-        raw[4 * w + 2] = (u16)(tl[w] >> 16);     raw[4 * w + 3] = (u16)(th[w] >> 16);
-      }
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
     }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int slot = nhit + incl - mine;
+    u32 mm = mask;
+    while (mm) {
+      const int b = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const int w = b >> 2, r = b & 3;
+      const u32 word = (r & 1) ? th[w] : tl[w];
+      const int raw = (r & 2) ? (int)(word >> 16) : (int)(word & 0xFFFFu);
+      const int j = pos0 + b;
+      if (DIRECT) {
+        const int row = j / cx.W, col = j - row * cx.W;
+        Cand cd;
+        cd.tsel = isel;
+        cd.x = col * cx.T + offset;
+        cd.y = row * cx.T + offset;
+        cd.sim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), denom), 0.5f);
+        out[slot] = cd;
+      } else if (slot < CW_QCAP) {
+        queue[slot] = ((u32)j << 11) | (u32)raw;  // raw <= 4*63*MAX_MOD = 1008 < 2048; j < 2^21
+      }
+      ++slot;
+    }
+    nhit += total;
+  }
+  return nhit;
+}
+
+template <bool SAFE>
+__device__ __forceinline__ void coarse_template(const MatchParams& mp, const CoarseCtx& cx, const u8* const* s_lm, u32* queue,
+                                                int isel, int frame, int lane) {
+  const int nhit = coarse_sweep<SAFE, false>(cx, s_lm, queue, nullptr, isel, lane);
+  int base = 0, run = nhit;
+  if (lane == 0) {
+    if (nhit > 0) {
+      base = atomicAdd(&mp.cand_count[frame], nhit);
+      if (base + nhit > mp.cand_cap) { mp.overflow[frame] = 1; run = 0; }
+    }
+    mp.tpl_start[(size_t)frame * mp.nsel_stride + isel] = base;
+    mp.tpl_cnt[(size_t)frame * mp.nsel_stride + isel] = run;
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  run = __shfl_sync(0xffffffffu, run, 0);
+  if (run == 0) return;
+  Cand* out = mp.cand + (size_t)frame * mp.cand_cap + base;
+  if (nhit <= CW_QCAP) {
+    __syncwarp();
+    const int offset = cx.T / 2 + (cx.T % 2 - 1);
+    const float denom = (float)(4 * cx.nf_total);
+    for (int q = lane; q < nhit; q += 32) {
+      const u32 e = queue[q];
+      const int j = (int)(e >> 11), raw = (int)(e & 2047u);
+      const int row = j / cx.W, col = j - row * cx.W;
+      Cand cd;
+      cd.tsel = isel;
+      cd.x = col * cx.T + offset;
+      cd.y = row * cx.T + offset;
+      cd.sim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), denom), 0.5f);
+      out[q] = cd;
+    }
+  } else {
+    coarse_sweep<SAFE, true>(cx, s_lm, nullptr, out, isel, lane);
   }
 }
 
-__global__ void __launch_bounds__(256) similarity_coarse_kernel(MatchParams mp, LevelParams lp) {
-  extern __shared__ __align__(16) u32 cs_smem[];
-  const int M = mp.M;
-  u32* lst = cs_smem;                               // [M][4][64] feature offsets bucketed by word shift
-  u32* lim = lst + M * 4 * FEAT_SLOTS;              // [M][4][64] per_label - base (guard for malformed templates)
-  int* cnt = (int*)(lim + M * 4 * FEAT_SLOTS);      // [M*4]
-  int* scan = cnt + 16;                             // [10]: warp totals, base
-  u16* bm = (u16*)(scan + 12);                      // [NC] hit bitmap + [NC][16] raw scores
-
-  const int isel = blockIdx.x, frame = blockIdx.y;
-  const int g = mp.sel[isel];
-  const HdrR hdr = load_hdr(lp.hdr + g);
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const int T = lp.g.T, W = lp.g.W, H = lp.g.H, HW = W * H;
-  const int NC = (HW + 15) >> 4;
-
+__global__ void __launch_bounds__(CW_WARPS * 32) similarity_coarse_kernel(MatchParams mp, LevelParams lp) {
   __shared__ const u8* s_lm[MAX_MOD];
-  if (tid == 0) {
+  __shared__ u32 s_queue[CW_WARPS][CW_QCAP];
+  __shared__ u32 s_off[CW_WARPS][MAX_MOD * FEAT_SLOTS];
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
     s_lm[0] = lp.lm[0] + (size_t)frame * lp.lm_stride[0];
     s_lm[1] = lp.lm[1] + (size_t)frame * lp.lm_stride[1];
     s_lm[2] = lp.lm[2] + (size_t)frame * lp.lm_stride[2];
     s_lm[3] = lp.lm[3] + (size_t)frame * lp.lm_stride[3];
   }
-  if (tid < M * 4) cnt[tid] = 0;
   __syncthreads();
-  const int nf_total = hdr.nf_total();
-  for (int s = tid; s < M * FEAT_SLOTS; s += NT) {
-    int m = s / FEAT_SLOTS, k = s - m * FEAT_SLOTS;
-    if (k < hdr.nf(m)) {
-      u32 off = lp.offs[(size_t)g * M * FEAT_SLOTS + s];
-      if (off != OFF_INVALID) {
-        int b = m * 4 + ((off >> 2) & 3);
-        int pos = atomicAdd(&cnt[b], 1);
-        lst[b * FEAT_SLOTS + pos] = off;
-        lim[b * FEAT_SLOTS + pos] = lp.g.per_label - off % lp.g.per_label;
-      }
-    }
-  }
-  __syncthreads();
-  const int raw_thr = raw_threshold(nf_total, mp.threshold);
-  if (hdr.flags & 2u) coarse_body<true>(mp, lp, hdr, lst, lim, cnt, bm, NC, s_lm, raw_thr);
-  else coarse_body<false>(mp, lp, hdr, lst, lim, cnt, bm, NC, s_lm, raw_thr);
-  __syncthreads();
-
-  // ---- emission in raster order: thread t owns chunks [t*CH, (t+1)*CH)
-  const int CH = (NC + NT - 1) / NT;
-  const int cb = tid * CH, ce = min(NC, cb + CH);
-  int mine = 0;
-  for (int c = cb; c < ce; ++c) mine += __popc((u32)bm[c]);
-  // block exclusive scan
-  const int lane = tid & 31, wid = tid >> 5;
-  int incl = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) scan[wid] = incl;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int w = 0; w < (NT + 31) / 32; ++w) { int v = scan[w]; scan[w] = run; run += v; }
-    int base = 0;
-    if (run > 0) {
-      base = atomicAdd(&mp.cand_count[frame], run);
-      if (base + run > mp.cand_cap) { mp.overflow[frame] = 1; run = 0; }
-    }
-    scan[8] = base; scan[9] = run;
-    mp.tpl_start[(size_t)frame * mp.nsel_stride + isel] = base;
-    mp.tpl_cnt[(size_t)frame * mp.nsel_stride + isel] = run;
-  }
-  __syncthreads();
-  const int total = scan[9];
-  if (total == 0) return;
-  int pos = scan[8] + scan[wid] + incl - mine;
-  Cand* out = mp.cand + (size_t)frame * mp.cand_cap;
-  const int offset = T / 2 + (T % 2 - 1);
-  const float denom = (float)(4 * nf_total);
-  const u16* rawbase = bm + ((NC + 1) & ~1);
-  for (int c = cb; c < ce; ++c) {
-    u32 m = bm[c];
-    while (m) {
-      int b = __ffs(m) - 1;
-      m &= m - 1;
-      int j = 16 * c + b;
-      int r = j / W, col = j - r * W;
-      int raw = rawbase[16 * c + b];
-      Cand cd;
-      cd.tsel = isel;
-      cd.x = col * T + offset;
-      cd.y = r * T + offset;
-      cd.sim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), denom), 0.5f);
-      out[pos++] = cd;
-    }
-  }
-}
-
-static size_t coarse_smem_bytes(int M, int HW) {
-  int NC = (HW + 15) >> 4;
-  size_t b = (size_t)M * 4 * FEAT_SLOTS * 4 * 2 + 16 * 4 + 12 * 4;
-  b += (size_t)((NC + 1) & ~1) * 2 + (size_t)NC * 16 * 2;
-  return b;
+  const int isel = blockIdx.x * CW_WARPS + warp;
+  if (isel >= mp.nsel) return;
+  const int g = mp.sel[isel];
+  CoarseCtx cx;
+  cx.hdr = load_hdr(lp.hdr + g);
+  cx.M = mp.M; cx.T = lp.g.T; cx.W = lp.g.W; cx.H = lp.g.H; cx.HW = lp.g.W * lp.g.H; cx.NC = (cx.HW + 15) >> 4;
+  cx.per_label = lp.g.per_label;
+  cx.nf_total = cx.hdr.nf_total();
+  cx.raw_thr = raw_threshold(cx.nf_total, mp.threshold);
+  cx.lst = s_off[warp];
+  for (int s = lane; s < cx.M * FEAT_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * FEAT_SLOTS + s);
+  __syncwarp();
+  if (cx.hdr.flags & 2u) coarse_template<true>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
+  else coarse_template<false>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
 }
 
 void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, cudaStream_t st) {
   if (mp.nsel <= 0 || mp.frames <= 0) return;
-  int HW = lp.g.W * lp.g.H;
-  int NC = (HW + 15) >> 4;
-  int NT = ((NC + 31) / 32) * 32;
-  if (NT > 256) NT = 256;
-  if (NT < 32) NT = 32;
-  size_t smem = coarse_smem_bytes(mp.M, HW);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(similarity_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  dim3 grid(mp.nsel, mp.frames);
-  similarity_coarse_kernel<<<grid, NT, smem, st>>>(mp, lp);
+  dim3 grid((mp.nsel + CW_WARPS - 1) / CW_WARPS, mp.frames);
+  similarity_coarse_kernel<<<grid, CW_WARPS * 32, 0, st>>>(mp, lp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,21 +362,30 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       u32 a0 = 0, a1 = 0;
       const u8* lmb = s_lm[m];
       if (hdr.flags & 1u) {
-        const int shift = (cyT + rr) * W + cxT + hh * 8;
+        // One aligned LDG.128 per lane: the lane pair (hh = 0,1) of a patch row loads the two 16 B chunks of
+        // the 32 B window that contains the row's 16 unaligned bytes, swaps the two words the partner
+        // needs (2 SHFL) and realigns its own 8 bytes with selects + two funnel shifts.  16 rows = 16 lines
+        // = 16 L1 wavefronts per feature, half of what two loads per lane cost.
+        const int shift = (cyT + rr) * W + cxT;
         const u32* offp = lp.offs + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
         for (int k0 = 0; k0 < nf; k0 += 32) {
           u32 myoff = (k0 + lane < nf) ? __ldg(offp + k0 + lane) : 0u;
           const int kn = min(32, nf - k0);
 #pragma unroll 4
           for (int kk = 0; kk < kn; ++kk) {
-            u32 a = __shfl_sync(0xffffffffu, myoff, kk) + (u32)shift;
-            const uint2* p = reinterpret_cast<const uint2*>(lmb + (a & ~7u));
-            uint2 A = __ldg(p), B = __ldg(p + 1);
-            u32 sh = (a & 3u) * 8u;
-            bool up = (a & 4u) != 0;
-            u32 lo = up ? A.y : A.x, mid = up ? B.x : A.y, hi = up ? B.y : B.x;
-            a0 += __funnelshift_r(lo, mid, sh);
-            a1 += __funnelshift_r(mid, hi, sh);
+            const u32 a = __shfl_sync(0xffffffffu, myoff, kk) + (u32)shift;
+            const uint4 c = __ldg(reinterpret_cast<const uint4*>(lmb + (a & ~15u)) + hh);
+            const u32 r0 = __shfl_xor_sync(0xffffffffu, hh ? c.x : c.z, 1);
+            const u32 r1 = __shfl_xor_sync(0xffffffffu, hh ? c.y : c.w, 1);
+            // this lane's byte stream (24 B) and the offset of its 8 bytes in it is (a & 15) for both halves
+            const u32 e0 = hh ? r0 : c.x, e1 = hh ? r1 : c.y, e2 = hh ? c.x : c.z, e3 = hh ? c.y : c.w;
+            const u32 e4 = hh ? c.z : r0, e5 = hh ? c.w : r1;
+            const bool s2 = (a & 8u) != 0, s1 = (a & 4u) != 0;
+            const u32 u0 = s2 ? e2 : e0, u1 = s2 ? e3 : e1, u2 = s2 ? e4 : e2, u3 = s2 ? e5 : e3;
+            const u32 v0 = s1 ? u1 : u0, v1 = s1 ? u2 : u1, v2 = s1 ? u3 : u2;
+            const u32 sh = (a & 3u) * 8u;
+            a0 += __funnelshift_r(v0, v1, sh);
+            a1 += __funnelshift_r(v1, v2, sh);
           }
         }
       } else {

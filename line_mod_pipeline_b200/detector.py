@@ -250,6 +250,23 @@ class Detector:
             self._out_cache = buf
         return buf
 
+    def prepareBatch(self, frames, cap=None):
+        """Marshals a frame list once (ctypes image array + result buffers) so repeated matchPrepared() calls
+        cost exactly one lmb200_match_batch C-ABI call — what a C/C++ caller pays."""
+        arr, keep, nsrc = self._frames(frames)
+        cap = cap or 1024 * len(frames)
+        return dict(arr=arr, keep=keep, nsrc=nsrc, n=len(frames), cap=cap, out=np.empty(cap, MATCH_DTYPE),
+                    offs=(C.c_size_t * (len(frames) + 1))())
+
+    def matchPrepared(self, prep, threshold, class_ids=()):
+        ids, nids = _cstr_array(class_ids)
+        rc = self._check(self._L.lmb200_match_batch(self._h, prep["arr"], prep["n"], prep["nsrc"], C.c_float(threshold), ids, nids,
+                                                    prep["out"].ctypes.data_as(C.POINTER(K.MatchRec)), prep["cap"], prep["offs"]),
+                         allow=(K.E_TRUNCATED,))
+        if rc == K.E_TRUNCATED:
+            raise LinemodError(rc, "prepared output buffer too small: need %d records" % prep["offs"][prep["n"]])
+        return int(prep["offs"][prep["n"]])
+
     def uploadFrames(self, frames, first_slot=0):
         arr, keep, nsrc = self._frames(frames)
         self._check(self._L.lmb200_upload_frames(self._h, arr, len(frames), nsrc, first_slot))
