@@ -103,18 +103,18 @@ void lmb200_destroy(lmb200_handle h) {
       for (int m = 0; m < LMB200_MAX_MODALITIES; ++m) { lb.bgr[m].release(); lb.q[m].release(); lb.mask[m].release(); lb.lm[m].release(); }
     for (int m = 0; m < LMB200_MAX_MODALITIES; ++m) { h->d_depth[m].release(); h->d_dnraw[m].release(); }
     for (int l = 0; l < LMB200_MAX_LEVELS; ++l) { h->d_hdr[l].release(); h->d_feat[l].release(); h->d_offs[l].release(); }
-    lmh::DevBuf* bufs[] = {&h->d_table, &h->d_normal_lut, &h->d_sel, &h->d_mag, &h->d_dnidx, &h->d_cand, &h->d_cand_count,
-                           &h->d_tpl_start, &h->d_tpl_cnt, &h->d_overflow, &h->d_stats, &h->d_out, &h->d_out_count,
-                           &h->d_gather_send, &h->d_gather_recv};
+    lmh::DevBuf* bufs[] = {&h->d_table, &h->d_normal_lut, &h->d_sel, &h->d_mag, &h->d_dnidx, &h->d_cand, &h->d_ctr,
+                           &h->d_tpl_start, &h->d_tpl_cnt, &h->d_out, &h->d_gather_send, &h->d_gather_recv};
     for (auto* b : bufs) b->release();
-    if (h->h_out_count) cudaFreeHost(h->h_out_count);
-    if (h->h_overflow) cudaFreeHost(h->h_overflow);
-    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_gather) cudaFreeHost(h->h_gather);
+    if (h->b_count) cudaFreeHost(h->b_count);
+    if (h->b_out) cudaFreeHost(h->b_out);
+    for (auto e : h->b_events) cudaEventDestroy(e);
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       if (h->lanes[i].done) cudaEventDestroy(h->lanes[i].done);
       if (h->lanes[i].stream) cudaStreamDestroy(h->lanes[i].stream);
     }

@@ -69,7 +69,7 @@ int ensure_device(lmb200_detector* h) {
   if (dev >= n) return set_error(h, LMB200_E_INVALID, "device ordinal out of range");
   CU(cudaSetDevice(dev));
   h->device = dev;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     CU(cudaStreamCreateWithFlags(&h->lanes[i].stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->lanes[i].done, cudaEventDisableTiming));
   }
@@ -175,11 +175,9 @@ static int rebuild_templates(lmb200_detector* h) {
 }
 
 static void free_host_mirrors(lmb200_detector* h) {
-  if (h->h_out_count) cudaFreeHost(h->h_out_count);
-  if (h->h_overflow) cudaFreeHost(h->h_overflow);
-  if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_out) cudaFreeHost(h->h_out);
-  h->h_out_count = nullptr; h->h_overflow = nullptr; h->h_stats = nullptr; h->h_out = nullptr;
+  h->h_ctr = nullptr; h->h_out = nullptr;
 }
 
 static int alloc_match_buffers(lmb200_detector* h) {
@@ -187,17 +185,12 @@ static int alloc_match_buffers(lmb200_detector* h) {
   h->nsel_stride = std::max(1, h->ntpl);
   ALLOC(h->d_cand, (size_t)S * h->cand_cap * sizeof(Cand));
   ALLOC(h->d_out, (size_t)S * h->out_cap * sizeof(Cand));
-  ALLOC(h->d_cand_count, (size_t)S * sizeof(int));
-  ALLOC(h->d_out_count, (size_t)S * sizeof(int));
-  ALLOC(h->d_overflow, (size_t)S * sizeof(int));
-  ALLOC(h->d_stats, (size_t)S * sizeof(unsigned long long));
+  ALLOC(h->d_ctr, (size_t)S * sizeof(SlotCtr));
   ALLOC(h->d_tpl_start, (size_t)S * h->nsel_stride * sizeof(int));
   ALLOC(h->d_tpl_cnt, (size_t)S * h->nsel_stride * sizeof(int));
   free_host_mirrors(h);
   h->h_head = std::min(h->out_cap, 1024);
-  CU(cudaHostAlloc((void**)&h->h_out_count, (size_t)S * sizeof(int), cudaHostAllocDefault));
-  CU(cudaHostAlloc((void**)&h->h_overflow, (size_t)S * sizeof(int), cudaHostAllocDefault));
-  CU(cudaHostAlloc((void**)&h->h_stats, (size_t)S * sizeof(unsigned long long), cudaHostAllocDefault));
+  CU(cudaHostAlloc((void**)&h->h_ctr, (size_t)S * sizeof(SlotCtr), cudaHostAllocDefault));
   CU(cudaHostAlloc((void**)&h->h_out, (size_t)S * h->out_cap * sizeof(Cand), cudaHostAllocDefault));
   h->slot_threshold.assign(S, 0.f);
   return LMB200_OK;
@@ -425,12 +418,10 @@ static MatchParams make_match_params(lmb200_detector* h, int first, int count, f
   mp.threshold = threshold;
   mp.cand = h->d_cand.as<Cand>() + (size_t)first * h->cand_cap;
   mp.cand_cap = h->cand_cap;
-  mp.cand_count = h->d_cand_count.as<int>() + first;
+  mp.ctr = h->d_ctr.as<SlotCtr>() + first;
   mp.nsel_stride = h->nsel_stride;
   mp.tpl_start = h->d_tpl_start.as<int>() + (size_t)first * h->nsel_stride;
   mp.tpl_cnt = h->d_tpl_cnt.as<int>() + (size_t)first * h->nsel_stride;
-  mp.overflow = h->d_overflow.as<int>() + first;
-  mp.stats = h->d_stats.as<unsigned long long>() + first;
   return mp;
 }
 
@@ -455,10 +446,7 @@ static int run_matching(lmb200_detector* h, int first, int count, float threshol
                         bool stop_after_coarse = false) {
   const int L = h->cfg.pyramid_levels;
   MatchParams mp = make_match_params(h, first, count, threshold);
-  CU(cudaMemsetAsync(mp.cand_count, 0, sizeof(int) * count, st));
-  CU(cudaMemsetAsync(mp.overflow, 0, sizeof(int) * count, st));
-  CU(cudaMemsetAsync(mp.stats, 0, sizeof(unsigned long long) * count, st));
-  CU(cudaMemsetAsync(h->d_out_count.as<int>() + first, 0, sizeof(int) * count, st));
+  CU(cudaMemsetAsync(mp.ctr, 0, sizeof(SlotCtr) * count, st));
   if (mp.nsel > 0) {
     {
       ProfScope ps(h, LMB200_K_SIM_COARSE, st);
@@ -470,7 +458,7 @@ static int run_matching(lmb200_detector* h, int first, int count, float threshol
         launch_similarity_local(mp, make_level_params(h, l, first), st);
       }
     ProfScope ps(h, LMB200_K_PACK, st);
-    launch_pack(mp, h->d_out.as<Cand>() + (size_t)first * h->out_cap, h->out_cap, h->d_out_count.as<int>() + first, st);
+    launch_pack(mp, h->d_out.as<Cand>() + (size_t)first * h->out_cap, h->out_cap, st);
   }
   CU(cudaGetLastError());
   for (int i = 0; i < count; ++i) h->slot_threshold[first + i] = threshold;
@@ -490,19 +478,16 @@ static int grow_capacity(lmb200_detector* h) {
 // index in .tsel).  Returns +1 (nothing consumed) when a device-side store overflowed: the caller
 // grows the stores (grow_capacity) and redoes the template side — linear memories stay resident.
 static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out) {
-  CU(cudaMemcpyAsync(h->h_out_count + first, h->d_out_count.as<int>() + first, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_overflow + first, h->d_overflow.as<int>() + first, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_stats + first, h->d_stats.as<unsigned long long>() + first, sizeof(unsigned long long) * count,
-                     cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_ctr + first, h->d_ctr.as<SlotCtr>() + first, sizeof(SlotCtr) * count, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpy2DAsync(h->h_out + (size_t)first * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
                        h->d_out.as<Cand>() + (size_t)first * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
                        (size_t)h->h_head * sizeof(Cand), count, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   for (int i = 0; i < count; ++i)
-    if (h->h_overflow[first + i] != 0 || h->h_out_count[first + i] > h->out_cap) return 1;
+    if (h->h_ctr[first + i].overflow != 0 || h->h_ctr[first + i].out_count > h->out_cap) return 1;
   bool any_tail = false;
   for (int i = 0; i < count; ++i) {
-    int n = h->h_out_count[first + i];
+    int n = h->h_ctr[first + i].out_count;
     if (n > h->h_head) {
       any_tail = true;
       CU(cudaMemcpyAsync(h->h_out + (size_t)(first + i) * h->out_cap + h->h_head,
@@ -513,10 +498,10 @@ static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, 
   if (any_tail) CU(cudaStreamSynchronize(st));
   out.resize(count);
   for (int i = 0; i < count; ++i) {
-    int n = h->h_out_count[first + i];
+    int n = h->h_ctr[first + i].out_count;
     const Cand* src = h->h_out + (size_t)(first + i) * h->out_cap;
     out[i].assign(src, src + n);
-    h->prof.bytes_local += (long long)h->h_stats[first + i];
+    h->prof.bytes_local += (long long)h->h_ctr[first + i].local_bytes;
   }
   if (h->profiling) collect_profile(h);
   return LMB200_OK;
@@ -633,7 +618,7 @@ int lmb200_fetch_resident(lmb200_handle h, int first_slot, int count, lmb200_mat
 int lmb200_synchronize(lmb200_handle h) {
   if (!h || !h->device_ready) return LMB200_OK;
   cudaSetDevice(h->device);
-  for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(h->lanes[i].stream));
+  for (int i = 0; i < 3; ++i) CU(cudaStreamSynchronize(h->lanes[i].stream));
   if (h->profiling) collect_profile(h);
   return LMB200_OK;
 }
@@ -743,70 +728,112 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
   return rc;
 }
 
-// Streaming batch: two lanes, each owning half of the slots; while lane A's chunk is being
-// post-processed on the host (sort/unique), lane B's chunk is copying/computing.
+// Streaming batch.  Stream C (copy) brings chunks of frames into one of G slot groups, stream X
+// (compute) runs the whole path on them and copies counts + list heads into per-frame pinned staging;
+// the two are chained by events only, so the host enqueues the ENTIRE batch without blocking and then
+// finalises chunk after chunk (sort/unique) while later chunks are still copying/computing.
+//   C:  [wait done(k-G)] H2D(k) rec h2d(k)          X:  [wait h2d(k)] kernels(k) D2H(k) rec done(k)
 int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
                        const char* const* class_ids, int n_class_ids, lmb200_match_rec* out, size_t cap, size_t* offsets) {
   int rc = prepare(h, frames, n_frames, n_sources, class_ids, n_class_ids);
   if (rc) return rc;
   h->masks_in_use = false;
-restart:
-  const int half = std::max(1, h->slots / 2);
-  int chunk = std::min(half, 8);
-  if (const char* e = std::getenv("LMB200_CHUNK")) chunk = std::max(1, std::min(half, std::atoi(e)));
-  struct Pending { int first_frame, count, slot0, lane; };
-  std::vector<Pending> inflight;
-  size_t base = 0;
-  int status = LMB200_OK;
-  std::vector<Match> m;
-  auto drain = [&](const Pending& p) -> int {
-    std::vector<std::vector<Cand>> raw;
-    int r = fetch_raw(h, p.slot0, p.count, h->lanes[p.lane].stream, raw);
-    if (r) return r;  // +1: stores overflowed, the whole batch is restarted with larger ones
-    for (int i = 0; i < p.count; ++i) {
-      to_matches(h, raw[i], m);
-      h->prof.candidates += (long long)raw[i].size();
-      finalize_matches(m);
-      h->prof.matches += (long long)m.size();
-      size_t n = 0;
-      if (offsets) offsets[p.first_frame + i] = base;
-      if (emit(h, m, out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
-      base += n;
+  cudaStream_t Xs[2] = {h->lanes[0].stream, h->lanes[2].stream}, Cs = h->lanes[1].stream;
+  for (;;) {
+    const int G = h->slots >= 6 ? 3 : (h->slots >= 2 ? 2 : 1);
+    const int gs = h->slots / G;
+    int chunk = std::min(gs, 12);
+    if (const char* e = std::getenv("LMB200_CHUNK")) chunk = std::max(1, std::min(gs, std::atoi(e)));
+    const int nchunks = (n_frames + chunk - 1) / chunk;
+    // per-frame pinned staging for the results of this batch
+    if (h->b_frames < n_frames || h->b_head != h->h_head) {
+      if (h->b_count) cudaFreeHost(h->b_count);
+      if (h->b_out) cudaFreeHost(h->b_out);
+      h->b_count = nullptr; h->b_out = nullptr;
+      CU(cudaHostAlloc((void**)&h->b_count, (size_t)n_frames * sizeof(SlotCtr), cudaHostAllocDefault));
+      CU(cudaHostAlloc((void**)&h->b_out, (size_t)n_frames * h->h_head * sizeof(Cand), cudaHostAllocDefault));
+      h->b_frames = n_frames; h->b_head = h->h_head;
     }
-    return LMB200_OK;
-  };
-  int lane = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
-    int cnt = std::min(chunk, n_frames - f0);
-    if (inflight.size() == 2) {  // lane about to be reused: drain its previous chunk first
-      rc = drain(inflight.front());
-      if (rc > 0) { rc = grow_capacity(h); if (rc) return rc; goto restart; }
-      if (rc) return rc;
-      inflight.erase(inflight.begin());
+    SlotCtr* b_ctr = (SlotCtr*)h->b_count;
+    while ((int)h->b_events.size() < 2 * nchunks) {
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      h->b_events.push_back(ev);
     }
-    int slot0 = lane * half;
-    cudaStream_t st = h->lanes[lane].stream;
-    {
-      ProfScope ps(h, LMB200_K_UPLOAD, st);
+    const bool trace = std::getenv("LMB200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;  // trace: 4 timing events per chunk (copy start/end, compute start/end)
+    if (trace) { tev.resize(4 * (size_t)nchunks); for (auto& e : tev) cudaEventCreate(&e); }
+    for (int k = 0; k < nchunks; ++k) {
+      const int f0 = k * chunk, cnt = std::min(chunk, n_frames - f0), slot0 = (k % G) * gs;
+      cudaEvent_t ev_h2d = h->b_events[2 * k], ev_done = h->b_events[2 * k + 1];
+      cudaStream_t X = Xs[k & 1];  // adjacent chunks overlap on two compute streams (fills the low-parallelism tails)
+      if (k >= G) CU(cudaStreamWaitEvent(Cs, h->b_events[2 * (k - G) + 1], 0));  // slot group free again
+      if (trace) cudaEventRecord(tev[4 * k], Cs);
       for (int i = 0; i < cnt; ++i) {
-        rc = upload_one(h, frames + (size_t)(f0 + i) * n_sources, slot0 + i, st);
+        rc = upload_one(h, frames + (size_t)(f0 + i) * n_sources, slot0 + i, Cs);
         if (rc) return rc;
       }
+      h->prof.launches[LMB200_K_UPLOAD]++;
+      CU(cudaEventRecord(ev_h2d, Cs));
+      if (trace) cudaEventRecord(tev[4 * k + 1], Cs);
+      CU(cudaStreamWaitEvent(X, ev_h2d, 0));
+      if (trace) cudaEventRecord(tev[4 * k + 2], X);
+      rc = run_frame_side(h, slot0, cnt, X);
+      if (rc) return rc;
+      rc = run_matching(h, slot0, cnt, threshold, X);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(b_ctr + f0, h->d_ctr.as<SlotCtr>() + slot0, sizeof(SlotCtr) * cnt, cudaMemcpyDeviceToHost, X));
+      CU(cudaMemcpy2DAsync(h->b_out + (size_t)f0 * h->h_head, (size_t)h->h_head * sizeof(Cand),
+                           h->d_out.as<Cand>() + (size_t)slot0 * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
+                           (size_t)h->h_head * sizeof(Cand), cnt, cudaMemcpyDeviceToHost, X));
+      CU(cudaEventRecord(ev_done, X));
+      if (trace) cudaEventRecord(tev[4 * k + 3], X);
     }
-    rc = run_frame_side(h, slot0, cnt, st);
-    if (rc) return rc;
-    rc = run_matching(h, slot0, cnt, threshold, st);
-    if (rc) return rc;
-    inflight.push_back(Pending{f0, cnt, slot0, lane});
-    lane ^= 1;
+    if (trace) {
+      cudaDeviceSynchronize();
+      for (int k = 0; k < nchunks; ++k) {
+        float t[4];
+        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[4 * k + j]);
+        std::fprintf(stderr, "[lmb200 trace] chunk %2d: h2d %.3f..%.3f  compute %.3f..%.3f ms\n", k, t[0], t[1], t[2], t[3]);
+      }
+      for (auto& e : tev) cudaEventDestroy(e);
+    }
+    // finalise in frame order while the GPU works on later chunks
+    size_t base = 0;
+    int status = LMB200_OK;
+    bool redo = false;
+    std::vector<Cand> raw;
+    std::vector<Match> m;
+    for (int k = 0; k < nchunks && !redo; ++k) {
+      const int f0 = k * chunk, cnt = std::min(chunk, n_frames - f0);
+      CU(cudaEventSynchronize(h->b_events[2 * k + 1]));
+      for (int i = 0; i < cnt; ++i) {
+        const int f = f0 + i, n = b_ctr[f].out_count;
+        if (b_ctr[f].overflow || n > h->out_cap || n > h->h_head) { redo = true; break; }
+        raw.assign(h->b_out + (size_t)f * h->h_head, h->b_out + (size_t)f * h->h_head + n);
+        h->prof.bytes_local += (long long)b_ctr[f].local_bytes;
+        to_matches(h, raw, m);
+        h->prof.candidates += (long long)raw.size();
+        finalize_matches(m);
+        h->prof.matches += (long long)m.size();
+        size_t w = 0;
+        if (offsets) offsets[f] = base;
+        if (emit(h, m, out, cap, base, &w) != LMB200_OK) status = LMB200_E_TRUNCATED;
+        base += w;
+      }
+    }
+    if (redo) {  // a candidate store or the staged list head was too small: grow and rerun the batch
+      CU(cudaDeviceSynchronize());
+      bool store = false;
+      for (int f = 0; f < n_frames; ++f) store |= b_ctr[f].overflow != 0 || b_ctr[f].out_count > h->out_cap;
+      if (store) { rc = grow_capacity(h); if (rc) return rc; }
+      else h->h_head = std::min(h->out_cap, h->h_head * 4);
+      continue;
+    }
+    if (h->profiling) { CU(cudaStreamSynchronize(Xs[0])); CU(cudaStreamSynchronize(Xs[1])); collect_profile(h); }
+    if (offsets) offsets[n_frames] = base;
+    return status;
   }
-  for (auto& p : inflight) {
-    rc = drain(p);
-    if (rc > 0) { rc = grow_capacity(h); if (rc) return rc; goto restart; }
-    if (rc) return rc;
-  }
-  if (offsets) offsets[n_frames] = base;
-  return status;
 }
 
 int lmb200_host_alloc(size_t bytes, void** out) {
@@ -825,7 +852,7 @@ int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset) {
   if (!h || !out) return LMB200_E_INVALID;
   if (h->device_ready && h->profiling) {
     cudaSetDevice(h->device);
-    for (int i = 0; i < 2; ++i) cudaStreamSynchronize(h->lanes[i].stream);
+    for (int i = 0; i < 3; ++i) cudaStreamSynchronize(h->lanes[i].stream);
     collect_profile(h);
   }
   *out = h->prof;
@@ -1016,12 +1043,10 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   const int world = h->comm_world;
   // 1. local overflow check (a rank that overflowed redoes its own template side; no collective involved)
   for (;;) {
-    CU(cudaMemcpyAsync(h->h_overflow + first_slot, h->d_overflow.as<int>() + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->h_out_count + first_slot, h->d_out_count.as<int>() + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->h_stats + first_slot, h->d_stats.as<unsigned long long>() + first_slot, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_ctr + first_slot, h->d_ctr.as<SlotCtr>() + first_slot, sizeof(SlotCtr) * count, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     bool over = false;
-    for (int i = 0; i < count; ++i) over |= h->h_overflow[first_slot + i] != 0 || h->h_out_count[first_slot + i] > h->out_cap;
+    for (int i = 0; i < count; ++i) over |= h->h_ctr[first_slot + i].overflow != 0 || h->h_ctr[first_slot + i].out_count > h->out_cap;
     if (!over) break;
     float thr = h->slot_threshold[first_slot];
     int rc = grow_capacity(h);
@@ -1029,19 +1054,22 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     rc = run_matching(h, first_slot, count, thr, st);
     if (rc) return rc;
   }
-  for (int i = 0; i < count; ++i) h->prof.bytes_local += (long long)h->h_stats[first_slot + i];
+  for (int i = 0; i < count; ++i) h->prof.bytes_local += (long long)h->h_ctr[first_slot + i].local_bytes;
   // 2. fixed-capacity send buffer per frame: record 0 = {count,..}, then up to gather_cap records.
   //    Every rank sees every count after the gather, so all ranks take the same grow decision.
-  if (h->gather_cap <= 0) h->gather_cap = 2048;
+  if (h->gather_cap <= 0) h->gather_cap = 255;  // 4 KB per frame and rank; doubles when a list is longer
   for (;;) {
     const size_t pitch = (size_t)(1 + h->gather_cap) * sizeof(Cand);
     const size_t bytes = pitch * count;
     ALLOC(h->d_gather_send, bytes);
     ALLOC(h->d_gather_recv, bytes * world);
-    if (h->h_gather) { cudaFreeHost(h->h_gather); h->h_gather = nullptr; }
-    CU(cudaHostAlloc((void**)&h->h_gather, bytes * world, cudaHostAllocDefault));
+    if (h->h_gather_bytes < bytes * world) {
+      if (h->h_gather) { cudaFreeHost(h->h_gather); h->h_gather = nullptr; }
+      CU(cudaHostAlloc((void**)&h->h_gather, bytes * world, cudaHostAllocDefault));
+      h->h_gather_bytes = bytes * world;
+    }
     CU(cudaMemsetAsync(h->d_gather_send.p, 0, bytes, st));
-    CU(cudaMemcpy2DAsync(h->d_gather_send.p, pitch, h->d_out_count.as<int>() + first_slot, sizeof(int), sizeof(int), count,
+    CU(cudaMemcpy2DAsync(h->d_gather_send.p, pitch, &h->d_ctr.as<SlotCtr>()[first_slot].out_count, sizeof(SlotCtr), sizeof(int), count,
                          cudaMemcpyDeviceToDevice, st));
     size_t w = (size_t)std::min(h->gather_cap, h->out_cap) * sizeof(Cand);
     CU(cudaMemcpy2DAsync((char*)h->d_gather_send.p + sizeof(Cand), pitch, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap,

@@ -75,7 +75,7 @@ struct lmb200_detector {
   // ---- device ----
   bool device_ready = false;
   int device = -1;
-  lmh::Lane lanes[2];
+  lmh::Lane lanes[3];   // 0: compute, 1: copy, 2: second compute lane of the batch path
   lmh::DevBuf d_table, d_normal_lut;
   bool luts_dirty = true;
 
@@ -100,13 +100,16 @@ struct lmb200_detector {
   std::vector<lmh::LevelBuffers> levels;
   lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
   size_t depth_stride = 0;
-  lmh::DevBuf d_cand, d_cand_count, d_tpl_start, d_tpl_cnt, d_overflow, d_stats, d_out, d_out_count;
+  lmh::DevBuf d_cand, d_ctr, d_tpl_start, d_tpl_cnt, d_out;
   int nsel_stride = 0;
   // pinned host mirrors
-  int* h_out_count = nullptr; int* h_overflow = nullptr; unsigned long long* h_stats = nullptr;
+  lmk::SlotCtr* h_ctr = nullptr;
   lmk::Cand* h_out = nullptr; int h_head = 0;      // first h_head records of every slot
   void* h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for pageable/strided inputs
   std::vector<float> slot_threshold;
+  // per-frame pinned staging of lmb200_match_batch
+  void* b_count = nullptr; lmk::Cand* b_out = nullptr; int b_frames = 0, b_head = 0;
+  std::vector<cudaEvent_t> b_events;
 
   // profiling
   bool profiling = false;
@@ -118,7 +121,7 @@ struct lmb200_detector {
   // comm
   void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
   lmh::DevBuf d_gather_send, d_gather_recv; int gather_cap = 0;
-  lmk::Cand* h_gather = nullptr;
+  lmk::Cand* h_gather = nullptr; size_t h_gather_bytes = 0;
 
   // scratch for lmb200_get_template
   std::vector<lmb200_feature> tmp_features;

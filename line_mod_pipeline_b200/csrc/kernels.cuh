@@ -64,6 +64,15 @@ struct Cand {
   float sim;                          // < 0 : filtered out
 };
 
+// Per-slot device counters, one contiguous record so a chunk needs one memset and one D2H copy.
+struct SlotCtr {
+  int cand_count;                     // coarse candidates appended (may exceed the store: overflow)
+  int overflow;                       // candidate store overflowed -> host grows it and redoes the frame
+  int out_count;                      // surviving matches written by pack_kernel
+  int pad;
+  unsigned long long local_bytes;     // algorithmic bytes gathered by similarityLocal (sum nf*256)
+};
+
 struct LevelGeom {
   int T, rows, cols, W, H;            // quantized image size; W=cols/T, H=rows/T
   u32 per_label;                      // T*T*W*H
@@ -100,11 +109,9 @@ struct MatchParams {
   float threshold;
   // candidate store, per frame
   Cand* cand; int cand_cap;
-  int* cand_count;                    // [frames]
+  SlotCtr* ctr;                       // [frames]
   int* tpl_start; int* tpl_cnt;       // [frames][nsel_stride]
   int nsel_stride;
-  int* overflow;                      // [frames]
-  unsigned long long* stats;          // [frames]: algorithmic bytes gathered by similarityLocal (nullable)
 };
 
 struct LevelParams {
@@ -116,6 +123,6 @@ struct LevelParams {
 void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
 void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
 // Ordered compaction: out[frame][0..n) in generation order, count[frame] = n (may exceed cap -> overflow).
-void launch_pack(const MatchParams& mp, Cand* out, int out_cap, int* out_count, cudaStream_t st);
+void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st);
 
 }  // namespace lmk

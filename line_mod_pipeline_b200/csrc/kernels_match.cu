@@ -254,8 +254,8 @@ __device__ __forceinline__ void coarse_template(const MatchParams& mp, const Coa
   int base = 0, run = nhit;
   if (lane == 0) {
     if (nhit > 0) {
-      base = atomicAdd(&mp.cand_count[frame], nhit);
-      if (base + nhit > mp.cand_cap) { mp.overflow[frame] = 1; run = 0; }
+      base = atomicAdd(&mp.ctr[frame].cand_count, nhit);
+      if (base + nhit > mp.cand_cap) { mp.ctr[frame].overflow = 1; run = 0; }
     }
     mp.tpl_start[(size_t)frame * mp.nsel_stride + isel] = base;
     mp.tpl_cnt[(size_t)frame * mp.nsel_stride + isel] = run;
@@ -328,8 +328,8 @@ void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, cuda
 __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, LevelParams lp) {
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (mp.overflow[frame]) return;  // candidate store overflowed: the host grows it and redoes this frame
-  const int n = min(mp.cand_count[frame], mp.cand_cap);
+  if (mp.ctr[frame].overflow) return;  // candidate store overflowed: the host grows it and redoes this frame
+  const int n = min(mp.ctr[frame].cand_count, mp.cand_cap);
   const int T = lp.g.T, W = lp.g.W, M = mp.M;
   const int border = 8 * T, offset = T / 2 + (T % 2 - 1);
   const u32 plane = (u32)W * lp.g.H;
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       float sim = __fdiv_rn(__fmul_rn((float)bs, 100.f), (float)(4 * nfl));
       rec.sim = sim < mp.threshold ? -1.0f : sim;
       cands[c] = rec;
-      if (mp.stats) atomicAdd(&mp.stats[frame], (unsigned long long)nfl * 256ull);
+      atomicAdd(&mp.ctr[frame].local_bytes, (unsigned long long)nfl * 256ull);
     }
   }
 }
@@ -444,47 +444,45 @@ void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaS
 // ---------------------------------------------------------------------------------------------
 // Ordered compaction: surviving candidates of frame f in (selection order, raster order).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __restrict__ out, int out_cap,
-                                                    int* __restrict__ out_count) {
+__global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __restrict__ out, int out_cap) {
   __shared__ int wsum[32];
-  __shared__ int s_run, s_total;
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const Cand* cands = mp.cand + (size_t)frame * mp.cand_cap;
   Cand* o = out + (size_t)frame * out_cap;
-  if (tid == 0) s_run = 0;
-  __syncthreads();
-  if (mp.overflow[frame]) {  // host will grow the store and redo this frame
-    if (tid == 0) out_count[frame] = 0;
-    return;
+  if (mp.ctr[frame].overflow) return;  // host will grow the store and redo this frame
+  // thread t owns the contiguous template range [t*per, (t+1)*per): one scan for the whole selection
+  const int per = (mp.nsel + 1023) >> 10;
+  const int i0 = tid * per, i1 = min(mp.nsel, i0 + per);
+  const int* ts = mp.tpl_start + (size_t)frame * mp.nsel_stride;
+  const int* tc = mp.tpl_cnt + (size_t)frame * mp.nsel_stride;
+  int alive = 0;
+  for (int i = i0; i < i1; ++i) {
+    const int st = ts[i], cn = tc[i];
+    for (int j = 0; j < cn; ++j) alive += cands[st + j].sim >= 0.f;
   }
-  for (int i0 = 0; i0 < mp.nsel; i0 += 1024) {
-    const int i = i0 + tid;
-    int st = 0, cn = 0, alive = 0;
-    if (i < mp.nsel) {
-      st = mp.tpl_start[(size_t)frame * mp.nsel_stride + i];
-      cn = mp.tpl_cnt[(size_t)frame * mp.nsel_stride + i];
-      for (int j = 0; j < cn; ++j) alive += cands[st + j].sim >= 0.f;
-    }
-    int incl = alive;
+  int incl = alive;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = wsum[lane], inc2 = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
+      int u = __shfl_up_sync(0xffffffffu, inc2, d);
+      if (lane >= d) inc2 += u;
     }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      int v = wsum[lane], inc2 = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, inc2, d);
-        if (lane >= d) inc2 += u;
-      }
-      wsum[lane] = inc2 - v;          // exclusive warp offsets
-      if (lane == 31) s_total = inc2; // candidates surviving in this round of 1024 templates
-    }
-    __syncthreads();
-    int pos = s_run + wsum[wid] + incl - alive;
+    wsum[lane] = inc2 - v;               // exclusive warp offsets
+    if (lane == 31) mp.ctr[frame].out_count = inc2;
+  }
+  __syncthreads();
+  if (alive == 0) return;
+  int pos = wsum[wid] + incl - alive;
+  for (int i = i0; i < i1; ++i) {
+    const int st = ts[i], cn = tc[i];
     for (int j = 0; j < cn; ++j) {
       Cand cd = cands[st + j];
       if (cd.sim >= 0.f) {
@@ -493,16 +491,12 @@ __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __rest
         ++pos;
       }
     }
-    __syncthreads();
-    if (tid == 0) s_run += s_total;
-    __syncthreads();
   }
-  if (tid == 0) out_count[frame] = s_run;
 }
 
-void launch_pack(const MatchParams& mp, Cand* out, int out_cap, int* out_count, cudaStream_t st) {
+void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st) {
   if (mp.frames <= 0) return;
-  pack_kernel<<<mp.frames, 1024, 0, st>>>(mp, out, out_cap, out_count);
+  pack_kernel<<<mp.frames, 1024, 0, st>>>(mp, out, out_cap);
 }
 
 }  // namespace lmk
