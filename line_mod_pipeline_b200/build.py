@@ -31,7 +31,8 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
+    extra = os.environ.get("LMB200_NVCC_EXTRA", "").split()
+    if not force and not needs_build() and not extra:
         return SO
     objs = []
     odir = os.path.join(HERE, "build")
@@ -39,7 +40,7 @@ def build(force=False, verbose=False):
     log = []
     for s in SOURCES:
         o = os.path.join(odir, s.rsplit(".", 1)[0] + ".o")
-        cmd = [nvcc()] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc()] + NVCC_FLAGS + extra + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:

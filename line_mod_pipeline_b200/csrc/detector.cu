@@ -140,6 +140,7 @@ static int rebuild_templates(lmb200_detector* h) {
     ++ci;
   }
   h->ntpl = (int)h->g_class.size();
+  h->max_nf_coarse = 0;
   std::vector<TplHdr> hdr((size_t)std::max(1, h->ntpl));
   std::vector<u32> feat((size_t)std::max(1, h->ntpl) * M * FEAT_SLOTS);
   for (int l = 0; l < L; ++l) {
@@ -149,6 +150,7 @@ static int rebuild_templates(lmb200_detector* h) {
       for (auto& tp : kv.second) {
         TplHdr& hd = hdr[g];
         std::memset(&hd, 0, sizeof(hd));
+        int nf_sum = 0;
         for (int m = 0; m < M; ++m) {
           const Template& t = tp[(size_t)l * M + m];
           if (t.features.size() > 63)
@@ -156,9 +158,11 @@ static int rebuild_templates(lmb200_detector* h) {
           hd.width[m] = (short)std::max(-32768, std::min(32767, t.width));
           hd.height[m] = (short)std::max(-32768, std::min(32767, t.height));
           hd.nf[m] = (u8)t.features.size();
+          nf_sum += (int)t.features.size();
           for (size_t k = 0; k < t.features.size(); ++k)
             feat[((size_t)g * M + m) * FEAT_SLOTS + k] = pack_feature(t.features[k].x, t.features[k].y, t.features[k].label);
         }
+        if (l == L - 1) h->max_nf_coarse = std::max(h->max_nf_coarse, nf_sum);
         ++g;
       }
     ALLOC(h->d_hdr[l], hdr.size() * sizeof(TplHdr));
@@ -188,6 +192,7 @@ static int alloc_match_buffers(lmb200_detector* h) {
   ALLOC(h->d_ctr, (size_t)S * sizeof(SlotCtr));
   ALLOC(h->d_tpl_start, (size_t)S * h->nsel_stride * sizeof(int));
   ALLOC(h->d_tpl_cnt, (size_t)S * h->nsel_stride * sizeof(int));
+  ALLOC(h->d_tpl_alive, (size_t)S * h->nsel_stride * sizeof(int));
   free_host_mirrors(h);
   h->h_head = std::min(h->out_cap, 1024);
   CU(cudaHostAlloc((void**)&h->h_ctr, (size_t)S * sizeof(SlotCtr), cudaHostAllocDefault));
@@ -232,6 +237,11 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
         ALLOC(lb.q[m], lb.q_stride * S);
         ALLOC(lb.lm[m], lb.lm_stride * S);
         CU(cudaMemset(lb.lm[m].p, 0, lb.lm_stride * S));  // the pad bytes stay zero forever
+        if (l == L - 1) {  // nibble-packed copy read by similarity_coarse_kernel
+          lb.lmn_stride = up256((size_t)4 * r * c + LM_PAD);
+          ALLOC(lb.lmn[m], lb.lmn_stride * S);
+          CU(cudaMemset(lb.lmn[m].p, 0, lb.lmn_stride * S));
+        }
         if (h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT) ALLOC(lb.bgr[m], lb.bgr_stride * S);
       }
       r /= 2; c /= 2;
@@ -257,7 +267,7 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
     cudaStream_t st = h->lanes[0].stream;
     for (int l = 0; l < L; ++l)
       launch_build_offsets(h->d_feat[l].as<u32>(), h->d_offs[l].as<u32>(), h->d_hdr[l].as<TplHdr>(), h->ntpl, M,
-                           h->levels[l].g, st);
+                           h->levels[l].g, l == L - 1, st);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     // algorithmic coarse bytes per template: sum_m nf * P  
@@ -403,6 +413,9 @@ static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t
       ProfScope ps(h, LMB200_K_LINEARIZE, st);
       launch_spread_linearize(q, lb.q_stride, mask, lb.q_stride, lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride,
                               lb.lm_stride, lb.g, h->d_table.as<uint2>(), count, st);
+      if (l == L - 1)
+        launch_pack_nibbles(lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride, lb.lm_stride,
+                            lb.lmn[m].as<u8>() + (size_t)first * lb.lmn_stride, lb.lmn_stride, lb.g, count, st);
     }
   }
   CU(cudaGetLastError());
@@ -422,17 +435,24 @@ static MatchParams make_match_params(lmb200_detector* h, int first, int count, f
   mp.nsel_stride = h->nsel_stride;
   mp.tpl_start = h->d_tpl_start.as<int>() + (size_t)first * h->nsel_stride;
   mp.tpl_cnt = h->d_tpl_cnt.as<int>() + (size_t)first * h->nsel_stride;
+  mp.tpl_alive = h->d_tpl_alive.as<int>() + (size_t)first * h->nsel_stride;
   return mp;
 }
 
-static LevelParams make_level_params(lmb200_detector* h, int l, int first) {
+// nibble = true: the coarsest level's nibble-packed linear memories (similarity_coarse_kernel)
+static LevelParams make_level_params(lmb200_detector* h, int l, int first, bool nibble = false) {
   LevelParams lp;
   LevelBuffers& lb = h->levels[l];
   lp.g = lb.g;
   for (int m = 0; m < MAX_MOD; ++m) {
     int mm = m < h->cfg.num_modalities ? m : 0;
-    lp.lm[m] = lb.lm[mm].as<u8>() + (size_t)first * lb.lm_stride;
-    lp.lm_stride[m] = lb.lm_stride;
+    if (nibble) {
+      lp.lm[m] = lb.lmn[mm].as<u8>() + (size_t)first * lb.lmn_stride;
+      lp.lm_stride[m] = lb.lmn_stride;
+    } else {
+      lp.lm[m] = lb.lm[mm].as<u8>() + (size_t)first * lb.lm_stride;
+      lp.lm_stride[m] = lb.lm_stride;
+    }
   }
   lp.hdr = h->d_hdr[l].as<TplHdr>();
   lp.offs = h->d_offs[l].as<u32>();
@@ -450,7 +470,7 @@ static int run_matching(lmb200_detector* h, int first, int count, float threshol
   if (mp.nsel > 0) {
     {
       ProfScope ps(h, LMB200_K_SIM_COARSE, st);
-      launch_similarity_coarse(mp, make_level_params(h, L - 1, first), st);
+      launch_similarity_coarse(mp, make_level_params(h, L - 1, first, true), 4 * h->max_nf_coarse > 255, st);
     }
     if (!stop_after_coarse)
       for (int l = L - 2; l >= 0; --l) {

@@ -45,11 +45,12 @@ struct DevBuf {
 
 struct LevelBuffers {
   lmk::LevelGeom g;
-  size_t q_stride = 0, lm_stride = 0, bgr_stride = 0;
+  size_t q_stride = 0, lm_stride = 0, bgr_stride = 0, lmn_stride = 0;
   DevBuf bgr[LMB200_MAX_MODALITIES];   // CG source at this level (level 0 = uploaded frame)
   DevBuf q[LMB200_MAX_MODALITIES];     // quantized map
   DevBuf mask[LMB200_MAX_MODALITIES];  // optional mask pyramid
   DevBuf lm[LMB200_MAX_MODALITIES];    // linear memories [slots][8*rows*cols + pad]
+  DevBuf lmn[LMB200_MAX_MODALITIES];   // coarsest level only: nibble-packed copy [slots][4*rows*cols + pad]
 };
 
 struct Lane {
@@ -81,6 +82,7 @@ struct lmb200_detector {
 
   // template tables (per level)
   int ntpl = 0;
+  int max_nf_coarse = 0;                           // max over templates of sum_m nf at the coarsest level
   std::vector<int> g_class, g_tid;                 // global template index -> (class index, template id)
   std::vector<std::string> class_list;             // sorted class ids (index = class_index)
   lmh::DevBuf d_hdr[LMB200_MAX_LEVELS], d_feat[LMB200_MAX_LEVELS], d_offs[LMB200_MAX_LEVELS];
@@ -100,7 +102,7 @@ struct lmb200_detector {
   std::vector<lmh::LevelBuffers> levels;
   lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
   size_t depth_stride = 0;
-  lmh::DevBuf d_cand, d_ctr, d_tpl_start, d_tpl_cnt, d_out;
+  lmh::DevBuf d_cand, d_ctr, d_tpl_start, d_tpl_cnt, d_tpl_alive, d_out;
   int nsel_stride = 0;
   // pinned host mirrors
   lmk::SlotCtr* h_ctr = nullptr;

@@ -101,7 +101,10 @@ void launch_spread_linearize(const u8* q, size_t q_stride, const u8* mask, size_
 // ------------------------------------------------------------------ template side
 // Plan: flat linear-memory offsets of every feature for one level's geometry + safe flags.
 void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g,
-                          cudaStream_t st);
+                          bool nibble_sort, cudaStream_t st);
+// byte linear memory -> nibble-packed copy (coarsest level only; input of similarity_coarse_kernel)
+void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_stride, LevelGeom g, int frames,
+                         cudaStream_t st);
 
 struct MatchParams {
   int M, nsel, frames;
@@ -110,7 +113,8 @@ struct MatchParams {
   // candidate store, per frame
   Cand* cand; int cand_cap;
   SlotCtr* ctr;                       // [frames]
-  int* tpl_start; int* tpl_cnt;       // [frames][nsel_stride]
+  int* tpl_start; int* tpl_cnt;       // [frames][nsel_stride] candidate block of every template
+  int* tpl_alive;                     // [frames][nsel_stride] candidates of the block still alive (local kernel decrements)
   int nsel_stride;
 };
 
@@ -120,7 +124,7 @@ struct LevelParams {
   const TplHdr* hdr; const u32* offs; const u32* feat; // this level's template tables
 };
 
-void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
+void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, bool wide, cudaStream_t st);
 void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
 // Ordered compaction: out[frame][0..n) in generation order, count[frame] = n (may exceed cap -> overflow).
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st);

@@ -15,13 +15,14 @@ namespace lmk {
 // ---------------------------------------------------------------------------------------------
 // Plan kernel: one warp per template.  For every modality the valid feature offsets
 //   off = label*per_label + grid_index*W*H + lm_index            (accessLinearMemory)
-// are written contiguously, SORTED by their word shift (off>>2)&3 (warp-level counting sort), with the
+// are written contiguously, SORTED by their word shift (off>>key_shift)&3 — key_shift 3 for the nibble-packed
+// coarsest level (8 positions per word), 2 otherwise — (warp-level counting sort), with the
 // four bucket sizes in hdr.bkt[m]; features upstream's similarity() would skip are dropped.
 // hdr.flags: bit0 local-safe  : similarityLocal can never skip a feature or leave its plane
 //            bit1 coarse-safe : every feature row + template_positions stays inside its label's block
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restrict__ feat, u32* __restrict__ offs,
-                                                            TplHdr* __restrict__ hdr, int ntpl, int M, LevelGeom g) {
+                                                            TplHdr* __restrict__ hdr, int ntpl, int M, LevelGeom g, int key_shift) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntpl) return;
   TplHdr h = hdr[warp];
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
         if (!(f >> 31) || x > h.width[0] || y > h.height[0]) local_safe = false;
       }
       off2[j] = off;
-      key2[j] = off == OFF_INVALID ? 4 : (int)((off >> 2) & 3);
+      key2[j] = off == OFF_INVALID ? 4 : (int)((off >> key_shift) & 3);
     }
     // counting sort by key (0..3 valid buckets, 4 = dropped)
     u32 start = 0, packed = 0;
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
   if (lane == 0) hdr[warp].flags = (local_safe ? 1u : 0u) | (coarse_safe ? 2u : 0u);
 }
 
-void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g, cudaStream_t st) {
+void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g, bool nibble_sort, cudaStream_t st) {
   if (ntpl <= 0) return;
   int blocks = (ntpl * 32 + 127) / 128;
-  build_offsets_kernel<<<blocks, 128, 0, st>>>(feat, offs, hdr, ntpl, M, g);
+  build_offsets_kernel<<<blocks, 128, 0, st>>>(feat, offs, hdr, ntpl, M, g, nibble_sort ? 3 : 2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -105,62 +106,124 @@ __device__ __forceinline__ int raw_threshold(int nf, float threshold) {
   return (int)__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f);
 }
 
-// Accumulate the features [k0, k0+n) of one word-shift bucket into 16 packed byte sums.
-// lst = the modality's sorted offsets staged in shared memory (LDS broadcast);
-// lmb = modality's linear memories + 16*chunk (16 B aligned).  WS is a
-// compile-time constant per bucket, so the realignment is straight-line: two aligned LDG.128 + four
-// funnel shifts per feature; a 32-bit IADD then adds four responses (bytes never carry: <= 63*4).
-template <int WS, bool SAFE>
-__device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u32* __restrict__ lst, int k0, int n, bool active,
-                                             int pos0, int P, u32 per_label, u32& a0, u32& a1, u32& a2, u32& a3) {
-#pragma unroll 4
-  for (int k = k0; k < k0 + n; ++k) {
-    const u32 off = lst[k];
-    int nv = 16;
-    bool go = active;
-    if (!SAFE) {
-      int lim = (int)(per_label - off % per_label);   // positions past the label block contribute 0 (oracle semantics)
-      nv = min(P, lim) - pos0;
-      go = go && nv > 0;                              // ... and are never loaded
-    }
-    if (go) {
-      const uint4* p = reinterpret_cast<const uint4*>(lmb + (off & ~15u));
-      const uint4 A = __ldg(p), B = __ldg(p + 1);
-      const u32 sh = (off & 3u) * 8u;
-      u32 w0, w1, w2, w3;
-      if (WS == 0) {
-        w0 = __funnelshift_r(A.x, A.y, sh); w1 = __funnelshift_r(A.y, A.z, sh);
-        w2 = __funnelshift_r(A.z, A.w, sh); w3 = __funnelshift_r(A.w, B.x, sh);
-      } else if (WS == 1) {
-        w0 = __funnelshift_r(A.y, A.z, sh); w1 = __funnelshift_r(A.z, A.w, sh);
-        w2 = __funnelshift_r(A.w, B.x, sh); w3 = __funnelshift_r(B.x, B.y, sh);
-      } else if (WS == 2) {
-        w0 = __funnelshift_r(A.z, A.w, sh); w1 = __funnelshift_r(A.w, B.x, sh);
-        w2 = __funnelshift_r(B.x, B.y, sh); w3 = __funnelshift_r(B.y, B.z, sh);
-      } else {
-        w0 = __funnelshift_r(A.w, B.x, sh); w1 = __funnelshift_r(B.x, B.y, sh);
-        w2 = __funnelshift_r(B.y, B.z, sh); w3 = __funnelshift_r(B.z, B.w, sh);
-      }
-      if (!SAFE && nv < 16) mask16(w0, w1, w2, w3, nv);
-      a0 += w0; a1 += w1; a2 += w2; a3 += w3;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Coarse similarity: one WARP per (template, frame) — no block barriers.  The warp sweeps the
-// H*W positions in passes of 32 lanes x 16 positions; hits are appended in raster order to a small
-// per-warp queue (lane order = position order, passes are sequential).  One atomicAdd per template
-// with hits reserves a contiguous block of the frame's candidate store; if a template has more hits
-// than the queue holds (low thresholds) the warp re-sweeps and writes directly into its block.
+// Coarse similarity on the NIBBLE-PACKED linear memories of the coarsest level (responses are 0..4:
+// two positions per byte halve the L1/L2 traffic of the gather).  One WARP per (template, frame), no
+// block barriers.  A lane owns 32 consecutive positions = one aligned 16 B chunk; a pass covers 1024
+// positions (cfg-A: 1200 positions, typical template_positions 800-1000 -> one pass).
+// Per feature: two aligned LDG.128 + four funnel shifts realign the row (the word shift is a compile-
+// time constant per plan bucket), four 32-bit IADDs add 32 responses into nibble accumulators; every
+// third feature (3*4 = 12 <= 15) they are spilled into byte accumulators.  Hits are appended in raster
+// order to a per-warp queue; one atomicAdd per template with hits reserves a contiguous block of the
+// frame's candidate store (templates with more hits than the queue holds re-sweep and write directly).
 // ---------------------------------------------------------------------------------------------
 constexpr int CW_WARPS = 4;          // warps (templates) per CTA
 constexpr int CW_QCAP = 96;          // queued hits per warp
+#ifndef CW_MINB
+#define CW_MINB 6                    // resident CTAs per SM the register allocation targets (6 -> <= 80 registers; measured best)
+#endif
+
+// zero the nibbles at index >= nv (nv < 32) of 32 nibbles held in 4 little-endian words
+__device__ __forceinline__ void mask_nibbles(u32& w0, u32& w1, u32& w2, u32& w3, int nv) {
+  u32 w[4] = {w0, w1, w2, w3};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = nv - 8 * i;
+    u32 m = r >= 8 ? 0xFFFFFFFFu : (r <= 0 ? 0u : ((1u << (4 * r)) - 1u));
+    w[i] &= m;
+  }
+  w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
+}
+
+struct NibAcc {
+  u32 n0, n1, n2, n3;   // nibble accumulators (32 positions)
+  u32 b[8];             // byte accumulators: b[2i+par] byte t <-> position 8i + 2t + par
+  int pend;             // features added since the last spill (warp-uniform)
+  __device__ __forceinline__ void spill() {
+    b[0] += n0 & 0x0F0F0F0Fu; b[1] += (n0 >> 4) & 0x0F0F0F0Fu;
+    b[2] += n1 & 0x0F0F0F0Fu; b[3] += (n1 >> 4) & 0x0F0F0F0Fu;
+    b[4] += n2 & 0x0F0F0F0Fu; b[5] += (n2 >> 4) & 0x0F0F0F0Fu;
+    b[6] += n3 & 0x0F0F0F0Fu; b[7] += (n3 >> 4) & 0x0F0F0F0Fu;
+    n0 = n1 = n2 = n3 = 0u; pend = 0;
+  }
+  // zero the byte sums of positions >= rem (0 < rem < 32): b[2i+par] byte t <-> position 8i + 2t + par
+  __device__ __forceinline__ void mask_tail(int rem) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      int nb = (rem - 8 * (w >> 1) - (w & 1) + 1) >> 1;  // valid bytes in this word
+      u32 m = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - nb))));
+      b[w] &= m;
+    }
+  }
+};
+
+template <int WS, bool MASK>
+__device__ __forceinline__ void realign_add(const uint4& A, const uint4& B, u32 off, int nv, NibAcc& acc) {
+  const u32 sh = (off & 7u) * 4u;
+  u32 w0, w1, w2, w3;
+  if (WS == 0) {
+    w0 = __funnelshift_r(A.x, A.y, sh); w1 = __funnelshift_r(A.y, A.z, sh);
+    w2 = __funnelshift_r(A.z, A.w, sh); w3 = __funnelshift_r(A.w, B.x, sh);
+  } else if (WS == 1) {
+    w0 = __funnelshift_r(A.y, A.z, sh); w1 = __funnelshift_r(A.z, A.w, sh);
+    w2 = __funnelshift_r(A.w, B.x, sh); w3 = __funnelshift_r(B.x, B.y, sh);
+  } else if (WS == 2) {
+    w0 = __funnelshift_r(A.z, A.w, sh); w1 = __funnelshift_r(A.w, B.x, sh);
+    w2 = __funnelshift_r(B.x, B.y, sh); w3 = __funnelshift_r(B.y, B.z, sh);
+  } else {
+    w0 = __funnelshift_r(A.w, B.x, sh); w1 = __funnelshift_r(B.x, B.y, sh);
+    w2 = __funnelshift_r(B.y, B.z, sh); w3 = __funnelshift_r(B.z, B.w, sh);
+  }
+  if (MASK && nv < 32) mask_nibbles(w0, w1, w2, w3, nv);
+  acc.n0 += w0; acc.n1 += w1; acc.n2 += w2; acc.n3 += w3;
+}
+
+#ifndef CW_GROUP
+#define CW_GROUP 3   // feature rows whose loads are issued back to back (memory-level parallelism per warp)
+#endif
+
+template <int WS, bool SAFE>
+__device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u32* __restrict__ lst, int k0, int n, int rem,
+                                             int pos0, int P, u32 per_label, NibAcc& acc) {
+  int k = k0;
+  const int end = k0 + n;
+  if (SAFE) {
+    // groups of CW_GROUP rows: all loads first (6 x LDG.128 in flight per lane), then realign + add, then spill
+    if (k + CW_GROUP <= end && acc.pend) acc.spill();
+    for (; k + CW_GROUP <= end; k += CW_GROUP) {
+      u32 off[CW_GROUP];
+      uint4 A[CW_GROUP], B[CW_GROUP];
+#pragma unroll
+      for (int j = 0; j < CW_GROUP; ++j) off[j] = lst[k + j];
+      if (rem > 0) {
+#pragma unroll
+        for (int j = 0; j < CW_GROUP; ++j) {
+          const uint4* p = reinterpret_cast<const uint4*>(lmb + ((off[j] >> 1) & ~15u));
+          A[j] = __ldg(p); B[j] = __ldg(p + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < CW_GROUP; ++j) realign_add<WS, false>(A[j], B[j], off[j], rem, acc);
+      }
+      acc.spill();  // CW_GROUP <= 3 rows x 4 <= 12 fits a nibble
+    }
+  }
+  for (; k < end; ++k) {
+    const u32 off = lst[k];
+    int nv = rem;
+    if (!SAFE) nv = min(P, (int)(per_label - off % per_label)) - pos0;  // positions past the label block contribute 0
+    if (nv > 0) {
+      const uint4* p = reinterpret_cast<const uint4*>(lmb + ((off >> 1) & ~15u));
+      const uint4 A = __ldg(p), B = __ldg(p + 1);
+      realign_add<WS, !SAFE>(A, B, off, nv, acc);
+    }
+    if (++acc.pend == 3) acc.spill();
+  }
+}
 
 struct CoarseCtx {
   HdrR hdr;
   const u32* lst;                    // this warp's staged offsets [M][FEAT_SLOTS] (shared memory)
-  int M, T, W, H, HW, NC, raw_thr, nf_total;
+  int M, T, W, H, HW, raw_thr, nf_total;
   u32 per_label;
   __device__ __forceinline__ int P(int m) const {  // upstream's template_positions
     int wf = (hdr.width(m) - 1) / T + 1, hf = (hdr.height(m) - 1) / T + 1;
@@ -169,49 +232,76 @@ struct CoarseCtx {
   }
 };
 
-// DIRECT=false: count hits and queue them (queue entries beyond CW_QCAP are dropped, count continues)
-// DIRECT=true : write Cand records at out[0..) in raster order
-template <bool SAFE, bool DIRECT>
-__device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const* s_lm, u32* queue, Cand* out, int isel, int lane) {
+// value of position p (compile-time) from the byte accumulators / the u16 totals
+template <bool WIDE>
+__device__ __forceinline__ int hit_val(const u32* t, int p) {
+  const int w = 2 * (p >> 3) + (p & 1), tt = (p & 7) >> 1;
+  if (WIDE) return (int)((t[2 * w + (tt & 1)] >> (16 * (tt >> 1))) & 0xFFFFu);
+  return (int)((t[w] >> (8 * tt)) & 0xFFu);
+}
+
+// WIDE=false: 4*nf_total <= 255, every modality accumulates into the same byte sums.
+// WIDE=true : per-modality byte sums are widened into u16 totals (upstream's addSimilarities).
+// direct=false: count hits and queue them (entries beyond CW_QCAP are dropped, the count continues);
+// direct=true : write Cand records at out[0..) in raster order.
+template <bool SAFE, bool WIDE>
+__device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const* s_lm, u32* queue, Cand* out, bool direct, int isel, int lane) {
   int nhit = 0;
   int Pmax = 0;
   for (int m = 0; m < cx.M; ++m) Pmax = max(Pmax, cx.P(m));
   const int offset = cx.T / 2 + (cx.T % 2 - 1);
   const float denom = (float)(4 * cx.nf_total);
-  for (int c0 = 0; c0 < cx.NC && 16 * c0 < Pmax; c0 += 32) {
-    const int c = c0 + lane, pos0 = 16 * c;
-    u32 tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, th0 = 0, th1 = 0, th2 = 0, th3 = 0;  // u16 pairs: (4w,4w+2) / (4w+1,4w+3)
+  const u32 K = (u32)(0x7FFF - cx.raw_thr) * 0x00010001u;  // field + K sets bit 15 iff field > raw_thr
+  for (int c0 = 0; 32 * c0 < Pmax; c0 += 32) {
+    const int pos0 = 32 * (c0 + lane);
+    NibAcc acc;
+    acc.n0 = acc.n1 = acc.n2 = acc.n3 = 0u; acc.pend = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.b[i] = 0u;
+    u32 tot[WIDE ? 16 : 8];  // WIDE: u16 pairs (see wide_val); else byte sums laid out like acc.b
+#pragma unroll
+    for (int i = 0; i < (WIDE ? 16 : 8); ++i) tot[i] = 0u;
     for (int m = 0; m < cx.M; ++m) {
       const int P = cx.P(m);
-      if (16 * c0 >= P) continue;  // warp-uniform
+      if (32 * c0 >= P) continue;  // warp-uniform
       const int rem = P - pos0;
-      const bool active = rem > 0;
-      u32 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      const u8* lmb = s_lm[m] + pos0;
-      const u32 b = cx.hdr.bkt(m);
-      const int n0 = b & 255, n1 = (b >> 8) & 255, n2 = (b >> 16) & 255, n3 = b >> 24;
+      const u8* lmb = s_lm[m] + (pos0 >> 1);
+      const u32 bk = cx.hdr.bkt(m);
+      const int n0 = bk & 255, n1 = (bk >> 8) & 255, n2 = (bk >> 16) & 255, n3 = bk >> 24;
       const u32* lst = cx.lst + m * FEAT_SLOTS;
-      accum_bucket<0, SAFE>(lmb, lst, 0, n0, active, pos0, P, cx.per_label, a0, a1, a2, a3);
-      accum_bucket<1, SAFE>(lmb, lst, n0, n1, active, pos0, P, cx.per_label, a0, a1, a2, a3);
-      accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, active, pos0, P, cx.per_label, a0, a1, a2, a3);
-      accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, active, pos0, P, cx.per_label, a0, a1, a2, a3);
-      if (SAFE && rem < 16) mask16(a0, a1, a2, a3, rem < 0 ? 0 : rem);
-      tl0 += a0 & 0x00FF00FFu; th0 += (a0 >> 8) & 0x00FF00FFu;
-      tl1 += a1 & 0x00FF00FFu; th1 += (a1 >> 8) & 0x00FF00FFu;
-      tl2 += a2 & 0x00FF00FFu; th2 += (a2 >> 8) & 0x00FF00FFu;
-      tl3 += a3 & 0x00FF00FFu; th3 += (a3 >> 8) & 0x00FF00FFu;
+      accum_bucket<0, SAFE>(lmb, lst, 0, n0, rem, pos0, P, cx.per_label, acc);
+      accum_bucket<1, SAFE>(lmb, lst, n0, n1, rem, pos0, P, cx.per_label, acc);
+      accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, rem, pos0, P, cx.per_label, acc);
+      accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, rem, pos0, P, cx.per_label, acc);
+      acc.spill();
+      if (SAFE && rem > 0 && rem < 32) acc.mask_tail(rem);  // at most one lane per modality: the row tail
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        if (WIDE) {
+          tot[2 * w] += acc.b[w] & 0x00FF00FFu;
+          tot[2 * w + 1] += (acc.b[w] >> 8) & 0x00FF00FFu;
+        } else {
+          tot[w] += acc.b[w];
+        }
+        acc.b[w] = 0u;
+      }
     }
-    const u32 tl[4] = {tl0, tl1, tl2, tl3}, th[4] = {th0, th1, th2, th3};
+    u32 any = 0;
+    if (WIDE) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) any |= tot[i] + K;
+    } else {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) any |= ((tot[w] & 0x00FF00FFu) + K) | (((tot[w] >> 8) & 0x00FF00FFu) + K);
+    }
+    if (!__any_sync(0xffffffffu, (any & 0x80008000u) != 0u)) continue;
+    // rare path: exact per-position test in raster order
     u32 mask = 0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      mask |= ((int)(tl[w] & 0xFFFFu) > cx.raw_thr ? 1u : 0u) << (4 * w);
-      mask |= ((int)(th[w] & 0xFFFFu) > cx.raw_thr ? 1u : 0u) << (4 * w + 1);
-      mask |= ((int)(tl[w] >> 16) > cx.raw_thr ? 1u : 0u) << (4 * w + 2);
-      mask |= ((int)(th[w] >> 16) > cx.raw_thr ? 1u : 0u) << (4 * w + 3);
+    for (int p = 0; p < 32; ++p) {
+      const int v = hit_val<WIDE>(tot, p);
+      mask |= (v > cx.raw_thr ? 1u : 0u) << p;
     }
-    if (!__any_sync(0xffffffffu, mask != 0)) continue;
-    // raster-ordered slots: exclusive prefix of per-lane hit counts
     const int mine = __popc(mask);
     int incl = mine;
 #pragma unroll
@@ -221,36 +311,34 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     int slot = nhit + incl - mine;
-    u32 mm = mask;
-    while (mm) {
-      const int b = __ffs(mm) - 1;
-      mm &= mm - 1;
-      const int w = b >> 2, r = b & 3;
-      const u32 word = (r & 1) ? th[w] : tl[w];
-      const int raw = (r & 2) ? (int)(word >> 16) : (int)(word & 0xFFFFu);
-      const int j = pos0 + b;
-      if (DIRECT) {
-        const int row = j / cx.W, col = j - row * cx.W;
-        Cand cd;
-        cd.tsel = isel;
-        cd.x = col * cx.T + offset;
-        cd.y = row * cx.T + offset;
-        cd.sim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), denom), 0.5f);
-        out[slot] = cd;
-      } else if (slot < CW_QCAP) {
-        queue[slot] = ((u32)j << 11) | (u32)raw;  // raw <= 4*63*MAX_MOD = 1008 < 2048; j < 2^21
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+      if (mask & (1u << p)) {
+        const int raw = hit_val<WIDE>(tot, p);
+        const int j = pos0 + p;
+        if (direct) {
+          const int row = j / cx.W, col = j - row * cx.W;
+          Cand cd;
+          cd.tsel = isel;
+          cd.x = col * cx.T + offset;
+          cd.y = row * cx.T + offset;
+          cd.sim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), denom), 0.5f);
+          out[slot] = cd;
+        } else if (slot < CW_QCAP) {
+          queue[slot] = ((u32)j << 11) | (u32)raw;  // raw <= 4*63*MAX_MOD = 1008 < 2048; j < 2^21
+        }
+        ++slot;
       }
-      ++slot;
     }
     nhit += total;
   }
   return nhit;
 }
 
-template <bool SAFE>
+template <bool SAFE, bool WIDE>
 __device__ __forceinline__ void coarse_template(const MatchParams& mp, const CoarseCtx& cx, const u8* const* s_lm, u32* queue,
                                                 int isel, int frame, int lane) {
-  const int nhit = coarse_sweep<SAFE, false>(cx, s_lm, queue, nullptr, isel, lane);
+  const int nhit = coarse_sweep<SAFE, WIDE>(cx, s_lm, queue, nullptr, false, isel, lane);
   int base = 0, run = nhit;
   if (lane == 0) {
     if (nhit > 0) {
@@ -259,6 +347,7 @@ __device__ __forceinline__ void coarse_template(const MatchParams& mp, const Coa
     }
     mp.tpl_start[(size_t)frame * mp.nsel_stride + isel] = base;
     mp.tpl_cnt[(size_t)frame * mp.nsel_stride + isel] = run;
+    mp.tpl_alive[(size_t)frame * mp.nsel_stride + isel] = run;
   }
   base = __shfl_sync(0xffffffffu, base, 0);
   run = __shfl_sync(0xffffffffu, run, 0);
@@ -280,17 +369,18 @@ __device__ __forceinline__ void coarse_template(const MatchParams& mp, const Coa
       out[q] = cd;
     }
   } else {
-    coarse_sweep<SAFE, true>(cx, s_lm, nullptr, out, isel, lane);
+    coarse_sweep<SAFE, WIDE>(cx, s_lm, nullptr, out, true, isel, lane);
   }
 }
 
-__global__ void __launch_bounds__(CW_WARPS * 32) similarity_coarse_kernel(MatchParams mp, LevelParams lp) {
+template <bool WIDE>
+__global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kernel(MatchParams mp, LevelParams lp) {
   __shared__ const u8* s_lm[MAX_MOD];
   __shared__ u32 s_queue[CW_WARPS][CW_QCAP];
   __shared__ u32 s_off[CW_WARPS][MAX_MOD * FEAT_SLOTS];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {  // lp.lm = nibble-packed linear memories of the coarsest level
     s_lm[0] = lp.lm[0] + (size_t)frame * lp.lm_stride[0];
     s_lm[1] = lp.lm[1] + (size_t)frame * lp.lm_stride[1];
     s_lm[2] = lp.lm[2] + (size_t)frame * lp.lm_stride[2];
@@ -302,21 +392,44 @@ __global__ void __launch_bounds__(CW_WARPS * 32) similarity_coarse_kernel(MatchP
   const int g = mp.sel[isel];
   CoarseCtx cx;
   cx.hdr = load_hdr(lp.hdr + g);
-  cx.M = mp.M; cx.T = lp.g.T; cx.W = lp.g.W; cx.H = lp.g.H; cx.HW = lp.g.W * lp.g.H; cx.NC = (cx.HW + 15) >> 4;
+  cx.M = mp.M; cx.T = lp.g.T; cx.W = lp.g.W; cx.H = lp.g.H; cx.HW = lp.g.W * lp.g.H;
   cx.per_label = lp.g.per_label;
   cx.nf_total = cx.hdr.nf_total();
   cx.raw_thr = raw_threshold(cx.nf_total, mp.threshold);
+  if (cx.raw_thr > 0x7FFE) cx.raw_thr = 0x7FFE;  // nothing can exceed it anyway (scores <= 1008)
+  if (cx.raw_thr < 0) cx.raw_thr = -1;
   cx.lst = s_off[warp];
   for (int s = lane; s < cx.M * FEAT_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * FEAT_SLOTS + s);
   __syncwarp();
-  if (cx.hdr.flags & 2u) coarse_template<true>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
-  else coarse_template<false>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
+  if (cx.hdr.flags & 2u) coarse_template<true, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
+  else coarse_template<false, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
 }
 
-void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, cudaStream_t st) {
+// wide: some template has 4*nf_total > 255 at the coarsest level (byte sums across modalities could carry)
+void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, bool wide, cudaStream_t st) {
   if (mp.nsel <= 0 || mp.frames <= 0) return;
   dim3 grid((mp.nsel + CW_WARPS - 1) / CW_WARPS, mp.frames);
-  similarity_coarse_kernel<<<grid, CW_WARPS * 32, 0, st>>>(mp, lp);
+  if (wide) similarity_coarse_kernel<true><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp);
+  else similarity_coarse_kernel<false><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp);
+}
+
+// Packs a byte linear memory (values 0..4) two positions per byte: out[q] = in[2q] | in[2q+1] << 4.
+__global__ void __launch_bounds__(256) pack_nibbles_kernel(const u8* __restrict__ lm, size_t lm_stride, u8* __restrict__ lmn,
+                                                           size_t lmn_stride, u32 n_out8 /* 8-byte output groups */) {
+  const u32 i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_out8) return;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(lm + (size_t)blockIdx.y * lm_stride) + i);
+  const u32 t0 = v.x | (v.x >> 4), t1 = v.y | (v.y >> 4), t2 = v.z | (v.z >> 4), t3 = v.w | (v.w >> 4);
+  uint2 o;
+  o.x = __byte_perm(t0, t1, 0x6420);
+  o.y = __byte_perm(t2, t3, 0x6420);
+  reinterpret_cast<uint2*>(lmn + (size_t)blockIdx.y * lmn_stride)[i] = o;
+}
+
+void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_stride, LevelGeom g, int frames, cudaStream_t st) {
+  u32 n_out8 = g.per_label / 2;  // 8*per_label positions / 16 per thread
+  dim3 grid((n_out8 + 255) / 256, frames);
+  pack_nibbles_kernel<<<grid, 256, 0, st>>>(lm, lm_stride, lmn, lmn_stride, n_out8);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,6 +540,7 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       float sim = __fdiv_rn(__fmul_rn((float)bs, 100.f), (float)(4 * nfl));
       rec.sim = sim < mp.threshold ? -1.0f : sim;
       cands[c] = rec;
+      if (rec.sim < 0.f) atomicSub(&mp.tpl_alive[(size_t)frame * mp.nsel_stride + rec.tsel], 1);
       atomicAdd(&mp.ctr[frame].local_bytes, (unsigned long long)nfl * 256ull);
     }
   }
@@ -444,54 +558,59 @@ void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaS
 // ---------------------------------------------------------------------------------------------
 // Ordered compaction: surviving candidates of frame f in (selection order, raster order).
 // ---------------------------------------------------------------------------------------------
+// The per-template alive counts are maintained by the coarse/local kernels, so the order-defining
+// prefix sum needs no candidate reads; only templates that still own matches copy anything.
 __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __restrict__ out, int out_cap) {
   __shared__ int wsum[32];
+  __shared__ int s_run;
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (mp.ctr[frame].overflow) return;  // host will grow the store and redo this frame
   const Cand* cands = mp.cand + (size_t)frame * mp.cand_cap;
   Cand* o = out + (size_t)frame * out_cap;
-  if (mp.ctr[frame].overflow) return;  // host will grow the store and redo this frame
-  // thread t owns the contiguous template range [t*per, (t+1)*per): one scan for the whole selection
-  const int per = (mp.nsel + 1023) >> 10;
-  const int i0 = tid * per, i1 = min(mp.nsel, i0 + per);
   const int* ts = mp.tpl_start + (size_t)frame * mp.nsel_stride;
   const int* tc = mp.tpl_cnt + (size_t)frame * mp.nsel_stride;
-  int alive = 0;
-  for (int i = i0; i < i1; ++i) {
-    const int st = ts[i], cn = tc[i];
-    for (int j = 0; j < cn; ++j) alive += cands[st + j].sim >= 0.f;
-  }
-  int incl = alive;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) wsum[wid] = incl;
+  const int* ta = mp.tpl_alive + (size_t)frame * mp.nsel_stride;
+  if (tid == 0) s_run = 0;
   __syncthreads();
-  if (wid == 0) {
-    int v = wsum[lane], inc2 = v;
+  for (int i0 = 0; i0 < mp.nsel; i0 += 1024) {
+    const int i = i0 + tid;
+    const int alive = i < mp.nsel ? ta[i] : 0;
+    int incl = alive;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, inc2, d);
-      if (lane >= d) inc2 += u;
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
     }
-    wsum[lane] = inc2 - v;               // exclusive warp offsets
-    if (lane == 31) mp.ctr[frame].out_count = inc2;
-  }
-  __syncthreads();
-  if (alive == 0) return;
-  int pos = wsum[wid] + incl - alive;
-  for (int i = i0; i < i1; ++i) {
-    const int st = ts[i], cn = tc[i];
-    for (int j = 0; j < cn; ++j) {
-      Cand cd = cands[st + j];
-      if (cd.sim >= 0.f) {
-        cd.tsel = mp.sel[cd.tsel];  // selection index -> global template index (rank-independent)
-        if (pos < out_cap) o[pos] = cd;
-        ++pos;
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int v = wsum[lane], inc2 = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc2, d);
+        if (lane >= d) inc2 += u;
+      }
+      wsum[lane] = inc2 - v;  // exclusive warp offsets
+    }
+    __syncthreads();
+    const int run = s_run;
+    if (alive > 0) {
+      int pos = run + wsum[wid] + incl - alive;
+      const int st = ts[i], cn = tc[i];
+      for (int j = 0; j < cn; ++j) {
+        Cand cd = cands[st + j];
+        if (cd.sim >= 0.f) {
+          cd.tsel = mp.sel[cd.tsel];  // selection index -> global template index (rank-independent)
+          if (pos < out_cap) o[pos] = cd;
+          ++pos;
+        }
       }
     }
+    __syncthreads();
+    if (tid == 1023) s_run = run + wsum[31] + incl;  // last thread: exclusive offset of its warp + its inclusive sum = round total
+    __syncthreads();
   }
+  if (tid == 0) mp.ctr[frame].out_count = s_run;
 }
 
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st) {
