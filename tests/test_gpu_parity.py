@@ -255,3 +255,62 @@ def test_config2_full_size():
     assert_same_matches(again, got, "idempotence")
     s = got.similarity
     assert np.all(s[:-1] >= s[1:]) and np.all(s >= 57.0)
+
+
+def test_config4_20000_templates_multi_class():
+    """BASELINE config 4 template set (20 000 templates, 10 classes) on one GPU vs the oracle."""
+    bgr, depth = synth.make_frame(1)
+    det, ora = make_pair(max_batch=2)
+    masks = synth.object_masks(1)
+    n_planted = add_planted_from_oracle(det, ora, [bgr, depth], masks, class_id="obj00")
+    per_class = 2000
+    tps = synth.random_templates(20000 - n_planted, seed=123)
+    k = 0
+    for c in range(10):
+        cid = "obj%02d" % c
+        want = per_class - (n_planted if c == 0 else 0)
+        for tp in tps[k:k + want]:
+            det.addSyntheticTemplate(tp, cid); ora.add_synthetic(tp, cid)
+        k += want
+    assert det.numTemplates() == 20000 and det.numClasses() == 10
+    for thr, ids in ((80.0, ()), (58.0, ("obj07", "obj00", "obj03"))):
+        got = det.match([bgr, depth], thr, class_ids=ids)
+        ref = ora.match([bgr, depth], thr, class_ids=ids, threads=16)
+        assert_same_matches(got, ref.matches(0), "config 4 thr=%g ids=%r" % (thr, ids))
+    assert len(got) > 0
+
+
+def test_config5_kinect_v2_size_three_levels():
+    """BASELINE config 5 geometry: 1920x1080 padded to 1920x1088 (linearize needs rows % T == 0 at every level),
+    T={4,8,16}, features 63/31/15; 2 000 templates here (the 10 000-template run is bench material)."""
+    rows, cols = 1088, 1920
+    bgr, depth = synth.make_frame(7, 1080, cols, n_shapes=60)
+    bgr = np.concatenate([bgr, np.zeros((8, cols, 3), np.uint8)], 0)
+    depth = np.concatenate([depth, np.zeros((8, cols), np.uint16)], 0)
+    det, ora = make_pair(T=(4, 8, 16), max_batch=2)
+    masks = [np.concatenate([m, np.zeros((8, cols), np.uint8)], 0) for m in synth.object_masks(7, 1080, cols, n_shapes=60, min_px=4000)]
+    n = add_planted_from_oracle(det, ora, [bgr, depth], masks[:12])
+    assert n >= 4
+    add_random(det, ora, 2000 - n, levels=3, wh_range=(80, 300))
+    for thr in (80.0, 60.0):
+        got, ref = _check_frame_side(det, ora, [bgr, depth], thr, n_maps=6)
+        assert_same_matches(det.debugFetch(K.DBG_COARSE, 0), ref.matches(2), "config 5 coarse thr=%g" % thr)
+        assert_same_matches(got, ref.matches(0), "config 5 thr=%g" % thr)
+    assert len(got) > 0
+
+
+def test_config3_streamed_batch_of_64():
+    """BASELINE config 3: 64 frames streamed through lmb200_match_batch vs 3 000 templates; every frame's list
+    must equal the single-frame call, and sampled frames must equal the oracle."""
+    det, ora = make_pair(max_batch=24)
+    bgr0, depth0 = synth.make_frame(0)
+    n = add_planted_from_oracle(det, ora, [bgr0, depth0], synth.object_masks(0) + synth.planted_masks(100, seed=17))
+    add_random(det, ora, 3000 - n)
+    frames = [list(synth.make_frame(i)) for i in range(64)]
+    batch = det.matchBatch(frames, 80.0)
+    assert len(batch) == 64
+    for i in (0, 1, 31, 63):
+        assert_same_matches(batch[i], ora.match(frames[i], 80.0, threads=16).matches(0), "config 3 frame %d vs oracle" % i)
+    for i in range(0, 64, 7):
+        assert_same_matches(batch[i], det.match(frames[i], 80.0), "config 3 frame %d vs single" % i)
+    assert len(batch[0]) > 0
