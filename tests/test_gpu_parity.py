@@ -314,3 +314,23 @@ def test_config3_streamed_batch_of_64():
     for i in range(0, 64, 7):
         assert_same_matches(batch[i], det.match(frames[i], 80.0), "config 3 frame %d vs single" % i)
     assert len(batch[0]) > 0
+
+
+def test_config1_reference_frame_and_model_templates(fixture_frame):
+    """BASELINE config 1: the reference's frame (benchmark/img0.png + depth0.png) vs the 1 950 lagergehaeuse templates
+    (13 viewpoints x 15 radii x 10 in-plane rotations, tests/golden/make_config1_templates.py), {CG,DN}, T={5,8},
+    threshold 80 (linemod_settings.yml:29) and 70.  Templates are loaded from the reference's file layout
+    through the product's own reader."""
+    import os
+    bgr, depth = fixture_frame
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagergehaeuse_templates.yml.gz")
+    det = lm.Detector.read(path)
+    assert det.classIds() == ["lagergehaeuse.ply"] and det.numTemplates() == 1950
+    ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
+    for t in range(1950):
+        ora.add_synthetic(det.getTemplates("lagergehaeuse.ply", t), "lagergehaeuse.ply")
+    for thr in (80.0, 70.0):
+        got = det.match([bgr, depth], thr, class_ids=["lagergehaeuse.ply"])
+        ref = ora.match([bgr, depth], thr, class_ids=["lagergehaeuse.ply"], threads=16)
+        assert_same_matches(got, ref.matches(0), "config 1 thr=%g" % thr)
+    assert len(got) > 1000

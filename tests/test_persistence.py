@@ -135,3 +135,16 @@ def test_write_read_classes(tmp_path):
     with pytest.raises(lm.LinemodError) as err:
         lm.Detector.read(str(tmp_path / "missing.yml.gz"))
     assert err.value.code == K.E_IO
+
+
+def test_config1_template_file_loads():
+    """The committed config-1 template set (reference file layout) parses into 1 950 pyramids of 63/63/31/31 features."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagergehaeuse_templates.yml.gz")
+    d = lm.Detector.read(path)
+    assert d.classIds() == ["lagergehaeuse.ply"] and d.numTemplates() == 1950
+    assert d.getModalities() == ["ColorGradient", "DepthNormal"] and [d.getT(0), d.getT(1)] == [5, 8]
+    for t in (0, 977, 1949):
+        tp = d.getTemplates("lagergehaeuse.ply", t)
+        assert [len(x["features"]) for x in tp] == [63, 63, 31, 31]
+        assert [x["pyramid_level"] for x in tp] == [0, 0, 1, 1]
+        assert tp[0]["width"] == tp[1]["width"] and tp[2]["width"] == tp[0]["width"] >> 1
