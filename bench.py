@@ -325,10 +325,10 @@ def main():
         ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
         copy_templates_to_oracle(det, ora)
         threads = O.max_threads()
-        nfr = args.cpu_frames or 24
+        nfr = args.cpu_frames or 96
         fps, dt, nm = cpu_sample(ora, nfr, args.threshold, threads, lambda i: frames[i % B])
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "%d of the step's frames x %d templates, oracle C++ port (frame side 1 thread, templates on %d threads), %.1f s" % (nfr, n_tpl, threads, dt)}
+               "sample": "%d of the step's frames x %d templates, oracle C++ port (one thread per modality on the frame side, templates on %d threads), %.1f s" % (nfr, n_tpl, threads, dt)}
 
     line = {"metric": "rgbd_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",

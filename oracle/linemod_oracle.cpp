@@ -82,42 +82,63 @@ static inline int reflect101(int p, int n) {
 // OpenCV imgproc primitives restated (integer-exact for 8-bit input)
 // ----------------------------------------------------------------------------------
 
+// Border-extended copy of an interleaved 8-bit image: pad pixels on every side, replicate (mode 0) or
+// reflect-101 (mode 1).  Lets the filters below run as plain contiguous loops the compiler vectorises.
+static void pad_image(const u8* src, int rows, int cols, int ch, int pad, int mode, std::vector<u8>& out) {
+  int pr = rows + 2 * pad, pc = cols + 2 * pad;
+  out.resize((size_t)pr * pc * ch);
+  for (int y = 0; y < pr; ++y) {
+    int sy = mode ? reflect101(y - pad, rows) : clampi(y - pad, 0, rows - 1);
+    const u8* s = src + (size_t)sy * cols * ch;
+    u8* d = out.data() + (size_t)y * pc * ch;
+    std::memcpy(d + (size_t)pad * ch, s, (size_t)cols * ch);
+    for (int x = 0; x < pad; ++x) {
+      int sl = mode ? reflect101(x - pad, cols) : 0, sr = mode ? reflect101(cols + x, cols) : cols - 1;
+      for (int c = 0; c < ch; ++c) {
+        d[(size_t)x * ch + c] = s[(size_t)sl * ch + c];
+        d[(size_t)(pad + cols + x) * ch + c] = s[(size_t)sr * ch + c];
+      }
+    }
+  }
+}
+
 // cv::GaussianBlur(src, dst, Size(7,7), 0, 0, BORDER_REPLICATE) on CV_8UC{ch}.
 // Fixed-point kernel 256*getGaussianKernel(7,0) = [8,28,56,72,56,28,8]; one rounding:
 // (sum + 2^15) >> 16.   
 static void gauss7(const u8* src, int rows, int cols, int ch, u8* dst) {
-  static const int k[7] = {8, 28, 56, 72, 56, 28, 8};
-  std::vector<int> tmp((size_t)rows * cols * ch);
-  for (int y = 0; y < rows; ++y)
-    for (int x = 0; x < cols; ++x)
-      for (int c = 0; c < ch; ++c) {
-        int s = 0;
-        for (int j = 0; j < 7; ++j) s += k[j] * src[((size_t)y * cols + clampi(x + j - 3, 0, cols - 1)) * ch + c];
-        tmp[((size_t)y * cols + x) * ch + c] = s;
-      }
-  for (int y = 0; y < rows; ++y)
-    for (int x = 0; x < cols; ++x)
-      for (int c = 0; c < ch; ++c) {
-        int s = 0;
-        for (int i = 0; i < 7; ++i) s += k[i] * tmp[((size_t)clampi(y + i - 3, 0, rows - 1) * cols + x) * ch + c];
-        dst[((size_t)y * cols + x) * ch + c] = (u8)((s + 32768) >> 16);
-      }
+  std::vector<u8> pad;
+  pad_image(src, rows, cols, ch, 3, 0, pad);
+  const int pc = cols + 6, n = cols * ch;
+  std::vector<u16> h((size_t)(rows + 6) * n);  // horizontal sums <= 255*256 fit 16 bits
+  for (int y = 0; y < rows + 6; ++y) {
+    const u8* p = pad.data() + (size_t)y * pc * ch;
+    u16* o = h.data() + (size_t)y * n;
+    for (int i = 0; i < n; ++i)
+      o[i] = (u16)(8 * (p[i] + p[i + 6 * ch]) + 28 * (p[i + ch] + p[i + 5 * ch]) + 56 * (p[i + 2 * ch] + p[i + 4 * ch]) + 72 * p[i + 3 * ch]);
+  }
+  for (int y = 0; y < rows; ++y) {
+    const u16 *r0 = h.data() + (size_t)y * n, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n, *r4 = r3 + n, *r5 = r4 + n, *r6 = r5 + n;
+    u8* o = dst + (size_t)y * n;
+    for (int i = 0; i < n; ++i) {
+      unsigned s = 8u * (r0[i] + r6[i]) + 28u * (r1[i] + r5[i]) + 56u * (r2[i] + r4[i]) + 72u * r3[i];
+      o[i] = (u8)((s + 32768u) >> 16);
+    }
+  }
 }
 
 // cv::Sobel(src, d, CV_16S, {1,0}|{0,1}, 3, 1, 0, BORDER_REPLICATE) on CV_8UC{ch}.
 static void sobel3(const u8* src, int rows, int cols, int ch, int16_t* dx, int16_t* dy) {
+  std::vector<u8> pad;
+  pad_image(src, rows, cols, ch, 1, 0, pad);
+  const int pc = cols + 2, n = cols * ch;
   for (int y = 0; y < rows; ++y) {
-    int ym = clampi(y - 1, 0, rows - 1), yp = clampi(y + 1, 0, rows - 1);
-    for (int x = 0; x < cols; ++x) {
-      int xm = clampi(x - 1, 0, cols - 1), xp = clampi(x + 1, 0, cols - 1);
-      for (int c = 0; c < ch; ++c) {
-#define P(yy, xx) ((int)src[((size_t)(yy) * cols + (xx)) * ch + c])
-        int gx = (P(ym, xp) + 2 * P(y, xp) + P(yp, xp)) - (P(ym, xm) + 2 * P(y, xm) + P(yp, xm));
-        int gy = (P(yp, xm) + 2 * P(yp, x) + P(yp, xp)) - (P(ym, xm) + 2 * P(ym, x) + P(ym, xp));
-#undef P
-        dx[((size_t)y * cols + x) * ch + c] = (int16_t)gx;
-        dy[((size_t)y * cols + x) * ch + c] = (int16_t)gy;
-      }
+    const u8 *a = pad.data() + (size_t)y * pc * ch, *b = a + (size_t)pc * ch, *c = b + (size_t)pc * ch;
+    int16_t *ox = dx + (size_t)y * n, *oy = dy + (size_t)y * n;
+    for (int i = 0; i < n; ++i) {
+      int l = a[i] + 2 * b[i] + c[i], r = a[i + 2 * ch] + 2 * b[i + 2 * ch] + c[i + 2 * ch];
+      int t = a[i] + 2 * a[i + ch] + a[i + 2 * ch], u = c[i] + 2 * c[i + ch] + c[i + 2 * ch];
+      ox[i] = (int16_t)(r - l);
+      oy[i] = (int16_t)(u - t);
     }
   }
 }
@@ -162,20 +183,25 @@ static inline int orientation16(int dx, int dy, int fused) {
 // cv::pyrDown(src, dst, Size(cols/2, rows/2)) on CV_8UC{ch}: 5x5 [1 4 6 4 1]^2,
 // BORDER_REFLECT_101, (sum+128)>>8.  
 static void pyrdown(const u8* src, int rows, int cols, int ch, u8* dst) {
-  static const int w[5] = {1, 4, 6, 4, 1};
   int drows = rows / 2, dcols = cols / 2;
-  for (int y = 0; y < drows; ++y)
+  std::vector<u8> pad;
+  pad_image(src, rows, cols, ch, 2, 1, pad);
+  const int pc = cols + 4, n = dcols * ch;
+  std::vector<u16> h((size_t)(rows + 4) * n);  // horizontal sums at even columns, <= 255*16
+  for (int y = 0; y < rows + 4; ++y) {
+    const u8* p = pad.data() + (size_t)y * pc * ch;
+    u16* o = h.data() + (size_t)y * n;
     for (int x = 0; x < dcols; ++x)
       for (int c = 0; c < ch; ++c) {
-        int s = 0;
-        for (int i = 0; i < 5; ++i) {
-          int sy = reflect101(2 * y + i - 2, rows);
-          int rs = 0;
-          for (int j = 0; j < 5; ++j) rs += w[j] * src[((size_t)sy * cols + reflect101(2 * x + j - 2, cols)) * ch + c];
-          s += w[i] * rs;
-        }
-        dst[((size_t)y * dcols + x) * ch + c] = (u8)((s + 128) >> 8);
+        const u8* q = p + (size_t)(2 * x) * ch + c;
+        o[x * ch + c] = (u16)(q[0] + 4 * q[ch] + 6 * q[2 * ch] + 4 * q[3 * ch] + q[4 * ch]);
       }
+  }
+  for (int y = 0; y < drows; ++y) {
+    const u16 *r0 = h.data() + (size_t)(2 * y) * n, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n, *r4 = r3 + n;
+    u8* o = dst + (size_t)y * n;
+    for (int i = 0; i < n; ++i) o[i] = (u8)((r0[i] + 4 * r1[i] + 6 * r2[i] + 4 * r3[i] + r4[i] + 128) >> 8);
+  }
 }
 
 // cv::resize(src, dst, Size(dcols,drows), 0, 0, INTER_NEAREST) on CV_8UC1.
@@ -191,17 +217,52 @@ static void resize_nn(const u8* src, int rows, int cols, u8* dst, int drows, int
 }
 
 // cv::medianBlur(src, dst, 5) on CV_8UC1 (replicate border, 13th of 25).
+// Maps made of 0 / one-hot bytes (every linemod normal map) take a counting path: per column the 5-row
+// window is folded into eight byte-wide label counters, each output adds five column counters.
 static void median5(const u8* src, int rows, int cols, u8* dst) {
   std::vector<u8> out((size_t)rows * cols);
-  u8 v[25];
-  for (int y = 0; y < rows; ++y)
-    for (int x = 0; x < cols; ++x) {
-      int n = 0;
-      for (int i = -2; i <= 2; ++i)
-        for (int j = -2; j <= 2; ++j) v[n++] = src[(size_t)clampi(y + i, 0, rows - 1) * cols + clampi(x + j, 0, cols - 1)];
-      std::nth_element(v, v + 12, v + 25);
-      out[(size_t)y * cols + x] = v[12];
+  bool onehot = true;
+  for (size_t i = 0; i < (size_t)rows * cols && onehot; ++i) onehot = (src[i] & (src[i] - 1)) == 0;
+  if (onehot) {
+    std::vector<u8> pad;
+    pad_image(src, rows, cols, 1, 2, 0, pad);
+    const int pc = cols + 4;
+    std::vector<uint32_t> lo(pc), hi(pc);
+    for (int y = 0; y < rows; ++y) {
+      for (int x = 0; x < pc; ++x) {
+        uint32_t l = 0, h = 0;
+        for (int i = 0; i < 5; ++i) {
+          uint32_t v = pad[(size_t)(y + i) * pc + x];
+          l += ((v & 15u) * 0x00204081u) & 0x01010101u;
+          h += ((v >> 4) * 0x00204081u) & 0x01010101u;
+        }
+        lo[x] = l; hi[x] = h;
+      }
+      for (int x = 0; x < cols; ++x) {
+        uint32_t l = lo[x] + lo[x + 1] + lo[x + 2] + lo[x + 3] + lo[x + 4];
+        uint32_t h = hi[x] + hi[x + 1] + hi[x + 2] + hi[x + 3] + hi[x + 4];
+        int c[8] = {(int)(l & 255), (int)((l >> 8) & 255), (int)((l >> 16) & 255), (int)(l >> 24),
+                    (int)(h & 255), (int)((h >> 8) & 255), (int)((h >> 16) & 255), (int)(h >> 24)};
+        int acc = 25 - (c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7]);
+        u8 res = 0;
+        for (int b = 0; b < 8 && acc < 13; ++b) {
+          acc += c[b];
+          if (acc >= 13) res = (u8)(1u << b);
+        }
+        out[(size_t)y * cols + x] = res;
+      }
     }
+  } else {
+    u8 v[25];
+    for (int y = 0; y < rows; ++y)
+      for (int x = 0; x < cols; ++x) {
+        int n = 0;
+        for (int i = -2; i <= 2; ++i)
+          for (int j = -2; j <= 2; ++j) v[n++] = src[(size_t)clampi(y + i, 0, rows - 1) * cols + clampi(x + j, 0, cols - 1)];
+        std::nth_element(v, v + 12, v + 25);
+        out[(size_t)y * cols + x] = v[12];
+      }
+  }
   std::memcpy(dst, out.data(), out.size());
 }
 
@@ -378,11 +439,12 @@ static void similarity_lut(int circular, u8* out) {
 }
 
 static void response_maps(const u8* spread_img, size_t n, const u8* lut, u8* out /*[8][n]*/) {
+  u8 tab[256][8];  // all 8 orientation responses of one spread byte: max(lut_low[s&15], lut_hi[s>>4])
+  for (int s = 0; s < 256; ++s)
+    for (int ori = 0; ori < 8; ++ori) tab[s][ori] = std::max(lut[32 * ori + (s & 15)], lut[32 * ori + 16 + (s >> 4)]);
   for (int ori = 0; ori < 8; ++ori) {
-    const u8* lo = lut + 32 * ori;
-    const u8* hi = lo + 16;
     u8* o = out + (size_t)ori * n;
-    for (size_t i = 0; i < n; ++i) o[i] = std::max(lo[spread_img[i] & 15], hi[spread_img[i] >> 4]);
+    for (size_t i = 0; i < n; ++i) o[i] = tab[spread_img[i]][ori];
   }
 }
 
@@ -813,23 +875,25 @@ struct Detector {
     MatchResult* R = new MatchResult();
     int M = (int)modalities.size();
     auto t0 = clk::now();
-    std::vector<Pyramid> quantizers;
-    for (int i = 0; i < M; ++i) quantizers.push_back(process(i, srcs[i], rows, cols, masks ? masks[i] : nullptr));
     R->mems.resize((size_t)levels * M);
     R->quantized.resize((size_t)levels * M);
     R->qrows.resize((size_t)levels * M);
     R->qcols.resize((size_t)levels * M);
-    for (int l = 0; l < levels; ++l) {
-      int Tl = T[l];
-      if (l > 0)
-        for (int i = 0; i < M; ++i) quantizers[i].pyr_down();
-      for (int i = 0; i < M; ++i) {
+    // Upstream walks levels outside, modalities inside; the per-modality chains are independent, so with
+    // threads > 1 each modality runs its whole pyramid (process, pyrDown, quantize, spread, response,
+    // linearize) on its own thread.  Results are identical.
+    std::vector<int> errs(M, 0);
+    auto chain = [&](int i) {
+      Pyramid qp = process(i, srcs[i], rows, cols, masks ? masks[i] : nullptr);
+      for (int l = 0; l < levels; ++l) {
+        int Tl = T[l];
+        if (l > 0) qp.pyr_down();
         std::vector<u8> q;
-        quantizers[i].quantize(q);
-        int r = quantizers[i].rows, c = quantizers[i].cols;
+        qp.quantize(q);
+        int r = qp.rows, c = qp.cols;
         if ((r * c) % 16 != 0 || r % Tl != 0 || c % Tl != 0) {  // [UP] CV_Assert in computeResponseMaps/linearize
-          R->error = -3;
-          return R;
+          errs[i] = -3;
+          return;
         }
         size_t n = (size_t)r * c;
         std::vector<u8> sp(n), resp(8 * n);
@@ -843,7 +907,16 @@ struct Detector {
         R->qcols[(size_t)l * M + i] = c;
         if (debug) R->quantized[(size_t)l * M + i] = q;
       }
+    };
+    if (threads > 1 && M > 1) {
+      std::vector<std::thread> pool;
+      for (int i = 0; i < M; ++i) pool.emplace_back(chain, i);
+      for (auto& th : pool) th.join();
+    } else {
+      for (int i = 0; i < M; ++i) chain(i);
     }
+    for (int i = 0; i < M; ++i)
+      if (errs[i]) { R->error = errs[i]; return R; }
     auto t1 = clk::now();
     std::vector<std::string> ids = class_ids();
     if (class_list.empty()) {
