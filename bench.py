@@ -311,8 +311,15 @@ def main():
             kernels[k]["alg_GBps"] = round(b / (prof["ms"][k] * 1e-3) / 1e9, 1)
     dom = "sim_coarse"
     ach = kernels.get(dom, {}).get("alg_GBps", 0.0)
+    traffic = None   # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (same launch shape only)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["similarity_coarse_kernel"]
+        if B == 96 and n_tpl == 3000 and args.shard == "frames":
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"kernel": "similarity_coarse_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4) if peak else None, "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4) if peak else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels.get(dom, {}).get("alg_bytes_per_launch"),
                 "note": "linear memories are L2-resident: the gather is bounded by L2, HBM copy bandwidth is the reported denominator"}
     sim_ms = prof["ms"]["sim_coarse"] + prof["ms"]["sim_local"]
