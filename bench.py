@@ -289,6 +289,18 @@ def main():
         e2e = {"value": B * K * world / dt, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES,
                "d2h_bytes_per_step": B * (16 + 1024 * 16), "ms_per_step": 1e3 * dt / K}
 
+    # ---- single-frame latency of the reference-facing call (configs[1] literally: one frame, host buffers in, matches out)
+    single = None
+    if not allg and not args.no_e2e:
+        prep1 = det.prepareBatch(frames[:1], cap=8192)
+        lat = []
+        for i in range(60):
+            t0 = time.perf_counter()
+            det.matchPrepared(prep1, args.threshold)
+            lat.append(time.perf_counter() - t0)
+        lat = sorted(lat[10:])
+        single = {"median_ms": 1e3 * lat[len(lat) // 2], "p90_ms": 1e3 * lat[int(len(lat) * 0.9)], "frames_per_s": 1.0 / lat[len(lat) // 2]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -345,7 +357,7 @@ def main():
                        "frames_per_step_per_gpu": B, "templates": n_tpl, "planted_templates": planted, "shard": args.shard,
                        "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of linear memories per step" % (B * FRAME_BYTES / 1e6, B * 6.144)},
             "e2e": e2e, "gpu_launches": int(sum(launches.values())), "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clocks, "kernels": kernels, "similarity_GBps": sim_gbps, "matches_per_step": n_matches,
+            "clocks": clocks, "kernels": kernels, "similarity_GBps": sim_gbps, "single_frame": single, "matches_per_step": n_matches,
             "candidates_per_step": None}
     print(json.dumps(line))
     if dist is not None:

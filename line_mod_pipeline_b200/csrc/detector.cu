@@ -167,7 +167,7 @@ static int rebuild_templates(lmb200_detector* h) {
       }
     ALLOC(h->d_hdr[l], hdr.size() * sizeof(TplHdr));
     ALLOC(h->d_feat[l], feat.size() * sizeof(u32));
-    ALLOC(h->d_offs[l], feat.size() * sizeof(u32));
+    ALLOC(h->d_offs[l], (size_t)std::max(1, h->ntpl) * M * (l == L - 1 ? COARSE_SLOTS : FEAT_SLOTS) * sizeof(u32));
     CU(cudaMemcpy(h->d_hdr[l].p, hdr.data(), hdr.size() * sizeof(TplHdr), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_feat[l].p, feat.data(), feat.size() * sizeof(u32), cudaMemcpyHostToDevice));
   }
@@ -238,7 +238,7 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
         ALLOC(lb.lm[m], lb.lm_stride * S);
         CU(cudaMemset(lb.lm[m].p, 0, lb.lm_stride * S));  // the pad bytes stay zero forever
         if (l == L - 1) {  // nibble-packed copy read by similarity_coarse_kernel
-          lb.lmn_stride = up256((size_t)4 * r * c + LM_PAD);
+          lb.lmn_stride = up256((size_t)4 * r * c + LM_PAD) + coarse_zero_tail(lb.g);  // zero tail: padded plan rows read it
           ALLOC(lb.lmn[m], lb.lmn_stride * S);
           CU(cudaMemset(lb.lmn[m].p, 0, lb.lmn_stride * S));
         }

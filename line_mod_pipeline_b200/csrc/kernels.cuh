@@ -13,6 +13,7 @@ typedef uint32_t u32;
 
 constexpr int MAX_MOD = 4;
 constexpr int FEAT_SLOTS = 64;        // per modality per template (upstream asserts <= 63 features)
+constexpr int COARSE_SLOTS = 72;      // coarsest-level plan: 63 features + padding of every word-shift bucket to a multiple of 3
 constexpr u32 OFF_INVALID = 0xFFFFFFFFu;
 constexpr int LM_PAD = 256;           // zero slack after each linear-memory block (realigned 16 B loads overrun)
 
@@ -30,7 +31,8 @@ struct alignas(8) TplHdr {
   short height[MAX_MOD];
   u8 nf[MAX_MOD];
   u32 flags;                          // bit0: local-safe, bit1: coarse-safe (set by the plan kernel)
-  u32 bkt[MAX_MOD];                   // plan: per modality, 4 x u8 counts of valid offsets per word shift (off>>2)&3
+  u32 bkt[MAX_MOD];                   // plan: per modality, 4 x u8 counts of (padded) offsets per word-shift bucket
+  int P[MAX_MOD];                     // plan: upstream's template_positions per modality (clamped to W*H)
 };
 
 // Register-resident view of a TplHdr (dynamic modality index without local memory).
@@ -100,8 +102,12 @@ void launch_spread_linearize(const u8* q, size_t q_stride, const u8* mask, size_
 
 // ------------------------------------------------------------------ template side
 // Plan: flat linear-memory offsets of every feature for one level's geometry + safe flags.
+// coarsest = true: nibble-space buckets ((off>>3)&3), COARSE_SLOTS per modality, every bucket padded to a multiple of 3
+// with offsets into the zero tail behind the nibble-packed linear memory (so the coarse kernel runs groups of 3 only).
 void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g,
-                          bool nibble_sort, cudaStream_t st);
+                          bool coarsest, cudaStream_t st);
+// bytes of the zero tail the coarse kernel may read behind a nibble-packed block of 4*per_label bytes
+inline size_t coarse_zero_tail(const LevelGeom& g) { return (((size_t)g.W * g.H / 2 + 64) + 255) & ~(size_t)255; }
 // byte linear memory -> nibble-packed copy (coarsest level only; input of similarity_coarse_kernel)
 void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_stride, LevelGeom g, int frames,
                          cudaStream_t st);

@@ -22,7 +22,7 @@ namespace lmk {
 //            bit1 coarse-safe : every feature row + template_positions stays inside its label's block
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restrict__ feat, u32* __restrict__ offs,
-                                                            TplHdr* __restrict__ hdr, int ntpl, int M, LevelGeom g, int key_shift) {
+                                                            TplHdr* __restrict__ hdr, int ntpl, int M, LevelGeom g, int coarsest) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntpl) return;
   TplHdr h = hdr[warp];
@@ -53,36 +53,48 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
         if (!(f >> 31) || x > h.width[0] || y > h.height[0]) local_safe = false;
       }
       off2[j] = off;
-      key2[j] = off == OFF_INVALID ? 4 : (int)((off >> key_shift) & 3);
+      key2[j] = off == OFF_INVALID ? 4 : (int)((off >> (coarsest ? 3 : 2)) & 3);
     }
     // counting sort by key (0..3 valid buckets, 4 = dropped)
+    const int slots = coarsest ? COARSE_SLOTS : FEAT_SLOTS;
     u32 start = 0, packed = 0;
     u32 dst[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    u32* o = offs + ((size_t)warp * M + m) * slots;
+    for (int s0 = lane; s0 < slots; s0 += 32) o[s0] = OFF_INVALID;
+    __syncwarp();
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       u32 b0 = __ballot_sync(0xffffffffu, key2[0] == w), b1 = __ballot_sync(0xffffffffu, key2[1] == w);
       u32 c0 = __popc(b0), c1 = __popc(b1);
       if (key2[0] == w) dst[0] = start + __popc(b0 & lt);
       if (key2[1] == w) dst[1] = start + c0 + __popc(b1 & lt);
-      packed |= (c0 + c1) << (8 * w);
-      start += c0 + c1;
+      u32 cnt = c0 + c1;
+      if (coarsest) {  // pad to a multiple of 3 with rows of the zero tail that have this bucket's word shift
+        u32 padded = (cnt + 2) / 3 * 3;
+        if (lane < (int)(padded - cnt)) o[start + cnt + lane] = 8u * g.per_label + 8u * (u32)w;
+        cnt = padded;
+      }
+      packed |= cnt << (8 * w);
+      start += cnt;
     }
-    u32* o = offs + ((size_t)warp * M + m) * FEAT_SLOTS;
-    o[lane] = OFF_INVALID; o[lane + 32] = OFF_INVALID;
-    __syncwarp();
     if (dst[0] != 0xFFFFFFFFu) o[dst[0]] = off2[0];
     if (dst[1] != 0xFFFFFFFFu) o[dst[1]] = off2[1];
-    if (lane == 0) hdr[warp].bkt[m] = packed;
+    if (lane == 0) {
+      hdr[warp].bkt[m] = packed;
+      int wf = (hdr[warp].width[m] - 1) / T + 1, hf = (hdr[warp].height[m] - 1) / T + 1;
+      int P = (H - hf) * W + (W - wf) + 1;
+      hdr[warp].P[m] = P > (int)plane ? (int)plane : P;
+    }
   }
   local_safe = __all_sync(0xffffffffu, local_safe);
   coarse_safe = __all_sync(0xffffffffu, coarse_safe);
   if (lane == 0) hdr[warp].flags = (local_safe ? 1u : 0u) | (coarse_safe ? 2u : 0u);
 }
 
-void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g, bool nibble_sort, cudaStream_t st) {
+void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g, bool coarsest, cudaStream_t st) {
   if (ntpl <= 0) return;
   int blocks = (ntpl * 32 + 127) / 128;
-  build_offsets_kernel<<<blocks, 128, 0, st>>>(feat, offs, hdr, ntpl, M, g, nibble_sort ? 3 : 2);
+  build_offsets_kernel<<<blocks, 128, 0, st>>>(feat, offs, hdr, ntpl, M, g, coarsest ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -138,13 +150,12 @@ __device__ __forceinline__ void mask_nibbles(u32& w0, u32& w1, u32& w2, u32& w3,
 struct NibAcc {
   u32 n0, n1, n2, n3;   // nibble accumulators (32 positions)
   u32 b[8];             // byte accumulators: b[2i+par] byte t <-> position 8i + 2t + par
-  int pend;             // features added since the last spill (warp-uniform)
   __device__ __forceinline__ void spill() {
     b[0] += n0 & 0x0F0F0F0Fu; b[1] += (n0 >> 4) & 0x0F0F0F0Fu;
     b[2] += n1 & 0x0F0F0F0Fu; b[3] += (n1 >> 4) & 0x0F0F0F0Fu;
     b[4] += n2 & 0x0F0F0F0Fu; b[5] += (n2 >> 4) & 0x0F0F0F0Fu;
     b[6] += n3 & 0x0F0F0F0Fu; b[7] += (n3 >> 4) & 0x0F0F0F0Fu;
-    n0 = n1 = n2 = n3 = 0u; pend = 0;
+    n0 = n1 = n2 = n3 = 0u;
   }
   // zero the byte sums of positions >= rem (0 < rem < 32): b[2i+par] byte t <-> position 8i + 2t + par
   __device__ __forceinline__ void mask_tail(int rem) {
@@ -178,58 +189,41 @@ __device__ __forceinline__ void realign_add(const uint4& A, const uint4& B, u32 
   acc.n0 += w0; acc.n1 += w1; acc.n2 += w2; acc.n3 += w3;
 }
 
-#ifndef CW_GROUP
-#define CW_GROUP 3   // feature rows whose loads are issued back to back (memory-level parallelism per warp)
-#endif
-
+// One word-shift bucket: its (padded) row count n is a multiple of 3, so the loop is groups of 3 rows only:
+// all loads first (6 x LDG.128 in flight per lane), then realign + one 3-input add per word (3*4 = 12 fits a
+// nibble), then the spill into byte sums.
 template <int WS, bool SAFE>
 __device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u32* __restrict__ lst, int k0, int n, int rem,
                                              int pos0, int P, u32 per_label, NibAcc& acc) {
-  int k = k0;
-  const int end = k0 + n;
-  if (SAFE) {
-    // groups of CW_GROUP rows: all loads first (6 x LDG.128 in flight per lane), then realign + add, then spill
-    if (k + CW_GROUP <= end && acc.pend) acc.spill();
-    for (; k + CW_GROUP <= end; k += CW_GROUP) {
-      u32 off[CW_GROUP];
-      uint4 A[CW_GROUP], B[CW_GROUP];
+  for (int k = k0; k < k0 + n; k += 3) {
+    u32 off[3];
+    uint4 A[3], B[3];
 #pragma unroll
-      for (int j = 0; j < CW_GROUP; ++j) off[j] = lst[k + j];
-      if (rem > 0) {
+    for (int j = 0; j < 3; ++j) off[j] = lst[k + j];
+    if (rem > 0) {
 #pragma unroll
-        for (int j = 0; j < CW_GROUP; ++j) {
-          const uint4* p = reinterpret_cast<const uint4*>(lmb + ((off[j] >> 1) & ~15u));
-          A[j] = __ldg(p); B[j] = __ldg(p + 1);
-        }
-#pragma unroll
-        for (int j = 0; j < CW_GROUP; ++j) realign_add<WS, false>(A[j], B[j], off[j], rem, acc);
+      for (int j = 0; j < 3; ++j) {
+        const uint4* p = reinterpret_cast<const uint4*>(lmb + ((off[j] >> 1) & ~15u));
+        A[j] = __ldg(p); B[j] = __ldg(p + 1);
       }
-      acc.spill();  // CW_GROUP <= 3 rows x 4 <= 12 fits a nibble
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        int nv = 32;
+        if (!SAFE) nv = min(P, (int)(per_label - off[j] % per_label)) - pos0;  // positions past the label block contribute 0
+        if (SAFE || nv > 0) realign_add<WS, !SAFE>(A[j], B[j], off[j], nv, acc);
+      }
     }
-  }
-  for (; k < end; ++k) {
-    const u32 off = lst[k];
-    int nv = rem;
-    if (!SAFE) nv = min(P, (int)(per_label - off % per_label)) - pos0;  // positions past the label block contribute 0
-    if (nv > 0) {
-      const uint4* p = reinterpret_cast<const uint4*>(lmb + ((off >> 1) & ~15u));
-      const uint4 A = __ldg(p), B = __ldg(p + 1);
-      realign_add<WS, !SAFE>(A, B, off, nv, acc);
-    }
-    if (++acc.pend == 3) acc.spill();
+    acc.spill();
   }
 }
 
 struct CoarseCtx {
   HdrR hdr;
-  const u32* lst;                    // this warp's staged offsets [M][FEAT_SLOTS] (shared memory)
+  const u32* lst;                    // this warp's staged offsets [M][COARSE_SLOTS] (shared memory)
   int M, T, W, H, HW, raw_thr, nf_total;
   u32 per_label;
-  __device__ __forceinline__ int P(int m) const {  // upstream's template_positions
-    int wf = (hdr.width(m) - 1) / T + 1, hf = (hdr.height(m) - 1) / T + 1;
-    int p = (H - hf) * W + (W - wf) + 1;
-    return p > HW ? HW : p;
-  }
+  const int* Pm;                     // plan: upstream's template_positions per modality
+  __device__ __forceinline__ int P(int m) const { return __ldg(Pm + m); }
 };
 
 // value of position p (compile-time) from the byte accumulators / the u16 totals
@@ -255,7 +249,7 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
   for (int c0 = 0; 32 * c0 < Pmax; c0 += 32) {
     const int pos0 = 32 * (c0 + lane);
     NibAcc acc;
-    acc.n0 = acc.n1 = acc.n2 = acc.n3 = 0u; acc.pend = 0;
+    acc.n0 = acc.n1 = acc.n2 = acc.n3 = 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.b[i] = 0u;
     u32 tot[WIDE ? 16 : 8];  // WIDE: u16 pairs (see wide_val); else byte sums laid out like acc.b
@@ -268,12 +262,11 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       const u8* lmb = s_lm[m] + (pos0 >> 1);
       const u32 bk = cx.hdr.bkt(m);
       const int n0 = bk & 255, n1 = (bk >> 8) & 255, n2 = (bk >> 16) & 255, n3 = bk >> 24;
-      const u32* lst = cx.lst + m * FEAT_SLOTS;
+      const u32* lst = cx.lst + m * COARSE_SLOTS;
       accum_bucket<0, SAFE>(lmb, lst, 0, n0, rem, pos0, P, cx.per_label, acc);
       accum_bucket<1, SAFE>(lmb, lst, n0, n1, rem, pos0, P, cx.per_label, acc);
       accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, rem, pos0, P, cx.per_label, acc);
       accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, rem, pos0, P, cx.per_label, acc);
-      acc.spill();
       if (SAFE && rem > 0 && rem < 32) acc.mask_tail(rem);  // at most one lane per modality: the row tail
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
@@ -377,7 +370,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kernel(MatchParams mp, LevelParams lp) {
   __shared__ const u8* s_lm[MAX_MOD];
   __shared__ u32 s_queue[CW_WARPS][CW_QCAP];
-  __shared__ u32 s_off[CW_WARPS][MAX_MOD * FEAT_SLOTS];
+  __shared__ u32 s_off[CW_WARPS][MAX_MOD * COARSE_SLOTS];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {  // lp.lm = nibble-packed linear memories of the coarsest level
@@ -399,7 +392,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kern
   if (cx.raw_thr > 0x7FFE) cx.raw_thr = 0x7FFE;  // nothing can exceed it anyway (scores <= 1008)
   if (cx.raw_thr < 0) cx.raw_thr = -1;
   cx.lst = s_off[warp];
-  for (int s = lane; s < cx.M * FEAT_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * FEAT_SLOTS + s);
+  cx.Pm = lp.hdr[g].P;
+  for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * COARSE_SLOTS + s);
   __syncwarp();
   if (cx.hdr.flags & 2u) coarse_template<true, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
   else coarse_template<false, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
