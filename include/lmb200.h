@@ -130,6 +130,24 @@ int lmb200_read(const char* path, int device, lmb200_handle* out);
 int lmb200_write_classes(lmb200_handle h, const char* format);
 int lmb200_read_classes(lmb200_handle h, const char* const* class_ids, int n, const char* format);
 
+/* Fast binary cache of the whole detector (config + every template pyramid, 5 bytes per feature): parsing the
+ * YAML of a 20 000-template set takes seconds, the cache loads in milliseconds.  Not an interchange format. */
+int lmb200_write_cache(lmb200_handle h, const char* path);
+int lmb200_read_cache(const char* path, int device, lmb200_handle* out);
+
+/* The reference's pose sidecar linemod_tempPosFile.bin (HighLevelLinemod.cpp:272-284, :302-317): u32 class count,
+ * then per class u64 n + n raw `struct HighLevelLineMOD::Template` records (HighLevelLinemod.h:130-148:
+ * glm::vec3, glm::qua<float>, cv::Rect, uint16_t; 48 bytes with padding).  It maps template_id -> pose. */
+typedef struct {
+  float translation[3];
+  float quaternion[4];      /* glm::qua<float> storage order as written by the reference build */
+  int bb[4];                /* cv::Rect x, y, width, height */
+  uint16_t median_depth;
+  uint16_t pad;
+} lmb200_template_pose;     /* sizeof == 48 == sizeof(HighLevelLineMOD::Template) */
+int lmb200_read_pose_sidecar(const char* path, int class_index, lmb200_template_pose* out, size_t cap, size_t* n_out);
+int lmb200_write_pose_sidecar(const char* path, const lmb200_template_pose* const* per_class, const size_t* counts, int n_classes);
+
 /* ---- matching ------------------------------------------------------------------------ */
 /* Replaces detector->match(sources, threshold, matches, class_ids, quantized_images, masks)
  * (HighLevelLinemod.cpp:152).  Result order is upstream's: generation order (class, template_id,

@@ -75,6 +75,10 @@ SIGNATURES = {
     "lmb200_read": (C.c_int, [C.c_char_p, C.c_int, _P(_H)]),
     "lmb200_write_classes": (C.c_int, [_H, C.c_char_p]),
     "lmb200_read_classes": (C.c_int, [_H, _P(C.c_char_p), C.c_int, C.c_char_p]),
+    "lmb200_write_cache": (C.c_int, [_H, C.c_char_p]),
+    "lmb200_read_cache": (C.c_int, [C.c_char_p, C.c_int, _P(_H)]),
+    "lmb200_read_pose_sidecar": (C.c_int, [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
+    "lmb200_write_pose_sidecar": (C.c_int, [C.c_char_p, _P(C.c_void_p), _P(C.c_size_t), C.c_int]),
     "lmb200_match": (C.c_int, [_H, _P(Image), C.c_int, C.c_float, _P(C.c_char_p), C.c_int, _P(MatchRec), C.c_size_t,
                                _P(C.c_size_t), _P(Image), _P(Image)]),
     "lmb200_match_batch": (C.c_int, [_H, _P(Image), C.c_int, C.c_int, C.c_float, _P(C.c_char_p), C.c_int,

@@ -48,6 +48,7 @@ void default_normal_lut(uint8_t* out) {
 }  // namespace lmh
 
 static std::string g_create_error;
+namespace lmh { void set_create_error(const std::string& msg) { g_create_error = msg; } }
 
 extern "C" {
 

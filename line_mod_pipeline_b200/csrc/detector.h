@@ -146,6 +146,9 @@ int write_detector_file(lmb200_detector* h, const char* path);
 int read_detector_file(const char* path, int device, lmb200_handle* out, std::string& err);
 int write_class_file(lmb200_detector* h, const std::string& class_id, const char* path);
 int read_class_file(lmb200_detector* h, const char* path, std::string& err);
+int write_cache_file(lmb200_detector* h, const char* path);
+int read_cache_file(const char* path, int device, lmb200_handle* out, std::string& err);
+void set_create_error(const std::string& msg);
 // comm.cpp
 int comm_unique_id(uint8_t* id128, std::string& err);
 int comm_init(lmb200_detector* h, const uint8_t* id128, int rank, int world);

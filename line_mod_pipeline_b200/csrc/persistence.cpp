@@ -377,4 +377,138 @@ int read_class_file(lmb200_detector* h, const char* path, std::string& err) {
   return LMB200_OK;
 }
 
+// ------------------------------------------------------------------ binary cache
+namespace {
+const char CACHE_MAGIC[8] = {'L', 'M', 'B', '2', 'T', 'P', 'L', '1'};
+template <typename T> void put(std::string& b, const T& v) { b.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <typename T> bool get(const std::string& b, size_t& p, T& v) {
+  if (p + sizeof(T) > b.size()) return false;
+  std::memcpy(&v, b.data() + p, sizeof(T));
+  p += sizeof(T);
+  return true;
+}
+}  // namespace
+
+int write_cache_file(lmb200_detector* h, const char* path) {
+  std::string b(CACHE_MAGIC, 8);
+  put(b, h->cfg);
+  put(b, (uint32_t)h->classes.size());
+  for (auto& kv : h->classes) {
+    put(b, (uint32_t)kv.first.size());
+    b += kv.first;
+    put(b, (uint32_t)kv.second.size());
+    for (auto& tp : kv.second)
+      for (auto& t : tp) {
+        put(b, (int32_t)t.width); put(b, (int32_t)t.height); put(b, (int32_t)t.pyramid_level); put(b, (uint32_t)t.features.size());
+        for (auto& f : t.features) { put(b, (int16_t)f.x); put(b, (int16_t)f.y); put(b, (uint8_t)f.label); }
+      }
+  }
+  FILE* fp = std::fopen(path, "wb");
+  if (!fp) return set_error(h, LMB200_E_IO, std::string("cannot open ") + path + " for writing");
+  size_t w = std::fwrite(b.data(), 1, b.size(), fp);
+  std::fclose(fp);
+  return w == b.size() ? LMB200_OK : set_error(h, LMB200_E_IO, "short write");
+}
+
+int read_cache_file(const char* path, int device, lmb200_handle* out, std::string& err) {
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) { err = std::string("cannot open ") + path; return LMB200_E_IO; }
+  std::string b;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, fp)) > 0) b.append(buf, n);
+  std::fclose(fp);
+  size_t p = 8;
+  lmb200_config cfg;
+  uint32_t ncls = 0;
+  if (b.size() < 8 || std::memcmp(b.data(), CACHE_MAGIC, 8) != 0 || !get(b, p, cfg) || !get(b, p, ncls)) { err = "not an lmb200 template cache"; return LMB200_E_IO; }
+  cfg.device = device;
+  lmb200_handle h = nullptr;
+  int rc = lmb200_create(&cfg, &h);
+  if (rc) { err = lmb200_last_error(nullptr); return rc; }
+  const int per = cfg.num_modalities * cfg.pyramid_levels;
+  for (uint32_t c = 0; c < ncls; ++c) {
+    uint32_t len = 0, nt = 0;
+    if (!get(b, p, len) || p + len > b.size()) { lmb200_destroy(h); err = "truncated cache"; return LMB200_E_IO; }
+    std::string id = b.substr(p, len);
+    p += len;
+    if (!get(b, p, nt)) { lmb200_destroy(h); err = "truncated cache"; return LMB200_E_IO; }
+    std::vector<TemplatePyramid>& tps = h->classes[id];
+    tps.resize(nt);
+    for (uint32_t t = 0; t < nt; ++t) {
+      tps[t].resize(per);
+      for (int k = 0; k < per; ++k) {
+        int32_t w, hh, lv; uint32_t nf;
+        if (!get(b, p, w) || !get(b, p, hh) || !get(b, p, lv) || !get(b, p, nf) || nf > 63 || p + 5ull * nf > b.size()) { lmb200_destroy(h); err = "corrupt cache"; return LMB200_E_IO; }
+        Template& tm = tps[t][k];
+        tm.width = w; tm.height = hh; tm.pyramid_level = lv;
+        tm.features.resize(nf);
+        for (uint32_t i = 0; i < nf; ++i) {
+          int16_t x, y; uint8_t l;
+          get(b, p, x); get(b, p, y); get(b, p, l);
+          tm.features[i] = Feature{x, y, l};
+        }
+      }
+    }
+  }
+  h->templates_dirty = true;
+  *out = h;
+  return LMB200_OK;
+}
+
 }  // namespace lmh
+
+extern "C" {
+
+int lmb200_write_cache(lmb200_handle h, const char* path) { return (h && path) ? lmh::write_cache_file(h, path) : LMB200_E_INVALID; }
+int lmb200_read_cache(const char* path, int device, lmb200_handle* out) {
+  if (!path || !out) return LMB200_E_INVALID;
+  std::string err;
+  int rc = lmh::read_cache_file(path, device, out, err);
+  if (rc) lmh::set_create_error(err);
+  return rc;
+}
+
+int lmb200_read_pose_sidecar(const char* path, int class_index, lmb200_template_pose* out, size_t cap, size_t* n_out) {
+  static_assert(sizeof(lmb200_template_pose) == 48, "must mirror HighLevelLineMOD::Template");
+  if (!path || !n_out || class_index < 0) return LMB200_E_INVALID;
+  *n_out = 0;
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return LMB200_E_IO;
+  uint32_t ncls = 0;
+  int rc = LMB200_E_IO;
+  if (std::fread(&ncls, sizeof ncls, 1, fp) == 1) {
+    for (uint32_t c = 0; c < ncls; ++c) {
+      uint64_t n = 0;
+      if (std::fread(&n, sizeof n, 1, fp) != 1) break;
+      if ((int)c == class_index) {
+        *n_out = (size_t)n;
+        size_t take = n < cap ? (size_t)n : cap;
+        if (out && take && std::fread(out, sizeof(lmb200_template_pose), take, fp) != take) break;
+        rc = (take < n) ? LMB200_E_TRUNCATED : LMB200_OK;
+        break;
+      }
+      if (std::fseek(fp, (long)(n * sizeof(lmb200_template_pose)), SEEK_CUR) != 0) break;
+    }
+    if (rc == LMB200_E_IO && class_index >= (int)ncls) rc = LMB200_E_CLASS;
+  }
+  std::fclose(fp);
+  return rc;
+}
+
+int lmb200_write_pose_sidecar(const char* path, const lmb200_template_pose* const* per_class, const size_t* counts, int n_classes) {
+  if (!path || n_classes < 0 || (n_classes > 0 && (!per_class || !counts))) return LMB200_E_INVALID;
+  FILE* fp = std::fopen(path, "wb");
+  if (!fp) return LMB200_E_IO;
+  uint32_t ncls = (uint32_t)n_classes;
+  std::fwrite(&ncls, sizeof ncls, 1, fp);
+  for (int c = 0; c < n_classes; ++c) {
+    uint64_t n = counts[c];
+    std::fwrite(&n, sizeof n, 1, fp);
+    if (n) std::fwrite(per_class[c], sizeof(lmb200_template_pose), (size_t)n, fp);
+  }
+  std::fclose(fp);
+  return LMB200_OK;
+}
+
+}  // extern "C"

@@ -177,6 +177,18 @@ class Detector:
             raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode())
         return cls(_handle=h)
 
+    def writeCache(self, path):
+        self._check(self._L.lmb200_write_cache(self._h, str(path).encode()))
+
+    @classmethod
+    def readCache(cls, path, device=-1):
+        L = K.lib()
+        h = K._H()
+        rc = L.lmb200_read_cache(str(path).encode(), device, C.byref(h))
+        if rc:
+            raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode())
+        return cls(_handle=h)
+
     def writeClasses(self, fmt="templates_%s.yml.gz"):
         self._check(self._L.lmb200_write_classes(self._h, fmt.encode()))
 
@@ -367,6 +379,36 @@ def getDefaultLINE(**kw):
 def getDefaultLINEMOD(**kw):
     """cv::linemod::getDefaultLINEMOD(): ColorGradient + DepthNormal, T={5,8} (reference: HighLevelLinemod.cpp:26-35)."""
     return Detector([ColorGradient(), DepthNormal()], (5, 8), **kw)
+
+
+POSE_DTYPE = np.dtype([("translation", np.float32, 3), ("quaternion", np.float32, 4), ("bb", np.int32, 4),
+                       ("median_depth", np.uint16), ("pad", np.uint16)])
+assert POSE_DTYPE.itemsize == 48
+
+
+def read_pose_sidecar(path, class_index):
+    """linemod_tempPosFile.bin (reference: HighLevelLinemod.cpp:272-284) -> structured array of one class."""
+    L = K.lib()
+    n = C.c_size_t(0)
+    rc = L.lmb200_read_pose_sidecar(str(path).encode(), class_index, None, 0, C.byref(n))
+    if rc not in (K.OK, K.E_TRUNCATED):
+        raise LinemodError(rc, "cannot read pose sidecar")
+    out = np.zeros(n.value, POSE_DTYPE)
+    if n.value:
+        rc = L.lmb200_read_pose_sidecar(str(path).encode(), class_index, out.ctypes.data, n.value, C.byref(n))
+        if rc:
+            raise LinemodError(rc, "cannot read pose sidecar")
+    return out
+
+
+def write_pose_sidecar(path, per_class):
+    L = K.lib()
+    arrs = [np.ascontiguousarray(a, POSE_DTYPE) for a in per_class]
+    ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+    counts = (C.c_size_t * max(1, len(arrs)))(*[len(a) for a in arrs])
+    rc = L.lmb200_write_pose_sidecar(str(path).encode(), ptrs, counts, len(arrs))
+    if rc:
+        raise LinemodError(rc, "cannot write pose sidecar")
 
 
 def comm_unique_id():

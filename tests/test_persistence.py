@@ -148,3 +148,41 @@ def test_config1_template_file_loads():
         assert [len(x["features"]) for x in tp] == [63, 63, 31, 31]
         assert [x["pyramid_level"] for x in tp] == [0, 0, 1, 1]
         assert tp[0]["width"] == tp[1]["width"] and tp[2]["width"] == tp[0]["width"] >> 1
+
+
+def test_binary_cache_round_trip_and_speed(tmp_path):
+    import time
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagergehaeuse_templates.yml.gz")
+    t0 = time.perf_counter(); d = lm.Detector.read(path); t_yaml = time.perf_counter() - t0
+    cache = str(tmp_path / "templates.lmb200")
+    d.writeCache(cache)
+    t0 = time.perf_counter(); e = lm.Detector.readCache(cache); t_bin = time.perf_counter() - t0
+    _same(d, e)
+    assert t_bin < t_yaml
+    with pytest.raises(lm.LinemodError) as err:
+        lm.Detector.readCache(path)          # a YAML file is not a cache
+    assert err.value.code == K.E_IO
+
+
+def test_pose_sidecar_round_trip(tmp_path):
+    """linemod_tempPosFile.bin: u32 class count, per class u64 n + n x 48-byte HighLevelLineMOD::Template records."""
+    import struct
+    rng = np.random.default_rng(3)
+    classes = []
+    for n in (5, 0, 3):
+        a = np.zeros(n, lm.POSE_DTYPE)
+        a["translation"] = rng.normal(size=(n, 3)); a["quaternion"] = rng.normal(size=(n, 4))
+        a["bb"] = rng.integers(0, 640, (n, 4)); a["median_depth"] = rng.integers(400, 1200, n)
+        classes.append(a)
+    p = str(tmp_path / "linemod_tempPosFile.bin")
+    lm.write_pose_sidecar(p, classes)
+    raw = open(p, "rb").read()
+    assert struct.unpack_from("<I", raw, 0)[0] == 3 and struct.unpack_from("<Q", raw, 4)[0] == 5
+    assert len(raw) == 4 + 3 * 8 + 8 * 48
+    tx, ty, tz, qx, qy, qz, qw, bx, by, bw, bh, md = struct.unpack_from("<3f4f4iH", raw, 12)   # the reference's raw struct dump
+    assert (bx, by, bw, bh, md) == tuple(classes[0]["bb"][0]) + (classes[0]["median_depth"][0],)
+    for i, a in enumerate(classes):
+        b = lm.read_pose_sidecar(p, i)
+        assert np.array_equal(a.tobytes(), b.tobytes())
+    with pytest.raises(lm.LinemodError):
+        lm.read_pose_sidecar(p, 7)
