@@ -9,6 +9,8 @@
 #include "../../include/lmb200.h"
 #include "kernels.cuh"
 
+#define LMB200_LANES 5
+
 namespace lmh {
 
 struct Feature { int x, y, label; };
@@ -39,7 +41,9 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   int alloc(size_t n);  // returns cudaError
+  bool view = false;    // alias of another allocation: never freed here
   void release();
+  void alias(void* ptr, size_t n);
   template <typename T> T* as() const { return (T*)p; }
 };
 
@@ -76,7 +80,7 @@ struct lmb200_detector {
   // ---- device ----
   bool device_ready = false;
   int device = -1;
-  lmh::Lane lanes[3];   // 0: compute, 1: copy, 2: second compute lane of the batch path
+  lmh::Lane lanes[LMB200_LANES];   // 0: compute, 1: copy, 2..4: extra compute lanes of the batch path
   lmh::DevBuf d_table, d_normal_lut;
   bool luts_dirty = true;
 
@@ -102,6 +106,7 @@ struct lmb200_detector {
   std::vector<lmh::LevelBuffers> levels;
   lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
   size_t depth_stride = 0;
+  lmh::DevBuf d_frames; size_t frame_bytes = 0, src_off[LMB200_MAX_MODALITIES] = {0, 0, 0, 0};  // [slots][sources back to back]
   lmh::DevBuf d_cand, d_ctr, d_tpl_start, d_tpl_cnt, d_tpl_alive, d_out;
   int nsel_stride = 0;
   // pinned host mirrors
