@@ -132,7 +132,7 @@ __device__ __forceinline__ int raw_threshold(int nf, float threshold) {
 constexpr int CW_WARPS = 4;          // warps (templates) per CTA
 constexpr int CW_QCAP = 96;          // queued hits per warp
 #ifndef CW_MINB
-#define CW_MINB 6                    // resident CTAs per SM the register allocation targets (6 -> <= 80 registers; measured best)
+#define CW_MINB 7                    // resident CTAs per SM the register allocation targets (7 -> <= 72 registers; measured best of 5..8)
 #endif
 
 // zero the nibbles at index >= nv (nv < 32) of 32 nibbles held in 4 little-endian words
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
         for (int k0 = 0; k0 < nf; k0 += 32) {
           u32 myoff = (k0 + lane < nf) ? __ldg(offp + k0 + lane) : 0u;
           const int kn = min(32, nf - k0);
-#pragma unroll 4
+#pragma unroll 8
           for (int kk = 0; kk < kn; ++kk) {
             const u32 a = __shfl_sync(0xffffffffu, myoff, kk) + (u32)shift;
             const uint4 c = __ldg(reinterpret_cast<const uint4*>(lmb + (a & ~15u)) + hh);
@@ -552,11 +552,15 @@ void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaS
 // ---------------------------------------------------------------------------------------------
 // Ordered compaction: surviving candidates of frame f in (selection order, raster order).
 // ---------------------------------------------------------------------------------------------
-// The per-template alive counts are maintained by the coarse/local kernels, so the order-defining
-// prefix sum needs no candidate reads; only templates that still own matches copy anything.
+// The per-template alive counts are maintained by the coarse/local kernels, so the order-defining prefix
+// sum needs no candidate reads.  Phase 1 scans the alive counts (1024 templates per round) and lists the
+// templates that still own matches with their output base; phase 2 copies those blocks warp-parallel
+// (ballot ranks keep the raster order), so no thread ever walks a candidate block serially.
+constexpr int PK_LIST = 2048;
 __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __restrict__ out, int out_cap) {
   __shared__ int wsum[32];
-  __shared__ int s_run;
+  __shared__ int s_run, s_n;
+  __shared__ int s_tpl[PK_LIST], s_base[PK_LIST];
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (mp.ctr[frame].overflow) return;  // host will grow the store and redo this frame
   const Cand* cands = mp.cand + (size_t)frame * mp.cand_cap;
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __rest
   const int* ts = mp.tpl_start + (size_t)frame * mp.nsel_stride;
   const int* tc = mp.tpl_cnt + (size_t)frame * mp.nsel_stride;
   const int* ta = mp.tpl_alive + (size_t)frame * mp.nsel_stride;
-  if (tid == 0) s_run = 0;
+  if (tid == 0) { s_run = 0; s_n = 0; }
   __syncthreads();
   for (int i0 = 0; i0 < mp.nsel; i0 += 1024) {
     const int i = i0 + tid;
@@ -589,14 +593,19 @@ __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __rest
     __syncthreads();
     const int run = s_run;
     if (alive > 0) {
-      int pos = run + wsum[wid] + incl - alive;
-      const int st = ts[i], cn = tc[i];
-      for (int j = 0; j < cn; ++j) {
-        Cand cd = cands[st + j];
-        if (cd.sim >= 0.f) {
-          cd.tsel = mp.sel[cd.tsel];  // selection index -> global template index (rank-independent)
-          if (pos < out_cap) o[pos] = cd;
-          ++pos;
+      const int base = run + wsum[wid] + incl - alive;
+      const int slot = atomicAdd(&s_n, 1);
+      if (slot < PK_LIST) { s_tpl[slot] = i; s_base[slot] = base; }
+      else {  // list full (thousands of matching templates): this thread copies its block itself
+        int pos = base;
+        const int st = ts[i], cn = tc[i];
+        for (int j = 0; j < cn; ++j) {
+          Cand cd = cands[st + j];
+          if (cd.sim >= 0.f) {
+            cd.tsel = mp.sel[cd.tsel];
+            if (pos < out_cap) o[pos] = cd;
+            ++pos;
+          }
         }
       }
     }
@@ -605,6 +614,27 @@ __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __rest
     __syncthreads();
   }
   if (tid == 0) mp.ctr[frame].out_count = s_run;
+  const int nlist = min(s_n, PK_LIST);
+  const u32 lt = (1u << lane) - 1u;
+  for (int e = wid; e < nlist; e += 32) {
+    const int i = s_tpl[e], st = ts[i], cn = tc[i];
+    int pos = s_base[e];
+    for (int j0 = 0; j0 < cn; j0 += 32) {
+      Cand cd;
+      bool keep = false;
+      if (j0 + lane < cn) {
+        cd = cands[st + j0 + lane];
+        keep = cd.sim >= 0.f;
+      }
+      const u32 bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int p = pos + __popc(bal & lt);
+        cd.tsel = mp.sel[cd.tsel];  // selection index -> global template index (rank-independent)
+        if (p < out_cap) o[p] = cd;
+      }
+      pos += __popc(bal);
+    }
+  }
 }
 
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st) {

@@ -2,8 +2,8 @@
 # quick regression + perf loop: parity subset, then bench
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -15
-timeout 300 python bench.py --steps 10 --warmup 3 --template-cache cache/tpl_cfg2.yml.gz --no-cpu 2>&1 | tail -1 > gpurun_out/bench_quick.log
+timeout 420 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 120 2>&1 | tail -15
+timeout 150 python bench.py --steps 10 --warmup 3 --template-cache cache/tpl_cfg2.yml.gz --no-cpu 2>&1 | tail -1 > gpurun_out/bench_quick.log
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_quick.log').read())
