@@ -427,7 +427,9 @@ void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_str
 }
 
 // ---------------------------------------------------------------------------------------------
-// Local refinement: one warp per candidate; lane = (row 0..15, half 0..1) owns 8 of the 16x16 sums.
+// Local refinement: one CTA (4 warps) per candidate, the template's features are split across the warps and the
+// four partial 16x16 maps are added through shared memory (a 4x shorter dependent-load chain per candidate:
+// small batches are latency-bound); lane = (row 0..15, half 0..1) owns 8 of the 16x16 sums.
 // Fast path (hdr.flags bit0): offsets are the plan offsets shifted by the candidate's patch origin.
 // Slow path: upstream's per-feature bounds checks with guarded byte loads (malformed / oversized
 // templates — N4 in SURVEY.md — where upstream itself is undefined; semantics = oracle's).
@@ -449,11 +451,12 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
     s_lm[2] = lp.lm[2] + (size_t)frame * lp.lm_stride[2];
     s_lm[3] = lp.lm[3] + (size_t)frame * lp.lm_stride[3];
   }
+  __shared__ uint4 s_part[4][32];
   __syncthreads();
 
-  for (int c = blockIdx.x * 4 + warp; c < n; c += gridDim.x * 4) {
+  for (int c = blockIdx.x; c < n; c += gridDim.x) {
     Cand rec = cands[c];
-    if (rec.sim < 0.f || rec.tsel < 0 || rec.tsel >= mp.nsel) continue;
+    if (rec.sim < 0.f || rec.tsel < 0 || rec.tsel >= mp.nsel) continue;  // CTA-uniform
     const int g = mp.sel[rec.tsel];
     const HdrR hdr = load_hdr(lp.hdr + g);
     int x = rec.x * 2 + 1, y = rec.y * 2 + 1;
@@ -475,10 +478,11 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
         // = 16 L1 wavefronts per feature, half of what two loads per lane cost.
         const int shift = (cyT + rr) * W + cxT;
         const u32* offp = lp.offs + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
-        for (int k0 = 0; k0 < nf; k0 += 32) {
-          u32 myoff = (k0 + lane < nf) ? __ldg(offp + k0 + lane) : 0u;
-          const int kn = min(32, nf - k0);
-#pragma unroll 8
+        const int q = (nf + 3) >> 2, kb = warp * q, ke = min(nf, kb + q);  // this warp's quarter of the features (<= 16)
+        {
+          u32 myoff = (kb + lane < ke) ? __ldg(offp + kb + lane) : 0u;
+          const int kn = ke - kb;
+#pragma unroll 4
           for (int kk = 0; kk < kn; ++kk) {
             const u32 a = __shfl_sync(0xffffffffu, myoff, kk) + (u32)shift;
             const uint4 c = __ldg(reinterpret_cast<const uint4*>(lmb + (a & ~15u)) + hh);
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
             a1 += __funnelshift_r(v1, v2, sh);
           }
         }
-      } else {
+      } else if (warp == 0) {
         const u32* fp = lp.feat + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
         for (int k = 0; k < nf; ++k) {
           u32 f = __ldg(fp + k);
@@ -516,6 +520,11 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       t0 += a0 & 0x00FF00FFu; t1 += (a0 >> 8) & 0x00FF00FFu;
       t2 += a1 & 0x00FF00FFu; t3 += (a1 >> 8) & 0x00FF00FFu;
     }
+    s_part[warp][lane] = make_uint4(t0, t1, t2, t3);
+    __syncthreads();
+    if (warp == 0) {
+      const uint4 p1 = s_part[1][lane], p2 = s_part[2][lane], p3 = s_part[3][lane];
+      t0 += p1.x + p2.x + p3.x; t1 += p1.y + p2.y + p3.y; t2 += p1.z + p2.z + p3.z; t3 += p1.w + p2.w + p3.w;
     // argmax, strict '>' in raster order from best = 0
     int v[8] = {(int)(t0 & 0xFFFF), (int)(t1 & 0xFFFF), (int)(t0 >> 16), (int)(t1 >> 16),
                 (int)(t2 & 0xFFFF), (int)(t3 & 0xFFFF), (int)(t2 >> 16), (int)(t3 >> 16)};
@@ -537,14 +546,16 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       if (rec.sim < 0.f) atomicSub(&mp.tpl_alive[(size_t)frame * mp.nsel_stride + rec.tsel], 1);
       atomicAdd(&mp.ctr[frame].local_bytes, (unsigned long long)nfl * 256ull);
     }
+    }
+    __syncthreads();  // s_part is reused by the next candidate
   }
 }
 
 void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaStream_t st) {
   if (mp.nsel <= 0 || mp.frames <= 0) return;
   // persistent grid: the candidate count lives on the device, warps stride over it
-  int bx = 148 * 4;
-  if (mp.frames >= 8) bx = 148;
+  int bx = 148 * 8;
+  if (mp.frames >= 8) bx = 148 * 2;
   dim3 grid(bx, mp.frames);
   similarity_local_kernel<<<grid, 128, 0, st>>>(mp, lp);
 }
