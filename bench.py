@@ -285,7 +285,7 @@ def main():
     e2e = None
     if not args.no_e2e and not allg:
         prep = det.prepareBatch(frames, cap=2048 * B)   # marshal once: the timed call is one lmb200_match_batch per step
-        for _ in range(2):
+        for _ in range(3):
             det.matchPrepared(prep, args.threshold)
         barrier()
         t0 = time.perf_counter()
@@ -299,7 +299,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": B * K * world / dt, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES,
-               "d2h_bytes_per_step": B * (16 + 1024 * 16), "ms_per_step": 1e3 * dt / K}
+               "d2h_bytes_per_step": B * (24 + 1024 * 16), "ms_per_step": 1e3 * dt / K}
 
     # ---- single-frame latency of the reference-facing call (configs[1] literally: one frame, host buffers in, matches out)
     single = None

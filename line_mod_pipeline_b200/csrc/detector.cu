@@ -444,6 +444,7 @@ static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t
       ProfScope ps(h, LMB200_K_LINEARIZE, st);
       launch_spread_linearize(q, lb.q_stride, mask, lb.q_stride, lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride,
                               lb.lm_stride, lb.g, h->d_table.as<uint2>(), count, st);
+      if (l == L - 1) h->prof.launches[LMB200_K_LINEARIZE]++;  // the nibble packer is a launch of its own
       if (l == L - 1)
         launch_pack_nibbles(lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride, lb.lm_stride,
                             lb.lmn[m].as<u8>() + (size_t)first * lb.lmn_stride, lb.lmn_stride, lb.g, count, st);

@@ -4,7 +4,7 @@ import numpy as np
 import line_mod_pipeline_b200 as lm
 from line_mod_pipeline_b200 import synth
 B = 96
-det0 = lm.Detector.readCache("cache/tpl_cfg2.lmb200") if os.path.exists("cache/tpl_cfg2.lmb200") else lm.Detector.read("cache/tpl_cfg2.yml.gz")
+det0 = lm.Detector.read("cache/tpl_cfg2.yml.gz")
 det = lm.getDefaultLINEMOD(max_batch=B)
 for cid in det0.classIds():
     for t in range(det0.numTemplates(cid)):
@@ -20,12 +20,14 @@ for i in range(B):
     hb[:] = bgr; hd[:] = depth; frames.append([hb, hd])
 prep = det.prepareBatch(frames, cap=2048*B)
 for _ in range(3): det.matchPrepared(prep, 80.0)
-for nx in (1, 2, 3, 4):
-    for G in (3, 4, 6):
-        for ch in (8, 12, 16):
-            if ch > B // G: continue
-            os.environ["LMB200_XSTREAMS"] = str(nx); os.environ["LMB200_GROUPS"] = str(G); os.environ["LMB200_CHUNK"] = str(ch)
-            det.matchPrepared(prep, 80.0)
-            t0 = time.perf_counter()
-            for _ in range(5): det.matchPrepared(prep, 80.0)
-            print("xstreams", nx, "groups", G, "chunk", ch, "ms/step %.3f" % ((time.perf_counter()-t0)/5*1e3), flush=True)
+def run(tag):
+    det.matchPrepared(prep, 80.0)
+    ts = []
+    for _ in range(8):
+        t0 = time.perf_counter(); det.matchPrepared(prep, 80.0); ts.append((time.perf_counter()-t0)*1e3)
+    ts.sort(); print(tag, "ms/step median %.3f min %.3f max %.3f" % (ts[len(ts)//2], ts[0], ts[-1]), flush=True)
+run("default")
+for nx in (3, 4):
+    for G, ch in ((6, 12), (6, 16), (4, 24), (4, 16), (3, 32), (8, 12), (8, 8)):
+        os.environ["LMB200_XSTREAMS"] = str(nx); os.environ["LMB200_GROUPS"] = str(G); os.environ["LMB200_CHUNK"] = str(ch)
+        run("xstreams %d groups %d chunk %d" % (nx, G, ch))
