@@ -169,6 +169,13 @@ int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames
                        const char* const* class_ids, int n_class_ids,
                        lmb200_match_rec* out, size_t cap, size_t* offsets);
 
+/* The same, split in two so consecutive batches pipeline into each other: submit enqueues every copy and kernel of
+ * the batch without blocking and returns a ticket (at most two in flight); collect waits for it and delivers the
+ * match lists.  `frames` (the descriptor array and the pixels) must stay valid until the ticket is collected. */
+int lmb200_match_batch_submit(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
+                              const char* const* class_ids, int n_class_ids, int* ticket);
+int lmb200_match_batch_collect(lmb200_handle h, int ticket, lmb200_match_rec* out, size_t cap, size_t* offsets);
+
 /* Device-resident variant used to time the path without PCIe: upload once, match many times.
  * lmb200_match_resident enqueues the whole device pipeline for frames [first, first+count) and
  * returns without synchronising; lmb200_fetch_resident synchronises, copies the packed match lists

@@ -83,6 +83,8 @@ SIGNATURES = {
                                _P(C.c_size_t), _P(Image), _P(Image)]),
     "lmb200_match_batch": (C.c_int, [_H, _P(Image), C.c_int, C.c_int, C.c_float, _P(C.c_char_p), C.c_int,
                                      _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
+    "lmb200_match_batch_submit": (C.c_int, [_H, _P(Image), C.c_int, C.c_int, C.c_float, _P(C.c_char_p), C.c_int, _P(C.c_int)]),
+    "lmb200_match_batch_collect": (C.c_int, [_H, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_upload_frames": (C.c_int, [_H, _P(Image), C.c_int, C.c_int, C.c_int]),
     "lmb200_match_resident": (C.c_int, [_H, C.c_int, C.c_int, C.c_float, _P(C.c_char_p), C.c_int]),
     "lmb200_fetch_resident": (C.c_int, [_H, C.c_int, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),

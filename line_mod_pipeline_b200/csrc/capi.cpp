@@ -110,9 +110,12 @@ void lmb200_destroy(lmb200_handle h) {
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_gather) cudaFreeHost(h->h_gather);
-    if (h->b_count) cudaFreeHost(h->b_count);
-    if (h->b_out) cudaFreeHost(h->b_out);
-    for (auto e : h->b_events) cudaEventDestroy(e);
+    for (auto& tk : h->tickets) {
+      if (tk.b_ctr) cudaFreeHost(tk.b_ctr);
+      if (tk.b_out) cudaFreeHost(tk.b_out);
+      for (auto e : tk.events) cudaEventDestroy(e);
+    }
+    for (auto e : h->group_done) cudaEventDestroy(e);
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < LMB200_LANES; ++i) {

@@ -523,6 +523,7 @@ static int grow_capacity(lmb200_detector* h) {
   CU(cudaDeviceSynchronize());
   if (h->cand_cap > (1 << 24)) return set_error(h, LMB200_E_CUDA, "candidate buffer overflow persists after growing");
   h->cand_cap *= 4; h->out_cap = h->cand_cap;
+  h->buffer_generation++;  // batches in flight were computed into the old stores: their tickets rerun at collect
   return alloc_match_buffers(h);
 }
 
@@ -594,6 +595,12 @@ static int emit(lmb200_detector* h, const std::vector<Match>& m, lmb200_match_re
   return w < n ? LMB200_E_TRUNCATED : LMB200_OK;
 }
 
+// The slot-addressed entry points (match, upload/match_resident) share slots with batches in flight.
+static void drain_tickets(lmb200_detector* h) {
+  if (!h->device_ready || !(h->tickets[0].active || h->tickets[1].active)) return;
+  for (int i = 0; i < LMB200_LANES; ++i) cudaStreamSynchronize(h->lanes[i].stream);
+}
+
 static int prepare(lmb200_detector* h, const lmb200_image* frames, int n_frames, int n_sources,
                    const char* const* class_ids, int n_class_ids) {
   if (!h || !frames || n_frames <= 0) return set_error(h, LMB200_E_INVALID, "bad arguments");
@@ -615,6 +622,7 @@ static int prepare(lmb200_detector* h, const lmb200_image* frames, int n_frames,
 extern "C" {
 
 int lmb200_upload_frames(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, int first_slot) {
+  if (h) drain_tickets(h);
   int rc = prepare(h, frames, n_frames, n_sources, nullptr, 0);
   if (rc) return rc;
   if (first_slot < 0 || first_slot + n_frames > h->slots) return set_error(h, LMB200_E_INVALID, "slot range exceeds max_batch");
@@ -633,6 +641,7 @@ int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float thre
   if (!h || !h->device_ready || h->rows == 0) return set_error(h, LMB200_E_INVALID, "no frames uploaded");
   if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
   cudaSetDevice(h->device);
+  drain_tickets(h);
   int rc = ensure_plan(h, h->rows, h->cols);
   if (rc) return rc;
   rc = ensure_selection(h, class_ids, n_class_ids);
@@ -726,6 +735,7 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
                  const char* const* class_ids, int n_class_ids, lmb200_match_rec* out, size_t cap, size_t* n_out,
                  lmb200_image* quantized_out, const lmb200_image* masks) {
   if (n_out) *n_out = 0;
+  if (h) drain_tickets(h);
   int rc = prepare(h, sources, 1, n_sources, class_ids, n_class_ids);
   if (rc) return rc;
   cudaStream_t st = h->lanes[0].stream;
@@ -780,129 +790,205 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
   return rc;
 }
 
-// Streaming batch.  Stream C (copy) brings chunks of frames into one of G slot groups, stream X
-// (compute) runs the whole path on them and copies counts + list heads into per-frame pinned staging;
-// the two are chained by events only, so the host enqueues the ENTIRE batch without blocking and then
-// finalises chunk after chunk (sort/unique) while later chunks are still copying/computing.
-//   C:  [wait done(k-G)] H2D(k) rec h2d(k)          X:  [wait h2d(k)] kernels(k) D2H(k) rec done(k)
-int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
-                       const char* const* class_ids, int n_class_ids, lmb200_match_rec* out, size_t cap, size_t* offsets) {
-  int rc = prepare(h, frames, n_frames, n_sources, class_ids, n_class_ids);
-  if (rc) return rc;
-  h->masks_in_use = false;
+// Streaming batch.  Stream C (copy) brings chunks of frames into one of G slot groups, the compute
+// streams run the whole path on them (round-robin) and copy counters + list heads into per-frame pinned
+// staging; copy and compute are chained by events only, so the host enqueues the ENTIRE batch without
+// blocking (submit) and later finalises chunk after chunk (collect: sort/unique) while later chunks — or the
+// next batch — are still copying/computing.  Slot groups are recycled through one rolling "done" event per
+// group, so consecutive batches pipeline into each other.
+//   C:  [wait group_done(g)] H2D(k) rec h2d(k)          X:  [wait h2d(k)] kernels(k) D2H(k) rec group_done(g), done(k)
+static int batch_enqueue(lmb200_detector* h, BatchTicket& tk) {
+  const int n_frames = tk.n_frames, n_sources = tk.n_sources;
+  const lmb200_image* frames = tk.frames.data();
   cudaStream_t Xs[4] = {h->lanes[0].stream, h->lanes[2].stream, h->lanes[3].stream, h->lanes[4].stream}, Cs = h->lanes[1].stream;
   int nx = 3;  // compute streams used round-robin by consecutive chunks (measured: 1 -> 5.4 ms, 2 -> 4.33, 3 -> 4.25 per 96 frames)
   if (const char* e = std::getenv("LMB200_XSTREAMS")) nx = std::max(1, std::min(4, std::atoi(e)));
-  for (;;) {
-    int G = std::max(1, std::min(6, h->slots / 12));  // slot groups of >= 12 frames
-    if (h->slots >= 2 && G < 2) G = 2;
-    if (const char* e = std::getenv("LMB200_GROUPS")) G = std::max(1, std::min(h->slots, std::atoi(e)));
-    const int gs = h->slots / G;
-    int chunk = std::min(gs, 12);
-    if (const char* e = std::getenv("LMB200_CHUNK")) chunk = std::max(1, std::min(gs, std::atoi(e)));
-    // chunk schedule: ramp up (chunk/3, 2*chunk/3, chunk, chunk, ...) so compute starts after a short first copy
-    std::vector<int> cf0, ccnt;
-    for (int f = 0, k = 0; f < n_frames; ++k) {
-      int want = k == 0 ? std::max(1, chunk / 3) : (k == 1 ? std::max(1, 2 * chunk / 3) : chunk);
-      int cnt = std::min(want, n_frames - f);
-      cf0.push_back(f); ccnt.push_back(cnt);
-      f += cnt;
-    }
-    const int nchunks = (int)cf0.size();
-    // per-frame pinned staging for the results of this batch
-    if (h->b_frames < n_frames || h->b_head != h->h_head) {
-      if (h->b_count) cudaFreeHost(h->b_count);
-      if (h->b_out) cudaFreeHost(h->b_out);
-      h->b_count = nullptr; h->b_out = nullptr;
-      CU(cudaHostAlloc((void**)&h->b_count, (size_t)n_frames * sizeof(SlotCtr), cudaHostAllocDefault));
-      CU(cudaHostAlloc((void**)&h->b_out, (size_t)n_frames * h->h_head * sizeof(Cand), cudaHostAllocDefault));
-      h->b_frames = n_frames; h->b_head = h->h_head;
-    }
-    SlotCtr* b_ctr = (SlotCtr*)h->b_count;
-    while ((int)h->b_events.size() < 2 * nchunks) {
-      cudaEvent_t ev;
-      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      h->b_events.push_back(ev);
-    }
-    const bool trace = std::getenv("LMB200_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;  // trace: 4 timing events per chunk (copy start/end, compute start/end)
-    if (trace) { tev.resize(4 * (size_t)nchunks); for (auto& e : tev) cudaEventCreate(&e); }
-    for (int k = 0; k < nchunks; ++k) {
-      const int f0 = cf0[k], cnt = ccnt[k], slot0 = (k % G) * gs;
-      cudaEvent_t ev_h2d = h->b_events[2 * k], ev_done = h->b_events[2 * k + 1];
-      cudaStream_t X = Xs[k % nx];  // adjacent chunks overlap on separate compute streams (fills the low-parallelism tails)
-      if (k >= G) CU(cudaStreamWaitEvent(Cs, h->b_events[2 * (k - G) + 1], 0));  // slot group free again
-      if (trace) cudaEventRecord(tev[4 * k], Cs);
-      if (chunk_is_contiguous(h, frames + (size_t)f0 * n_sources, cnt, n_sources)) {
-        CU(cudaMemcpyAsync((u8*)h->d_frames.p + (size_t)slot0 * h->frame_bytes, frames[(size_t)f0 * n_sources].data,
-                           h->frame_bytes * cnt, cudaMemcpyHostToDevice, Cs));   // one DMA for the whole chunk
-      } else {
-        for (int i = 0; i < cnt; ++i) {
-          rc = upload_one(h, frames + (size_t)(f0 + i) * n_sources, slot0 + i, Cs);
-          if (rc) return rc;
-        }
-      }
-      h->prof.launches[LMB200_K_UPLOAD]++;
-      CU(cudaEventRecord(ev_h2d, Cs));
-      if (trace) cudaEventRecord(tev[4 * k + 1], Cs);
-      CU(cudaStreamWaitEvent(X, ev_h2d, 0));
-      if (trace) cudaEventRecord(tev[4 * k + 2], X);
-      rc = run_frame_side(h, slot0, cnt, X);
-      if (rc) return rc;
-      rc = run_matching(h, slot0, cnt, threshold, X);
-      if (rc) return rc;
-      CU(cudaMemcpyAsync(b_ctr + f0, h->d_ctr.as<SlotCtr>() + slot0, sizeof(SlotCtr) * cnt, cudaMemcpyDeviceToHost, X));
-      CU(cudaMemcpy2DAsync(h->b_out + (size_t)f0 * h->h_head, (size_t)h->h_head * sizeof(Cand),
-                           h->d_out.as<Cand>() + (size_t)slot0 * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
-                           (size_t)h->h_head * sizeof(Cand), cnt, cudaMemcpyDeviceToHost, X));
-      CU(cudaEventRecord(ev_done, X));
-      if (trace) cudaEventRecord(tev[4 * k + 3], X);
-    }
-    if (trace) {
-      cudaDeviceSynchronize();
-      for (int k = 0; k < nchunks; ++k) {
-        float t[4];
-        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[4 * k + j]);
-        std::fprintf(stderr, "[lmb200 trace] chunk %2d: h2d %.3f..%.3f  compute %.3f..%.3f ms\n", k, t[0], t[1], t[2], t[3]);
-      }
-      for (auto& e : tev) cudaEventDestroy(e);
-    }
-    // finalise in frame order while the GPU works on later chunks
-    size_t base = 0;
-    int status = LMB200_OK;
-    bool redo = false;
-    std::vector<Cand> raw;
-    std::vector<Match> m;
-    for (int k = 0; k < nchunks && !redo; ++k) {
-      const int f0 = cf0[k], cnt = ccnt[k];
-      CU(cudaEventSynchronize(h->b_events[2 * k + 1]));
-      for (int i = 0; i < cnt; ++i) {
-        const int f = f0 + i, n = b_ctr[f].out_count;
-        if (b_ctr[f].overflow || n > h->out_cap || n > h->h_head) { redo = true; break; }
-        raw.assign(h->b_out + (size_t)f * h->h_head, h->b_out + (size_t)f * h->h_head + n);
-        h->prof.bytes_local += (long long)b_ctr[f].local_bytes;
-        to_matches(h, raw, m);
-        h->prof.candidates += (long long)raw.size();
-        finalize_matches(m);
-        h->prof.matches += (long long)m.size();
-        size_t w = 0;
-        if (offsets) offsets[f] = base;
-        if (emit(h, m, out, cap, base, &w) != LMB200_OK) status = LMB200_E_TRUNCATED;
-        base += w;
-      }
-    }
-    if (redo) {  // a candidate store or the staged list head was too small: grow and rerun the batch
-      CU(cudaDeviceSynchronize());
-      bool store = false;
-      for (int f = 0; f < n_frames; ++f) store |= b_ctr[f].overflow != 0 || b_ctr[f].out_count > h->out_cap;
-      if (store) { rc = grow_capacity(h); if (rc) return rc; }
-      else h->h_head = std::min(h->out_cap, h->h_head * 4);
-      continue;
-    }
-    if (h->profiling) { for (int i = 0; i < 4; ++i) CU(cudaStreamSynchronize(Xs[i])); collect_profile(h); }
-    if (offsets) offsets[n_frames] = base;
-    return status;
+  int G = std::max(1, std::min(6, h->slots / 12));  // slot groups of >= 12 frames
+  if (h->slots >= 2 && G < 2) G = 2;
+  if (const char* e = std::getenv("LMB200_GROUPS")) G = std::max(1, std::min(h->slots, std::atoi(e)));
+  const int gs = h->slots / G;
+  int chunk = std::min(gs, 12);
+  if (const char* e = std::getenv("LMB200_CHUNK")) chunk = std::max(1, std::min(gs, std::atoi(e)));
+  if (G != h->b_groups) {  // (re)create the rolling per-group events
+    CU(cudaDeviceSynchronize());
+    for (auto e : h->group_done) cudaEventDestroy(e);
+    h->group_done.assign(G, nullptr);
+    for (auto& e : h->group_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->group_used.assign(G, 0);
+    h->b_groups = G;
   }
+  // chunk schedule: ramp up (chunk/3, 2*chunk/3, chunk, chunk, ...) so compute starts after a short first copy
+  tk.cf0.clear(); tk.ccnt.clear();
+  for (int f = 0, k = 0; f < n_frames; ++k) {
+    int want = k == 0 ? std::max(1, chunk / 3) : (k == 1 ? std::max(1, 2 * chunk / 3) : chunk);
+    int cnt = std::min(want, n_frames - f);
+    tk.cf0.push_back(f); tk.ccnt.push_back(cnt);
+    f += cnt;
+  }
+  const int nchunks = (int)tk.cf0.size();
+  // per-frame pinned staging for the results of this batch
+  if (tk.cap_frames < n_frames || tk.head != h->h_head) {
+    if (tk.b_ctr) cudaFreeHost(tk.b_ctr);
+    if (tk.b_out) cudaFreeHost(tk.b_out);
+    tk.b_ctr = nullptr; tk.b_out = nullptr;
+    CU(cudaHostAlloc((void**)&tk.b_ctr, (size_t)n_frames * sizeof(SlotCtr), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&tk.b_out, (size_t)n_frames * h->h_head * sizeof(Cand), cudaHostAllocDefault));
+    tk.cap_frames = n_frames; tk.head = h->h_head;
+  }
+  while ((int)tk.events.size() < 2 * nchunks) {
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    tk.events.push_back(ev);
+  }
+  const bool trace = std::getenv("LMB200_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;  // trace: 4 timing events per chunk (copy start/end, compute start/end)
+  if (trace) { tev.resize(4 * (size_t)nchunks); for (auto& e : tev) cudaEventCreate(&e); }
+  for (int k = 0; k < nchunks; ++k) {
+    const int f0 = tk.cf0[k], cnt = tk.ccnt[k];
+    const long long seq = h->chunk_seq++;
+    const int g = (int)(seq % G), slot0 = g * gs;
+    cudaEvent_t ev_h2d = tk.events[2 * k], ev_done = tk.events[2 * k + 1];
+    cudaStream_t X = Xs[seq % nx];  // adjacent chunks overlap on separate compute streams (fills the low-parallelism tails)
+    if (h->group_used[g]) CU(cudaStreamWaitEvent(Cs, h->group_done[g], 0));  // slot group free again
+    if (trace) cudaEventRecord(tev[4 * k], Cs);
+    if (chunk_is_contiguous(h, frames + (size_t)f0 * n_sources, cnt, n_sources)) {
+      CU(cudaMemcpyAsync((u8*)h->d_frames.p + (size_t)slot0 * h->frame_bytes, frames[(size_t)f0 * n_sources].data,
+                         h->frame_bytes * cnt, cudaMemcpyHostToDevice, Cs));   // one DMA for the whole chunk
+    } else {
+      for (int i = 0; i < cnt; ++i) {
+        int rc = upload_one(h, frames + (size_t)(f0 + i) * n_sources, slot0 + i, Cs);
+        if (rc) return rc;
+      }
+    }
+    h->prof.launches[LMB200_K_UPLOAD]++;
+    CU(cudaEventRecord(ev_h2d, Cs));
+    if (trace) cudaEventRecord(tev[4 * k + 1], Cs);
+    CU(cudaStreamWaitEvent(X, ev_h2d, 0));
+    if (trace) cudaEventRecord(tev[4 * k + 2], X);
+    int rc = run_frame_side(h, slot0, cnt, X);
+    if (rc) return rc;
+    rc = run_matching(h, slot0, cnt, tk.threshold, X);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(tk.b_ctr + f0, h->d_ctr.as<SlotCtr>() + slot0, sizeof(SlotCtr) * cnt, cudaMemcpyDeviceToHost, X));
+    CU(cudaMemcpy2DAsync(tk.b_out + (size_t)f0 * h->h_head, (size_t)h->h_head * sizeof(Cand),
+                         h->d_out.as<Cand>() + (size_t)slot0 * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
+                         (size_t)h->h_head * sizeof(Cand), cnt, cudaMemcpyDeviceToHost, X));
+    CU(cudaEventRecord(ev_done, X));
+    CU(cudaEventRecord(h->group_done[g], X));
+    h->group_used[g] = 1;
+    if (trace) cudaEventRecord(tev[4 * k + 3], X);
+  }
+  if (trace) {
+    cudaDeviceSynchronize();
+    for (int k = 0; k < nchunks; ++k) {
+      float t[4];
+      for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[4 * k + j]);
+      std::fprintf(stderr, "[lmb200 trace] chunk %2d: h2d %.3f..%.3f  compute %.3f..%.3f ms\n", k, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
+  tk.head_used = h->h_head;
+  tk.generation = h->buffer_generation;
+  return LMB200_OK;
+}
+
+// Finalise a submitted batch in frame order.  Returns +1 when a device-side store (or the staged list head) was
+// too small, or when the stores were reallocated under the ticket: the caller grows and re-runs the batch.
+static int batch_finalize(lmb200_detector* h, BatchTicket& tk, lmb200_match_rec* out, size_t cap, size_t* offsets, int* status) {
+  const int nchunks = (int)tk.cf0.size();
+  if (tk.generation != h->buffer_generation) return 1;
+  size_t base = 0;
+  std::vector<Cand> raw;
+  std::vector<Match> m;
+  *status = LMB200_OK;
+  for (int k = 0; k < nchunks; ++k) {
+    const int f0 = tk.cf0[k], cnt = tk.ccnt[k];
+    CU(cudaEventSynchronize(tk.events[2 * k + 1]));
+    for (int i = 0; i < cnt; ++i) {
+      const int f = f0 + i, n = tk.b_ctr[f].out_count;
+      if (tk.b_ctr[f].overflow || n > h->out_cap || n > tk.head_used) return 1;
+      raw.assign(tk.b_out + (size_t)f * tk.head_used, tk.b_out + (size_t)f * tk.head_used + n);
+      h->prof.bytes_local += (long long)tk.b_ctr[f].local_bytes;
+      to_matches(h, raw, m);
+      h->prof.candidates += (long long)raw.size();
+      finalize_matches(m);
+      h->prof.matches += (long long)m.size();
+      size_t w = 0;
+      if (offsets) offsets[f] = base;
+      if (emit(h, m, out, cap, base, &w) != LMB200_OK) *status = LMB200_E_TRUNCATED;
+      base += w;
+    }
+  }
+  if (offsets) offsets[tk.n_frames] = base;
+  return LMB200_OK;
+}
+
+int lmb200_match_batch_submit(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
+                              const char* const* class_ids, int n_class_ids, int* ticket) {
+  if (!h || !ticket) return LMB200_E_INVALID;
+  int t = -1;
+  for (int i = 0; i < 2; ++i)
+    if (!h->tickets[i].active) { t = i; break; }
+  if (t < 0) return set_error(h, LMB200_E_INVALID, "two batches are already in flight: collect one first");
+  // a different class selection than the batch in flight would overwrite the shared selection list under it
+  std::string key;
+  for (int i = 0; i < n_class_ids; ++i) { key += class_ids[i]; key.push_back('\x1f'); }
+  BatchTicket& other = h->tickets[t ^ 1];
+  if (other.active && (other.sel_key != key) && h->device_ready) {
+    cudaSetDevice(h->device);
+    for (int i = 0; i < LMB200_LANES; ++i) cudaStreamSynchronize(h->lanes[i].stream);
+  }
+  int rc = prepare(h, frames, n_frames, n_sources, class_ids, n_class_ids);
+  if (rc) return rc;
+  h->masks_in_use = false;
+  BatchTicket& tk = h->tickets[t];
+  tk.frames.assign(frames, frames + (size_t)n_frames * n_sources);
+  tk.n_frames = n_frames; tk.n_sources = n_sources; tk.threshold = threshold; tk.sel_key = key;
+  tk.class_ids.clear();
+  for (int i = 0; i < n_class_ids; ++i) tk.class_ids.push_back(class_ids[i]);
+  rc = batch_enqueue(h, tk);
+  if (rc) return rc;
+  tk.active = true;
+  *ticket = t;
+  return LMB200_OK;
+}
+
+int lmb200_match_batch_collect(lmb200_handle h, int ticket, lmb200_match_rec* out, size_t cap, size_t* offsets) {
+  if (!h || ticket < 0 || ticket > 1 || !h->tickets[ticket].active) return set_error(h, LMB200_E_INVALID, "no such batch in flight");
+  cudaSetDevice(h->device);
+  BatchTicket& tk = h->tickets[ticket];
+  for (;;) {
+    int status = LMB200_OK;
+    int rc = batch_finalize(h, tk, out, cap, offsets, &status);
+    if (rc == LMB200_OK) {
+      if (h->profiling) { for (int i = 0; i < LMB200_LANES; ++i) CU(cudaStreamSynchronize(h->lanes[i].stream)); collect_profile(h); }
+      tk.active = false;
+      return status;
+    }
+    if (rc < 0) { tk.active = false; return rc; }
+    // grow (unless another collect already did) and rerun this batch; the caller's frames must still be alive
+    CU(cudaDeviceSynchronize());
+    if (tk.generation == h->buffer_generation) {
+      bool store = false;
+      for (int f = 0; f < tk.n_frames; ++f) store |= tk.b_ctr[f].overflow != 0 || tk.b_ctr[f].out_count > h->out_cap;
+      if (store) { rc = grow_capacity(h); if (rc) { tk.active = false; return rc; } }
+      else { h->h_head = std::min(h->out_cap, h->h_head * 4); h->buffer_generation++; }
+    }
+    std::vector<const char*> ids;
+    for (auto& s : tk.class_ids) ids.push_back(s.c_str());
+    rc = ensure_selection(h, ids.empty() ? nullptr : ids.data(), (int)ids.size());
+    if (rc) { tk.active = false; return rc; }
+    rc = batch_enqueue(h, tk);
+    if (rc) { tk.active = false; return rc; }
+  }
+}
+
+int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
+                       const char* const* class_ids, int n_class_ids, lmb200_match_rec* out, size_t cap, size_t* offsets) {
+  int ticket = -1;
+  int rc = lmb200_match_batch_submit(h, frames, n_frames, n_sources, threshold, class_ids, n_class_ids, &ticket);
+  if (rc) return rc;
+  return lmb200_match_batch_collect(h, ticket, out, cap, offsets);
 }
 
 int lmb200_host_alloc(size_t bytes, void** out) {

@@ -64,6 +64,21 @@ struct Lane {
 
 struct ProfRec { int family; cudaEvent_t a, b; };
 
+// One submitted lmb200_match_batch: chunk schedule, completion events and per-frame pinned result staging.
+struct BatchTicket {
+  bool active = false;
+  std::vector<lmb200_image> frames;
+  int n_frames = 0, n_sources = 0;
+  float threshold = 0.f;
+  std::string sel_key;
+  std::vector<std::string> class_ids;
+  std::vector<int> cf0, ccnt;
+  std::vector<cudaEvent_t> events;        // per chunk: h2d done, chunk done
+  lmk::SlotCtr* b_ctr = nullptr; lmk::Cand* b_out = nullptr;
+  int cap_frames = 0, head = 0, head_used = 0;
+  long long generation = 0;               // buffer_generation at enqueue time
+};
+
 }  // namespace lmh
 
 struct lmb200_detector {
@@ -114,9 +129,10 @@ struct lmb200_detector {
   lmk::Cand* h_out = nullptr; int h_head = 0;      // first h_head records of every slot
   void* h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for pageable/strided inputs
   std::vector<float> slot_threshold;
-  // per-frame pinned staging of lmb200_match_batch
-  void* b_count = nullptr; lmk::Cand* b_out = nullptr; int b_frames = 0, b_head = 0;
-  std::vector<cudaEvent_t> b_events;
+  // batches in flight (lmb200_match_batch_submit / _collect)
+  lmh::BatchTicket tickets[2];
+  std::vector<cudaEvent_t> group_done; std::vector<char> group_used; int b_groups = 0;
+  long long chunk_seq = 0, buffer_generation = 0;
 
   // profiling
   bool profiling = false;

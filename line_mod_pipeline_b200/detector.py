@@ -279,6 +279,20 @@ class Detector:
             raise LinemodError(rc, "prepared output buffer too small: need %d records" % prep["offs"][prep["n"]])
         return int(prep["offs"][prep["n"]])
 
+    def submitPrepared(self, prep, threshold, class_ids=()):
+        """Non-blocking half of matchPrepared: enqueues the whole batch, returns a ticket (max. two in flight)."""
+        ids, nids = _cstr_array(class_ids)
+        t = C.c_int(-1)
+        self._check(self._L.lmb200_match_batch_submit(self._h, prep["arr"], prep["n"], prep["nsrc"], C.c_float(threshold), ids, nids, C.byref(t)))
+        return t.value
+
+    def collectPrepared(self, prep, ticket):
+        rc = self._check(self._L.lmb200_match_batch_collect(self._h, ticket, prep["out"].ctypes.data_as(C.POINTER(K.MatchRec)),
+                                                            prep["cap"], prep["offs"]), allow=(K.E_TRUNCATED,))
+        if rc == K.E_TRUNCATED:
+            raise LinemodError(rc, "prepared output buffer too small: need %d records" % prep["offs"][prep["n"]])
+        return int(prep["offs"][prep["n"]])
+
     def uploadFrames(self, frames, first_slot=0):
         arr, keep, nsrc = self._frames(frames)
         self._check(self._L.lmb200_upload_frames(self._h, arr, len(frames), nsrc, first_slot))

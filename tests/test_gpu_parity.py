@@ -334,3 +334,52 @@ def test_config1_reference_frame_and_model_templates(fixture_frame):
         ref = ora.match([bgr, depth], thr, class_ids=["lagergehaeuse.ply"], threads=16)
         assert_same_matches(got, ref.matches(0), "config 1 thr=%g" % thr)
     assert len(got) > 1000
+
+
+def test_pipelined_submit_collect(cfg2_small):
+    """Two batches in flight (submit k+1 before collecting k): every frame's list equals the blocking single-frame call."""
+    det, ora, _, _ = cfg2_small
+    fa = [list(synth.make_frame(i)) for i in range(0, 9)]
+    fb = [list(synth.make_frame(i)) for i in range(9, 20)]
+    pa, pb = det.prepareBatch(fa, cap=20000), det.prepareBatch(fb, cap=20000)
+    ta = det.submitPrepared(pa, 65.0)
+    tb = det.submitPrepared(pb, 65.0)
+    with pytest.raises(lm.LinemodError):
+        det.submitPrepared(pa, 65.0)              # at most two in flight
+    def lists(prep):
+        offs = prep["offs"]
+        return [prep["out"][offs[i]:offs[i + 1]].copy().view(np.recarray) for i in range(prep["n"])]
+    det.collectPrepared(pa, ta)
+    ra = lists(pa)
+    tc = det.submitPrepared(pa, 65.0)             # ticket slot is free again; batch c pipelines behind b
+    det.collectPrepared(pb, tb)
+    rb = lists(pb)
+    det.collectPrepared(pa, tc)
+    rc = lists(pa)
+    for i, f in enumerate(fa):
+        want = det.match(f, 65.0)
+        assert_same_matches(ra[i], want, "pipelined batch a frame %d" % i)
+        assert_same_matches(rc[i], want, "pipelined batch c frame %d" % i)
+    for i, f in enumerate(fb):
+        assert_same_matches(rb[i], det.match(f, 65.0), "pipelined batch b frame %d" % i)
+    assert_same_matches(rb[4], ora.match(fb[4], 65.0, threads=8).matches(0), "pipelined vs oracle")
+
+
+def test_pipelined_overflow_regrows_both_tickets():
+    bgr, depth = synth.make_frame(0)
+    det, ora = make_pair(candidate_capacity=64, max_batch=24)
+    add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(0))
+    add_random(det, ora, 100)
+    fa = [list(synth.make_frame(i)) for i in range(3)]
+    fb = [list(synth.make_frame(i)) for i in range(3, 7)]
+    pa, pb = det.prepareBatch(fa, cap=200000), det.prepareBatch(fb, cap=200000)
+    ta = det.submitPrepared(pa, 20.0)
+    tb = det.submitPrepared(pb, 20.0)
+    det.collectPrepared(pa, ta)      # overflows the 64-entry store: grows, reruns a; b was computed into the old store
+    det.collectPrepared(pb, tb)      # ... so b reruns too
+    for prep, fr in ((pa, fa), (pb, fb)):
+        offs = prep["offs"]
+        for i, f in enumerate(fr):
+            got = prep["out"][offs[i]:offs[i + 1]].view(np.recarray)
+            assert len(got) > 64
+            assert_same_matches(got, ora.match(f, 20.0, threads=8).matches(0), "overflow pipelined frame %d" % i)
