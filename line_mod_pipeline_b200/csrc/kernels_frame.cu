@@ -278,31 +278,28 @@ void launch_dn_quantize(const u16* depth, size_t depth_stride, u8* out, size_t o
 // medianBlur(5), replicate border, on bytes that are 0 or one-hot: the sorted order is
 // 0 < 1 < 2 < 4 < ... < 128, so the 13th of 25 falls out of nine 5-bit counters.
 // ---------------------------------------------------------------------------------------------
-// Separable: per column the 5-row window is folded into eight byte-wide label counters (two u32; a
-// one-hot byte's nibble n becomes (n*0x204081)&0x01010101, one counter byte per set bit), then every
-// output adds five neighbouring column counters and walks the cumulative count to the 13th element.
+// Counting median.  Every pixel is expanded ONCE into eight byte-wide one-hot counters (two u32: a one-hot byte's
+// nibble n becomes (n*0x204081)&0x01010101, one counter byte per set bit); a column entry adds five of them
+// vertically, an output adds five column entries.  The 13th of 25 then falls out of packed prefix sums:
+// c*0x01010101 turns four byte counts into their running sums, adding (128-13) to every byte sets bit 7 exactly
+// where the running count (zeros first, then labels 0..7: the sorted order 0 < 1 < 2 < 4 < ... < 128) reaches 13.
 __global__ void __launch_bounds__(256) median5_kernel(const u8* __restrict__ src, size_t src_stride,
                                                       u8* __restrict__ dst, size_t dst_stride, int rows, int cols) {
-  __shared__ u8 tile[8 + 4][32 + 4 + 4];
+  __shared__ uint2 enc[8 + 4][32 + 4];
   __shared__ uint2 colcnt[8][32 + 4];
   const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
   const u8* s = src + (size_t)blockIdx.z * src_stride;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   for (int idx = tid; idx < 12 * 36; idx += 256) {
     int ty = idx / 36, tx = idx - ty * 36;
-    tile[ty][tx] = s[(size_t)clampi(y0 - 2 + ty, 0, rows - 1) * cols + clampi(x0 - 2 + tx, 0, cols - 1)];
+    u32 v = s[(size_t)clampi(y0 - 2 + ty, 0, rows - 1) * cols + clampi(x0 - 2 + tx, 0, cols - 1)];
+    enc[ty][tx] = make_uint2(((v & 15u) * 0x00204081u) & 0x01010101u, ((v >> 4) * 0x00204081u) & 0x01010101u);
   }
   __syncthreads();
   for (int idx = tid; idx < 8 * 36; idx += 256) {
     int ty = idx / 36, tx = idx - ty * 36;
-    u32 lo = 0, hi = 0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      u32 v = tile[ty + i][tx];
-      lo += ((v & 15u) * 0x00204081u) & 0x01010101u;
-      hi += ((v >> 4) * 0x00204081u) & 0x01010101u;
-    }
-    colcnt[ty][tx] = make_uint2(lo, hi);
+    uint2 a = enc[ty][tx], b = enc[ty + 1][tx], c = enc[ty + 2][tx], d = enc[ty + 3][tx], e = enc[ty + 4][tx];
+    colcnt[ty][tx] = make_uint2(a.x + b.x + c.x + d.x + e.x, a.y + b.y + c.y + d.y + e.y);
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -313,19 +310,15 @@ __global__ void __launch_bounds__(256) median5_kernel(const u8* __restrict__ src
     uint2 c = colcnt[threadIdx.y][threadIdx.x + j];
     lo += c.x; hi += c.y;
   }
-  // sorted order 0 < 1 < 2 < ... < 128: zeros first, then labels 0..7
-  u32 s4 = (lo & 0x00FF00FFu) + ((lo >> 8) & 0x00FF00FFu) + (hi & 0x00FF00FFu) + ((hi >> 8) & 0x00FF00FFu);
-  int acc = 25 - (int)((s4 & 0xFFFFu) + (s4 >> 16));
-  u8 res = 0;
-  if (acc < 13) {
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      int c = (int)(((b < 4 ? lo : hi) >> (8 * (b & 3))) & 0xFFu);
-      if (acc < 13 && acc + c >= 13) res = (u8)(1u << b);
-      acc += c;
-    }
-  }
-  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * cols + x] = res;
+  const u32 plo = lo * 0x01010101u;                  // running sums of labels 0..3
+  const u32 tlo = plo >> 24;                         // count of labels 0..3
+  const u32 phi = hi * 0x01010101u;                  // running sums of labels 4..7 (without the low half)
+  const u32 zeros = 25u - tlo - (phi >> 24);
+  const u32 bias = (zeros + 115u) * 0x01010101u;     // + zeros, + (128 - 13)
+  const u32 ge_lo = (plo + bias) & 0x80808080u;
+  const u32 ge_hi = (phi + tlo * 0x01010101u + bias) & 0x80808080u;
+  const int nge = __popc(ge_lo) + __popc(ge_hi);     // labels whose running count has reached 13 (>= 1 when zeros < 13)
+  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * cols + x] = zeros >= 13u ? (u8)0 : (u8)(1u << (8 - nge));
 }
 
 void launch_median5(const u8* src, size_t src_stride, u8* dst, size_t dst_stride, int rows, int cols, int frames,
