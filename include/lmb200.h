@@ -205,8 +205,9 @@ int lmb200_set_normal_lut(lmb200_handle h, const uint8_t* lut8000);
 int lmb200_get_normal_lut(lmb200_handle h, uint8_t* lut8000);
 
 /* ---- multi-GPU (one process per GPU) -------------------------------------------------- */
-/* Template sharding: this handle scores only shard `rank` of `world` contiguous, cost-balanced
- * blocks of the generation-ordered template list.  world=1 restores the full set. */
+/* Template sharding: this handle scores only shard `rank` of `world`.  Shards are interleaved over the
+ * generation-ordered selection list (positions rank, rank+world, ...), which spreads the templates of one object over
+ * all ranks; lmb200_fetch_resident_allgather restores generation order by selection position.  world=1 = full set. */
 int lmb200_set_template_shard(lmb200_handle h, int rank, int world);
 /* NCCL plumbing (libnccl.so.2 is dlopen'ed on first use). unique_id is 128 bytes. */
 int lmb200_comm_unique_id(uint8_t* unique_id128);

@@ -116,6 +116,7 @@ void lmb200_destroy(lmb200_handle h) {
       for (auto e : tk.events) cudaEventDestroy(e);
     }
     for (auto e : h->group_done) cudaEventDestroy(e);
+    for (auto& mk : h->resident_marks) if (mk.ev) cudaEventDestroy(mk.ev);
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < LMB200_LANES; ++i) {

@@ -10,7 +10,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <thread>
 
 using namespace lmk;
 
@@ -104,13 +106,19 @@ struct ProfScope {
 };
 
 static void collect_profile(lmb200_detector* h) {
+  std::vector<ProfRec> keep;
   for (auto& r : h->prof_pending) {
+    if (cudaEventQuery(r.b) != cudaSuccess) {  // still in flight on another stream: resolve at a later collect
+      cudaGetLastError();
+      keep.push_back(r);
+      continue;
+    }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) h->prof.ms[r.family] += ms;
     h->event_pool.push_back(r.a);
     h->event_pool.push_back(r.b);
   }
-  h->prof_pending.clear();
+  h->prof_pending.swap(keep);
 }
 
 // ---------------------------------------------------------------- tables
@@ -337,12 +345,29 @@ static int ensure_selection(lmb200_detector* h, const char* const* class_ids, in
       for (int g = first[c]; g < first[c + 1]; ++g) sel.push_back(g);
     }
   }
+  h->shard_interleaved = false;
   if (h->shard_world > 1) {
-    std::vector<double> costs(sel.size());
-    for (size_t i = 0; i < sel.size(); ++i) costs[i] = h->tpl_cost[sel[i]] + 1.0;
-    std::vector<int> begin(h->shard_world + 1);
-    lmb200_shard_plan(costs.data(), (int)sel.size(), h->shard_world, begin.data());
-    sel = std::vector<int>(sel.begin() + begin[h->shard_rank], sel.begin() + begin[h->shard_rank + 1]);
+    // Interleaved shards (rank r scores selection positions r, r+world, ...): neighbouring templates of a class
+    // (viewpoints/rotations of one object, the ones that fire together) spread over all ranks, which balances
+    // both the coarse gather and the refinement work.  The merge restores generation order by selection position.
+    // With a template listed twice (duplicate class ids) positions are ambiguous: fall back to contiguous
+    // cost-balanced blocks, whose rank-ordered concatenation is generation order by construction.
+    std::vector<int> pos(std::max(1, h->ntpl), -1);
+    bool dup = false;
+    for (size_t i = 0; i < sel.size(); ++i) { if (pos[sel[i]] >= 0) dup = true; else pos[sel[i]] = (int)i; }
+    if (!dup) {
+      std::vector<int> mine;
+      for (size_t i = (size_t)h->shard_rank; i < sel.size(); i += (size_t)h->shard_world) mine.push_back(sel[i]);
+      sel.swap(mine);
+      h->pos_of_g.swap(pos);
+      h->shard_interleaved = true;
+    } else {
+      std::vector<double> costs(sel.size());
+      for (size_t i = 0; i < sel.size(); ++i) costs[i] = h->tpl_cost[sel[i]] + 1.0;
+      std::vector<int> begin(h->shard_world + 1);
+      lmb200_shard_plan(costs.data(), (int)sel.size(), h->shard_world, begin.data());
+      sel = std::vector<int>(sel.begin() + begin[h->shard_rank], sel.begin() + begin[h->shard_rank + 1]);
+    }
   }
   h->h_sel = sel;
   h->sel_bytes_coarse = 0;
@@ -568,8 +593,9 @@ static int fetch_grow(lmb200_detector* h, int first, int count, cudaStream_t st,
     float thr = h->slot_threshold[first];
     rc = grow_capacity(h);
     if (rc) return rc;
-    rc = run_matching(h, first, count, thr, st);
+    rc = run_matching(h, first, count, thr, h->lanes[0].stream);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(h->lanes[0].stream));
   }
 }
 
@@ -599,6 +625,22 @@ static int emit(lmb200_detector* h, const std::vector<Match>& m, lmb200_match_re
 static void drain_tickets(lmb200_detector* h) {
   if (!h->device_ready || !(h->tickets[0].active || h->tickets[1].active)) return;
   for (int i = 0; i < LMB200_LANES; ++i) cudaStreamSynchronize(h->lanes[i].stream);
+}
+
+// Host epilogue of n independent frames (record -> Match, std::sort, std::unique) on a few threads.
+static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Cand>>& raws, std::vector<std::vector<Match>>& outs) {
+  const int n = (int)raws.size();
+  outs.resize(n);
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i) { to_matches(h, raws[i], outs[i]); finalize_matches(outs[i]); }
+  };
+  size_t total = 0;
+  for (auto& r : raws) total += r.size();
+  int nt = (int)std::min<size_t>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), total / 2048 + 1);
+  if (nt <= 1 || n < 2) { work(0, n); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t) pool.emplace_back(work, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
+  for (auto& th : pool) th.join();
 }
 
 static int prepare(lmb200_detector* h, const lmb200_image* frames, int n_frames, int n_sources,
@@ -649,7 +691,28 @@ int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float thre
   cudaStream_t st = h->lanes[0].stream;
   rc = run_frame_side(h, first_slot, count, st);
   if (rc) return rc;
-  return run_matching(h, first_slot, count, threshold, st);
+  rc = run_matching(h, first_slot, count, threshold, st);
+  if (rc) return rc;
+  // completion event of this slot range: the fetch calls wait on it from the copy stream, so a fetch of step k does
+  // not queue behind the kernels of step k+1 that were already enqueued on the compute stream
+  ResidentMark& mk = h->resident_marks[h->resident_next++ & 3];
+  if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
+  mk.first = first_slot; mk.count = count;
+  CU(cudaEventRecord(mk.ev, st));
+  return LMB200_OK;
+}
+
+// Stream on which the results of slots [first, first+count) can be read: the copy stream, made to wait for the
+// matching lmb200_match_resident call (falls back to the compute stream when no mark covers the range).
+static cudaStream_t resident_fetch_stream(lmb200_detector* h, int first, int count) {
+  for (int i = 1; i <= 4; ++i) {
+    ResidentMark& mk = h->resident_marks[(h->resident_next - i) & 3];
+    if (mk.ev && mk.first <= first && first + count <= mk.first + mk.count) {
+      if (cudaStreamWaitEvent(h->lanes[1].stream, mk.ev, 0) == cudaSuccess) return h->lanes[1].stream;
+      break;
+    }
+  }
+  return h->lanes[0].stream;
 }
 
 int lmb200_fetch_resident(lmb200_handle h, int first_slot, int count, lmb200_match_rec* out, size_t cap, size_t* offsets) {
@@ -657,19 +720,18 @@ int lmb200_fetch_resident(lmb200_handle h, int first_slot, int count, lmb200_mat
   if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
   cudaSetDevice(h->device);
   std::vector<std::vector<Cand>> raw;
-  int rc = fetch_grow(h, first_slot, count, h->lanes[0].stream, raw);
+  int rc = fetch_grow(h, first_slot, count, resident_fetch_stream(h, first_slot, count), raw);
   if (rc) return rc;
   size_t base = 0;
   int status = LMB200_OK;
-  std::vector<Match> m;
+  std::vector<std::vector<Match>> ms;
+  finalize_frames(h, raw, ms);
   for (int i = 0; i < count; ++i) {
-    to_matches(h, raw[i], m);
     h->prof.candidates += (long long)raw[i].size();
-    finalize_matches(m);
-    h->prof.matches += (long long)m.size();
+    h->prof.matches += (long long)ms[i].size();
     size_t n = 0;
     if (offsets) offsets[i] = base;
-    if (emit(h, m, out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
+    if (emit(h, ms[i], out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
     base += n;
   }
   if (offsets) offsets[count] = base;
@@ -1194,8 +1256,11 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
   if (!h->nccl_comm) return set_error(h, LMB200_E_COMM, "communicator not initialised (lmb200_comm_init)");
   cudaSetDevice(h->device);
-  cudaStream_t st = h->lanes[0].stream;
+  cudaStream_t st = resident_fetch_stream(h, first_slot, count);
   const int world = h->comm_world;
+  const bool trace = std::getenv("LMB200_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tt[5] = {now(), 0, 0, 0, 0};
   // 1. local overflow check (a rank that overflowed redoes its own template side; no collective involved)
   for (;;) {
     CU(cudaMemcpyAsync(h->h_ctr + first_slot, h->d_ctr.as<SlotCtr>() + first_slot, sizeof(SlotCtr) * count, cudaMemcpyDeviceToHost, st));
@@ -1206,10 +1271,12 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     float thr = h->slot_threshold[first_slot];
     int rc = grow_capacity(h);
     if (rc) return rc;
-    rc = run_matching(h, first_slot, count, thr, st);
+    rc = run_matching(h, first_slot, count, thr, h->lanes[0].stream);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(h->lanes[0].stream));
   }
   for (int i = 0; i < count; ++i) h->prof.bytes_local += (long long)h->h_ctr[first_slot + i].local_bytes;
+  tt[1] = now();
   // 2. fixed-capacity send buffer per frame: record 0 = {count,..}, then up to gather_cap records.
   //    Every rank sees every count after the gather, so all ranks take the same grow decision.
   if (h->gather_cap <= 0) h->gather_cap = 255;  // 4 KB per frame and rank; doubles when a list is longer
@@ -1240,24 +1307,46 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     while (h->gather_cap < maxc) h->gather_cap *= 2;
   }
   if (h->profiling) collect_profile(h);
-  // 3. rank-ordered concatenation == reference generation order; same epilogue as the 1-GPU path
+  tt[2] = now();
+  // 3. restore reference generation order (rank-ordered concatenation for contiguous shards; ordered by selection
+  //    position for interleaved shards: every template lives on exactly one rank and its records are already in
+  //    raster order), then the same epilogue as the 1-GPU path
   size_t base = 0;
   int status = LMB200_OK;
-  std::vector<Cand> all;
-  std::vector<Match> m;
-  for (int i = 0; i < count; ++i) {
-    all.clear();
-    for (int r = 0; r < world; ++r) {
-      const Cand* rec = h->h_gather + ((size_t)r * count + i) * (1 + h->gather_cap);
-      all.insert(all.end(), rec + 1, rec + 1 + rec[0].tsel);
+  std::vector<std::vector<Cand>> alls(count);
+  {
+    auto gather_frames = [&](int lo, int hi) {
+      for (int i = lo; i < hi; ++i) {
+        std::vector<Cand>& all = alls[i];
+        for (int r = 0; r < world; ++r) {
+          const Cand* rec = h->h_gather + ((size_t)r * count + i) * (1 + h->gather_cap);
+          all.insert(all.end(), rec + 1, rec + 1 + rec[0].tsel);
+        }
+        if (h->shard_interleaved)
+          std::stable_sort(all.begin(), all.end(), [h](const Cand& a, const Cand& b) { return h->pos_of_g[a.tsel] < h->pos_of_g[b.tsel]; });
+      }
+    };
+    const int nt = count >= 16 ? 4 : 1;
+    if (nt == 1) gather_frames(0, count);
+    else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; ++t) pool.emplace_back(gather_frames, count * t / nt, count * (t + 1) / nt);
+      for (auto& th : pool) th.join();
     }
-    to_matches(h, all, m);
-    h->prof.candidates += (long long)all.size();
-    finalize_matches(m);
-    h->prof.matches += (long long)m.size();
+  }
+  tt[3] = now();
+  std::vector<std::vector<Match>> ms;
+  finalize_frames(h, alls, ms);
+  tt[4] = now();
+  if (trace && h->comm_rank == 0)
+    std::fprintf(stderr, "[lmb200 trace] allgather fetch: wait compute %.3f ms, gather+D2H %.3f ms, reorder %.3f ms, sort/unique %.3f ms\n",
+                 tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3]);
+  for (int i = 0; i < count; ++i) {
+    h->prof.candidates += (long long)alls[i].size();
+    h->prof.matches += (long long)ms[i].size();
     size_t n = 0;
     if (offsets) offsets[i] = base;
-    if (emit(h, m, out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
+    if (emit(h, ms[i], out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
     base += n;
   }
   if (offsets) offsets[count] = base;

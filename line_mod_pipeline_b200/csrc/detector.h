@@ -63,6 +63,7 @@ struct Lane {
 };
 
 struct ProfRec { int family; cudaEvent_t a, b; };
+struct ResidentMark { cudaEvent_t ev = nullptr; int first = 0, count = 0; };  // completion of one lmb200_match_resident call
 
 // One submitted lmb200_match_batch: chunk schedule, completion events and per-frame pinned result staging.
 struct BatchTicket {
@@ -113,6 +114,7 @@ struct lmb200_detector {
   lmh::DevBuf d_sel;
   long long sel_bytes_coarse = 0;
   int shard_rank = 0, shard_world = 1;
+  bool shard_interleaved = false; std::vector<int> pos_of_g;  // interleaved shards: global template index -> selection position
 
   // frame plan
   int rows = 0, cols = 0, slots = 0;
@@ -133,6 +135,7 @@ struct lmb200_detector {
   lmh::BatchTicket tickets[2];
   std::vector<cudaEvent_t> group_done; std::vector<char> group_used; int b_groups = 0;
   long long chunk_seq = 0, buffer_generation = 0;
+  lmh::ResidentMark resident_marks[4]; unsigned resident_next = 0;
 
   // profiling
   bool profiling = false;
