@@ -103,6 +103,31 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for bit, n in self.REASONS.items() if self.mask & bit], "samples": len(sm), "source": self.src}
 
 
+def pin_to_gpu_numa_node(index):
+    """One process per GPU: run (and first-touch the pinned frame buffers) on the CPUs of the GPU's NUMA node, so eight
+    ranks do not pull their H2D traffic across the socket interconnect.  Best effort; returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                      # 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return "numa_node unknown"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "numa node %d, %d cpus" % (node, len(allowed))
+        return "numa node %d has no allowed cpus" % node
+    except Exception as e:
+        return "not pinned (%s)" % type(e).__name__
+
+
 def build_templates_product(det, n_templates, bgr, depth):
     """configs[1] template set through the PRODUCT's own addTemplate: ~10 % planted on frame 0, rest random (seed 99)."""
     from line_mod_pipeline_b200 import synth
@@ -195,6 +220,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    affinity = pin_to_gpu_numa_node(local) if world > 1 else "single process: not pinned"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -413,7 +439,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "configs[1]: 640x480 RGB-D frame vs %d templates (CG+DN, T={5,8}), threshold %g; step = batch of %d distinct frames per GPU"
                                    % (n_tpl, args.threshold, B),
-                       "frames_per_step_per_gpu": B, "templates": n_tpl, "planted_templates": planted, "shard": args.shard,
+                       "frames_per_step_per_gpu": B, "cpu_affinity": affinity, "templates": n_tpl, "planted_templates": planted, "shard": args.shard,
                        "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of linear memories per step" % (B * FRAME_BYTES / 1e6, B * 6.144)},
             "e2e": e2e, "gpu_launches": int(sum(launches.values())), "roofline": roofline, "cpu_baseline": cpu,
             "clocks": clocks, "kernels": kernels, "similarity_GBps": sim_gbps, "single_frame": single, "matches_per_step": n_matches,
