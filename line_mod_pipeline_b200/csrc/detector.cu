@@ -231,6 +231,8 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
         return set_error(h, LMB200_E_SIZE, "image size at pyramid level " + std::to_string(l) + " (" + std::to_string(c) +
                                                 "x" + std::to_string(r) + ") must be divisible by T and rows*cols by 16");
       if (c > 16383 || r > 16383) return set_error(h, LMB200_E_SIZE, "image larger than 16383 pixels per side");
+      if (l == L - 1 && (long long)(r / T) * (c / T) >= (1 << 21))
+        return set_error(h, LMB200_E_SIZE, "coarsest level has more than 2^21 positions (add a pyramid level or use a larger T)");
       r /= 2; c /= 2;
     }
     CU(cudaDeviceSynchronize());

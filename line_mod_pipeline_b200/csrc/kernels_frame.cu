@@ -484,12 +484,9 @@ static size_t sl_smem_bytes(int T, int cw) {
 
 void launch_spread_linearize(const u8* q, size_t q_stride, const u8* mask, size_t mask_stride, u8* lm,
                              size_t lm_stride, LevelGeom g, const uint2* table, int frames, cudaStream_t st) {
-  static size_t configured = 0;
   size_t smem = sl_smem_bytes(g.T, g.W < SL_CW ? g.W : SL_CW);
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device, so set it on every such launch (cheap) rather than caching it per process
     cudaFuncSetAttribute(spread_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   dim3 grid(g.H, (g.W + SL_CW - 1) / SL_CW, frames);
   spread_linearize_kernel<<<grid, 256, smem, st>>>(q, q_stride, mask, mask_stride, lm, lm_stride, g, table);
 }

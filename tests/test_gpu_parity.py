@@ -383,3 +383,36 @@ def test_pipelined_overflow_regrows_both_tickets():
             got = prep["out"][offs[i]:offs[i + 1]].view(np.recarray)
             assert len(got) > 64
             assert_same_matches(got, ora.match(f, 20.0, threads=8).matches(0), "overflow pipelined frame %d" % i)
+
+
+def test_single_level_pyramid_wide_sums():
+    """One pyramid level with two modalities: 63+63 features at the (only = coarsest) level, raw scores up to 504 —
+    the u16-widening instantiation of the coarse kernel — and no refinement (scores keep upstream's +0.5f)."""
+    bgr, depth = synth.make_frame(8)
+    det, ora = make_pair(T=(8,))
+    n = add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(8))
+    assert n >= 5
+    add_random(det, ora, 150, levels=1)
+    for thr in (80.0, 45.0):
+        got, ref = _check_frame_side(det, ora, [bgr, depth], thr, n_maps=2)
+        assert_same_matches(det.debugFetch(K.DBG_COARSE, 0), ref.matches(2), "1-level coarse thr=%g" % thr)
+        assert_same_matches(got, ref.matches(0), "1-level thr=%g" % thr)
+    assert len(got) > 0 and got.similarity.max() > 100.0      # 100 % + 0.5
+
+
+def test_three_modalities():
+    """More than two modalities (ColorGradient, DepthNormal, ColorGradient): the per-modality paths of every kernel."""
+    bgr, depth = synth.make_frame(9)
+    bgr2 = np.ascontiguousarray(bgr[:, ::-1])
+    mods = ("cg", "dn", "cg")
+    det, ora = make_pair(modalities=mods)
+    srcs = [bgr, depth, bgr2]
+    n = add_planted_from_oracle(det, ora, srcs, synth.object_masks(9))
+    add_random(det, ora, 150, n_modalities=3)
+    for thr in (75.0, 50.0):
+        got, ref = _check_frame_side(det, ora, srcs, thr, n_maps=6)
+        assert_same_matches(det.debugFetch(K.DBG_UNSORTED, 0), ref.matches(1), "3-modality generation order thr=%g" % thr)
+        assert_same_matches(got, ref.matches(0), "3-modality thr=%g" % thr)
+    frames = [[f[0], f[1], np.ascontiguousarray(f[0][:, ::-1])] for f in (synth.make_frame(i) for i in range(9, 14))]
+    for i, b in enumerate(det.matchBatch(frames, 60.0)):
+        assert_same_matches(b, ora.match(frames[i], 60.0, threads=8).matches(0), "3-modality batch frame %d" % i)
