@@ -114,6 +114,13 @@ int lmb200_get_template(lmb200_handle h, const char* class_id, int template_id, 
  * bb4 (nullable) = x, y, width, height of the cropped bounding box. */
 int lmb200_add_template(lmb200_handle h, const char* class_id, const lmb200_image* sources, int n_sources,
                         const lmb200_image* object_mask /* nullable */, int* bb4, int* template_id);
+/* Bulk form of lmb200_add_template for the reference's generateTemplates loop (HighLevelLinemod.cpp:68-110, one
+ * addTemplate per rendered view): n_views views of one size, sources[view * n_sources + modality], masks[view]
+ * (array nullable, entries with data == NULL mean "no mask").  The views are quantised in batches on the GPU while
+ * host threads select features of the previous batch.  Result = n_views successive lmb200_add_template calls:
+ * template_ids[view] = id or -1, bb4 (nullable) = 4 ints per view (untouched for failed views). */
+int lmb200_add_templates(lmb200_handle h, const char* class_id, int n_views, const lmb200_image* sources, int n_sources,
+                         const lmb200_image* masks, int* bb4, int* template_ids);
 /* Detector::addSyntheticTemplate: n = pyramid_levels*num_modalities templates, index level*M+modality. */
 int lmb200_add_synthetic_template(lmb200_handle h, const char* class_id, const lmb200_template* templates,
                                   int n, int* template_id);

@@ -142,6 +142,23 @@ class Detector {
     if (bounding_box && tid >= 0) { bounding_box->x = bb[0]; bounding_box->y = bb[1]; bounding_box->width = bb[2]; bounding_box->height = bb[3]; }
     return tid;
   }
+  // n successive addTemplate calls in one batched GPU pass (views[i] = that view's sources; masks may be empty or hold
+  // empty entries); returns the template ids (-1 = extraction failed), bounding boxes optional
+  std::vector<int> addTemplates(const std::vector<std::vector<ImageView>>& views, const std::string& class_id,
+                                const std::vector<ImageView>& object_masks = {}, std::vector<Rect>* bounding_boxes = nullptr) {
+    std::vector<lmb200_image> src, mk;
+    for (auto& v : views) for (auto& s : v) src.push_back(s.c());
+    for (auto& m : object_masks) mk.push_back(m.c());
+    if (!mk.empty() && mk.size() != views.size()) throw Error(LMB200_E_INVALID, "one mask per view expected");
+    std::vector<int> tids(views.size(), -1), bb(views.size() * 4, 0);
+    int per = views.empty() ? 0 : (int)views[0].size();
+    check(lmb200_add_templates(h_, class_id.c_str(), (int)views.size(), src.data(), per, mk.empty() ? nullptr : mk.data(), bb.data(), tids.data()));
+    if (bounding_boxes) {
+      bounding_boxes->resize(views.size());
+      for (size_t i = 0; i < views.size(); ++i) { Rect r; r.x = bb[4 * i]; r.y = bb[4 * i + 1]; r.width = bb[4 * i + 2]; r.height = bb[4 * i + 3]; (*bounding_boxes)[i] = r; }
+    }
+    return tids;
+  }
   int addSyntheticTemplate(const std::vector<Template>& templates, const std::string& class_id) {
     std::vector<lmb200_template> t(templates.size());
     std::vector<std::vector<lmb200_feature>> f(templates.size());

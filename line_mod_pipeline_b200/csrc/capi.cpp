@@ -174,6 +174,13 @@ int lmb200_add_template(lmb200_handle h, const char* class_id, const lmb200_imag
   return add_template_gpu(h, class_id, sources, n_sources, object_mask, bb4, template_id);
 }
 
+int lmb200_add_templates(lmb200_handle h, const char* class_id, int n_views, const lmb200_image* sources, int n_sources,
+                         const lmb200_image* masks, int* bb4, int* template_ids) {
+  if (!h || !class_id || !sources || !template_ids || n_views < 0) return LMB200_E_INVALID;
+  if (n_views == 0) return LMB200_OK;
+  return add_templates_bulk(h, class_id, n_views, sources, n_sources, masks, bb4, template_ids);
+}
+
 int lmb200_add_synthetic_template(lmb200_handle h, const char* class_id, const lmb200_template* templates, int n, int* template_id) {
   if (!h || !class_id || !templates) return LMB200_E_INVALID;
   if (n != h->cfg.num_modalities * h->cfg.pyramid_levels)

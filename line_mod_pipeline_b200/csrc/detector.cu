@@ -7,6 +7,7 @@
 #include "detector.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1246,6 +1247,169 @@ int add_template_gpu(lmb200_detector* h, const char* class_id, const lmb200_imag
   if (bb4) std::memcpy(bb4, bb, sizeof(bb));
   *template_id = (int)tps.size();
   tps.push_back(tp);
+  return LMB200_OK;
+}
+
+
+// Bulk form of addTemplate: the reference's generateTemplates loop renders one view after the
+// other and calls detector->addTemplate on each (HighLevelLinemod.cpp:68-110).  Here `n` rendered views of one
+// size are quantised by the batched frame-side kernels, `BULK_CHUNK` views per launch, while a pool of host
+// threads runs feature selection on the previous chunk (two pinned arenas).  Template ids are assigned in input
+// order to the views whose extraction succeeds, exactly as n successive addTemplate calls would.
+static const int BULK_CHUNK = 32;
+
+int add_templates_bulk(lmb200_detector* h, const char* class_id, int n, const lmb200_image* sources, int n_sources,
+                       const lmb200_image* masks, int* bb4, int* template_ids) {
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  rc = upload_luts(h);
+  if (rc) return rc;
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  int rows = 0, cols = 0;
+  for (int i = 0; i < n; ++i) {
+    int r, c;
+    rc = check_sources(h, sources + (size_t)i * n_sources, n_sources, &r, &c);
+    if (rc) return rc;
+    if (i == 0) { rows = r; cols = c; }
+    else if (r != rows || c != cols) return set_error(h, LMB200_E_SOURCES, "bulk addTemplate needs views of one size");
+    if (masks && masks[i].data && (masks[i].type != LMB200_8UC1 || masks[i].rows != rows || masks[i].cols != cols))
+      return set_error(h, LMB200_E_SOURCES, "object_mask must be 8UC1 of the source size");
+  }
+  std::vector<int> lr(L), lc(L);
+  for (int l = 0; l < L; ++l) { lr[l] = l ? lr[l - 1] / 2 : rows; lc[l] = l ? lc[l - 1] / 2 : cols; }
+  const size_t n0 = (size_t)rows * cols;
+  // per-view record in the pinned arena: ColorGradient keeps (quantized, magnitude) of every level, DepthNormal the
+  // level-0 map (coarser levels are decimations, done by the worker)
+  std::vector<size_t> off_q((size_t)M * L, 0), off_mag((size_t)M * L, 0);
+  size_t rec = 0;
+  for (int m = 0; m < M; ++m) {
+    bool cg = h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT;
+    for (int l = 0; l < (cg ? L : 1); ++l) {
+      size_t nl = (size_t)lr[l] * lc[l];
+      off_q[(size_t)m * L + l] = rec; rec += (nl + 15) & ~(size_t)15;
+      if (cg) { off_mag[(size_t)m * L + l] = rec; rec += (nl * sizeof(float) + 15) & ~(size_t)15; }
+    }
+  }
+  const int B = std::min(n, BULK_CHUNK);
+  const int nchunks = (n + B - 1) / B;
+  u8* arena[2] = {nullptr, nullptr};
+  DevBuf d_a, d_b, d_q, d_mag;
+  auto cleanup = [&]() {
+    for (int a = 0; a < 2; ++a) if (arena[a]) { cudaFreeHost(arena[a]); arena[a] = nullptr; }
+    d_a.release(); d_b.release(); d_q.release(); d_mag.release();
+  };
+  struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};
+  for (int a = 0; a < (nchunks > 1 ? 2 : 1); ++a) CU(cudaHostAlloc((void**)&arena[a], rec * B, cudaHostAllocDefault));
+  ALLOC(d_a, n0 * 3 * B); ALLOC(d_b, n0 * 3 * B); ALLOC(d_q, n0 * B); ALLOC(d_mag, n0 * sizeof(float) * B);
+  cudaStream_t st = h->lanes[0].stream;
+
+  auto enqueue = [&](int k, u8* ar) -> int {
+    const int first = k * B, cnt = std::min(B, n - first);
+    for (int m = 0; m < M; ++m) {
+      const lmb200_modality& mod = h->cfg.modalities[m];
+      const bool cg = mod.type == LMB200_COLOR_GRADIENT;
+      const size_t rowb = (size_t)cols * (cg ? 3 : 2);
+      for (int i = 0; i < cnt; ++i) {
+        const lmb200_image& im = sources[(size_t)(first + i) * n_sources + m];
+        CU(cudaMemcpy2DAsync(d_a.as<u8>() + (size_t)i * rowb * rows, rowb, im.data, im.step ? im.step : rowb, rowb, rows,
+                             cudaMemcpyHostToDevice, st));
+      }
+      if (cg) {
+        u8* cur = d_a.as<u8>();
+        u8* nxt = d_b.as<u8>();
+        for (int l = 0; l < L; ++l) {
+          const size_t nl = (size_t)lr[l] * lc[l];
+          if (l > 0) {
+            launch_pyrdown_bgr(cur, (size_t)lr[l - 1] * lc[l - 1] * 3, nxt, nl * 3, lr[l - 1], lc[l - 1], cnt, st);
+            std::swap(cur, nxt);
+          }
+          launch_cg_quantize(cur, nl * 3, d_q.as<u8>(), nl, d_mag.as<float>(), nl, lr[l], lc[l],
+                             mod.weak_threshold * mod.weak_threshold, cnt, st);
+          CU(cudaMemcpy2DAsync(ar + off_q[(size_t)m * L + l], rec, d_q.p, nl, nl, cnt, cudaMemcpyDeviceToHost, st));
+          CU(cudaMemcpy2DAsync(ar + off_mag[(size_t)m * L + l], rec, d_mag.p, nl * sizeof(float), nl * sizeof(float), cnt,
+                               cudaMemcpyDeviceToHost, st));
+        }
+      } else {
+        launch_dn_quantize(d_a.as<u16>(), n0, d_b.as<u8>(), n0, nullptr, rows, cols, mod.distance_threshold,
+                           mod.difference_threshold, h->d_normal_lut.as<u8>(), cnt, st);
+        launch_median5(d_b.as<u8>(), n0, d_q.as<u8>(), n0, rows, cols, cnt, st);
+        CU(cudaMemcpy2DAsync(ar + off_q[(size_t)m * L], rec, d_q.p, n0, n0, cnt, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CU(cudaGetLastError());
+    return LMB200_OK;
+  };
+
+  struct View { TemplatePyramid tp; int bb[4]; bool ok; };
+  auto extract_view = [&](int idx, const u8* recp, View& v) {
+    v.tp.assign((size_t)M * L, Template());
+    v.ok = true;
+    // mask pyramid (nearest-neighbour halvings, as both quantizers' pyrDown do)
+    std::vector<std::vector<u8>> mk;
+    if (masks && masks[idx].data) {
+      mk.resize(L);
+      const lmb200_image& mi = masks[idx];
+      size_t step = mi.step ? mi.step : (size_t)cols;
+      mk[0].resize(n0);
+      for (int r = 0; r < rows; ++r) std::memcpy(&mk[0][(size_t)r * cols], (const u8*)mi.data + (size_t)r * step, cols);
+      for (int l = 1; l < L; ++l) {
+        mk[l].resize((size_t)lr[l] * lc[l]);
+        resize_nn_host(mk[l - 1].data(), lr[l - 1], lc[l - 1], mk[l].data(), lr[l], lc[l]);
+      }
+    }
+    for (int m = 0; m < M && v.ok; ++m) {
+      const lmb200_modality& mod = h->cfg.modalities[m];
+      int num_features = mod.num_features, extract_threshold = mod.extract_threshold;
+      std::vector<u8> cur, nxt;
+      for (int l = 0; l < L && v.ok; ++l) {
+        if (l > 0) { num_features /= 2; extract_threshold /= 2; }
+        const u8* mask_l = mk.empty() ? nullptr : mk[l].data();
+        if (mod.type == LMB200_COLOR_GRADIENT) {
+          v.ok = extract_color_gradient(recp + off_q[(size_t)m * L + l], (const float*)(recp + off_mag[(size_t)m * L + l]), mask_l,
+                                        lr[l], lc[l], num_features, mod.strong_threshold, l, v.tp[(size_t)l * M + m]);
+        } else {
+          const u8* q = recp + off_q[(size_t)m * L];
+          if (l > 0) {
+            nxt.resize((size_t)lr[l] * lc[l]);
+            resize_nn_host(l == 1 ? q : cur.data(), lr[l - 1], lc[l - 1], nxt.data(), lr[l], lc[l]);
+            cur.swap(nxt);
+            q = cur.data();
+          }
+          v.ok = extract_depth_normal(q, mask_l, lr[l], lc[l], num_features, extract_threshold, l, v.tp[(size_t)l * M + m]);
+        }
+      }
+    }
+    if (v.ok) crop_templates(v.tp, v.bb);
+  };
+
+  // upstream default-inserts the class entry before extraction can fail
+  h->classes[class_id];
+  h->templates_dirty = true;
+  for (int i = 0; i < n; ++i) template_ids[i] = -1;
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int nthreads = std::max(1, std::min(std::min(hw > 0 ? hw : 1, 16), B));
+  rc = enqueue(0, arena[0]);
+  if (rc) return rc;
+  std::vector<View> views(B);
+  for (int k = 0; k < nchunks; ++k) {
+    CU(cudaStreamSynchronize(st));
+    if (k + 1 < nchunks) { rc = enqueue(k + 1, arena[(k + 1) & 1]); if (rc) return rc; }
+    const int first = k * B, cnt = std::min(B, n - first);
+    const u8* ar = arena[k & 1];
+    std::atomic<int> next(0);
+    auto work = [&]() { for (int i; (i = next.fetch_add(1)) < cnt;) extract_view(first + i, ar + (size_t)i * rec, views[i]); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < std::min(nthreads, cnt); ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    std::vector<TemplatePyramid>& tps = h->classes[class_id];
+    for (int i = 0; i < cnt; ++i) {
+      if (!views[i].ok) continue;
+      template_ids[first + i] = (int)tps.size();
+      if (bb4) std::memcpy(bb4 + (size_t)(first + i) * 4, views[i].bb, sizeof(views[i].bb));
+      tps.push_back(std::move(views[i].tp));
+    }
+  }
   return LMB200_OK;
 }
 

@@ -157,6 +157,10 @@ namespace lmh {
 // detector.cu
 int ensure_device(lmb200_detector* h);
 int set_error(lmb200_detector* h, int code, const std::string& msg);
+int add_template_gpu(lmb200_detector* h, const char* class_id, const lmb200_image* sources, int n_sources,
+                     const lmb200_image* object_mask, int* bb4, int* template_id);
+int add_templates_bulk(lmb200_detector* h, const char* class_id, int n, const lmb200_image* sources, int n_sources,
+                       const lmb200_image* masks, int* bb4, int* template_ids);
 int cuda_fail(lmb200_detector* h, cudaError_t e, const char* what);
 // extract.cpp (host feature selection; images are level-sized row-major arrays)
 bool extract_color_gradient(const uint8_t* quant, const float* magnitude, const uint8_t* mask /*nullable*/,

@@ -150,6 +150,24 @@ class Detector:
                                                 C.byref(mimg) if object_mask is not None else None, bb, C.byref(tid)))
         return tid.value, tuple(bb)
 
+    def addTemplates(self, views, class_id, object_masks=None):
+        """Bulk addTemplate: `views` = list of per-view source lists, `object_masks` = list (entries may be None).
+        -> list of (template_id, (x, y, w, h)), the result of len(views) successive addTemplate calls."""
+        n = len(views)
+        if n == 0:
+            return []
+        M = len(views[0])
+        keep = [[_image(s) for s in v] for v in views]
+        arr = (K.Image * (n * M))(*[i[0] for v in keep for i in v])
+        marr = None
+        if object_masks is not None:
+            mkeep = [_image(m) for m in object_masks]
+            marr = (K.Image * n)(*[m[0] for m in mkeep])
+        bb = (C.c_int * (4 * n))()
+        tids = (C.c_int * n)()
+        self._check(self._L.lmb200_add_templates(self._h, class_id.encode(), n, arr, M, marr, bb, tids))
+        return [(tids[i], tuple(bb[4 * i:4 * i + 4])) for i in range(n)]
+
     def addSyntheticTemplate(self, templates, class_id):
         arr = (K.Template * len(templates))()
         keep = []

@@ -237,6 +237,43 @@ def test_add_template_parity(fixture_frame):
         assert_same_matches(det.match([bgr, depth], 75.0), ora.match([bgr, depth], 75.0).matches(0), "after addTemplate")
 
 
+def test_add_templates_bulk_parity():
+    """lmb200_add_templates (batched GPU quantisation, threaded host selection, two chunks) == one oracle addTemplate
+    per view, including failed views, the ids after them, and the matches the resulting set produces."""
+    views, masks = [], []
+    for i in range(3):
+        bgr, depth = synth.make_frame(20 + i)
+        for m in synth.object_masks(20 + i)[:12] + synth.planted_masks(6, seed=40 + i):
+            views.append([bgr, depth]); masks.append(m)
+        views.append([bgr, depth]); masks.append(np.zeros((480, 640), np.uint8))        # fails
+        views.append([bgr, depth]); masks.append(None)                                   # whole image
+    assert len(views) > 32                                                                # more than one chunk
+    for mods, T in ((("cg", "dn"), (5, 8)), (("cg",), (2, 8))):
+        det, ora = make_pair(modalities=mods, T=T)
+        v = [vw[:len(mods)] for vw in views]
+        res = det.addTemplates(v, "obj", masks)
+        ok = 0
+        for i, (tid, bb) in enumerate(res):
+            otid, obb = ora.add_template(v[i], "obj", masks[i])
+            assert tid == otid, "view %d: template id %d vs oracle %d" % (i, tid, otid)
+            if tid < 0:
+                continue
+            ok += 1
+            assert tuple(bb) == tuple(obb)
+            want = O.decode_pyramid(ora.get_template_flat("obj", tid))
+            for a, b in zip(det.getTemplates("obj", tid), want):
+                assert (a["width"], a["height"], a["pyramid_level"]) == (b["width"], b["height"], b["pyramid_level"])
+                assert np.array_equal(a["features"], b["features"])
+        assert ok >= 20 and ok < len(views) and det.numTemplates("obj") == ora.num_templates("obj") == ok
+        # a second bulk call continues the id sequence, exactly like further addTemplate calls
+        more = det.addTemplates(v[:3], "obj", masks[:3])
+        assert [t for t, _ in more if t >= 0] == list(range(ok, ok + sum(1 for t, _ in more if t >= 0)))
+        for i in range(3):
+            ora.add_template(v[i], "obj", masks[i])
+        src = views[0][:len(mods)]
+        assert_same_matches(det.match(src, 75.0), ora.match(src, 75.0).matches(0), "after bulk addTemplates")
+
+
 def test_config2_full_size():
     """BASELINE config 2: one 640x480 frame vs 3 000 templates (300 planted + 2 700 random), thresholds 80 and 57."""
     bgr, depth = synth.make_frame(0)
