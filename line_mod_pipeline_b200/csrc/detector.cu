@@ -203,6 +203,7 @@ static int alloc_match_buffers(lmb200_detector* h) {
   ALLOC(h->d_cand, (size_t)S * h->cand_cap * sizeof(Cand));
   ALLOC(h->d_out, (size_t)S * h->out_cap * sizeof(Cand));
   ALLOC(h->d_ctr, (size_t)S * sizeof(SlotCtr));
+  ALLOC(h->d_resp_sum, (size_t)S * MAX_MOD * sizeof(u32));
   ALLOC(h->d_tpl_start, (size_t)S * h->nsel_stride * sizeof(int));
   ALLOC(h->d_tpl_cnt, (size_t)S * h->nsel_stride * sizeof(int));
   ALLOC(h->d_tpl_alive, (size_t)S * h->nsel_stride * sizeof(int));
@@ -433,6 +434,7 @@ static bool chunk_is_contiguous(lmb200_detector* h, const lmb200_image* frames, 
 // spread + response + linearize.  (Detector::match, first half.)
 static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st) {
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  CU(cudaMemsetAsync(h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD, 0, (size_t)count * MAX_MOD * sizeof(u32), st));
   for (int l = 0; l < L; ++l) {
     LevelBuffers& lb = h->levels[l];
     for (int m = 0; m < M; ++m) {
@@ -475,7 +477,8 @@ static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t
       if (l == L - 1) h->prof.launches[LMB200_K_LINEARIZE]++;  // the nibble packer is a launch of its own
       if (l == L - 1)
         launch_pack_nibbles(lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride, lb.lm_stride,
-                            lb.lmn[m].as<u8>() + (size_t)first * lb.lmn_stride, lb.lmn_stride, lb.g, count, st);
+                            lb.lmn[m].as<u8>() + (size_t)first * lb.lmn_stride, lb.lmn_stride, lb.g, count,
+                            h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD + m, MAX_MOD, st);
     }
   }
   CU(cudaGetLastError());
@@ -517,6 +520,7 @@ static LevelParams make_level_params(lmb200_detector* h, int l, int first, bool 
   lp.hdr = h->d_hdr[l].as<TplHdr>();
   lp.offs = h->d_offs[l].as<u32>();
   lp.feat = h->d_feat[l].as<u32>();
+  lp.resp_sum = h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD;
   return lp;
 }
 

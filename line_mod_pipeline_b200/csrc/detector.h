@@ -124,6 +124,7 @@ struct lmb200_detector {
   lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
   size_t depth_stride = 0;
   lmh::DevBuf d_frames; size_t frame_bytes = 0, src_off[LMB200_MAX_MODALITIES] = {0, 0, 0, 0};  // [slots][sources back to back]
+  lmh::DevBuf d_resp_sum;                           // [slots][MAX_MOD] response sums of the coarsest linear memories
   lmh::DevBuf d_cand, d_ctr, d_tpl_start, d_tpl_cnt, d_tpl_alive, d_out;
   int nsel_stride = 0;
   // pinned host mirrors

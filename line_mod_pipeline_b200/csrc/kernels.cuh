@@ -110,7 +110,7 @@ void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int
 inline size_t coarse_zero_tail(const LevelGeom& g) { return (((size_t)g.W * g.H / 2 + 64) + 255) & ~(size_t)255; }
 // byte linear memory -> nibble-packed copy (coarsest level only; input of similarity_coarse_kernel)
 void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_stride, LevelGeom g, int frames,
-                         cudaStream_t st);
+                         u32* resp_sum /*+= responses, per frame*/, int resp_stride, cudaStream_t st);
 
 struct MatchParams {
   int M, nsel, frames;
@@ -128,6 +128,7 @@ struct LevelParams {
   LevelGeom g;
   const u8* lm[MAX_MOD]; size_t lm_stride[MAX_MOD];   // this level's linear memories per modality
   const TplHdr* hdr; const u32* offs; const u32* feat; // this level's template tables
+  const u32* resp_sum;                                 // coarsest level: [frames][MAX_MOD] response sums (modality order)
 };
 
 void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, bool wide, cudaStream_t st);

@@ -131,6 +131,9 @@ __device__ __forceinline__ int raw_threshold(int nf, float threshold) {
 // ---------------------------------------------------------------------------------------------
 constexpr int CW_WARPS = 4;          // warps (templates) per CTA
 constexpr int CW_QCAP = 96;          // queued hits per warp
+#ifndef CW_TPW
+#define CW_TPW 8                     // most templates per warp (consecutive groups of CW_WARPS); chosen per launch
+#endif
 #ifndef CW_MINB
 #define CW_MINB 7                    // resident CTAs per SM the register allocation targets (7 -> <= 72 registers; measured best of 5..8)
 #endif
@@ -223,6 +226,7 @@ struct CoarseCtx {
   int M, T, W, H, HW, raw_thr, nf_total;
   u32 per_label;
   const int* Pm;                     // plan: upstream's template_positions per modality
+  const int* ord;                    // this frame's modality order (shared memory)
   __device__ __forceinline__ int P(int m) const { return __ldg(Pm + m); }
 };
 
@@ -255,7 +259,9 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
     u32 tot[WIDE ? 16 : 8];  // WIDE: u16 pairs (see wide_val); else byte sums laid out like acc.b
 #pragma unroll
     for (int i = 0; i < (WIDE ? 16 : 8); ++i) tot[i] = 0u;
-    for (int m = 0; m < cx.M; ++m) {
+    bool dead = false;
+    for (int mi = 0; mi < cx.M; ++mi) {
+      const int m = cx.ord[mi];  // most selective modality of this frame first (see the early exit below)
       const int P = cx.P(m);
       if (32 * c0 >= P) continue;  // warp-uniform
       const int rem = P - pos0;
@@ -278,7 +284,25 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
         }
         acc.b[w] = 0u;
       }
+      // exact early exit: when no position of this pass can still exceed raw_thr, the remaining modalities
+      // cannot produce a hit (responses are <= 4 per feature) and the pass ends here
+      int later = 0;  // features of the modalities still to come
+      for (int k = mi + 1; k < cx.M; ++k) later += cx.hdr.nf(cx.ord[k]);
+      const int bound = cx.raw_thr - 4 * later;
+      if (mi + 1 < cx.M && bound >= 0) {  // warp-uniform
+        const u32 Kb = (u32)(0x7FFF - bound) * 0x00010001u;
+        u32 alive = 0;
+        if (WIDE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) alive |= tot[i] + Kb;
+        } else {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) alive |= ((tot[w] & 0x00FF00FFu) + Kb) | (((tot[w] >> 8) & 0x00FF00FFu) + Kb);
+        }
+        if (!__any_sync(0xffffffffu, (alive & 0x80008000u) != 0u)) { dead = true; break; }
+      }
     }
+    if (dead) continue;
     u32 any = 0;
     if (WIDE) {
 #pragma unroll
@@ -367,8 +391,9 @@ __device__ __forceinline__ void coarse_template(const MatchParams& mp, const Coa
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kernel(MatchParams mp, LevelParams lp) {
+__global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kernel(MatchParams mp, LevelParams lp, int tpw) {
   __shared__ const u8* s_lm[MAX_MOD];
+  __shared__ int s_ord[MAX_MOD];
   __shared__ u32 s_queue[CW_WARPS][CW_QCAP];
   __shared__ u32 s_off[CW_WARPS][MAX_MOD * COARSE_SLOTS];
   const int frame = blockIdx.y;
@@ -378,52 +403,84 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kern
     s_lm[1] = lp.lm[1] + (size_t)frame * lp.lm_stride[1];
     s_lm[2] = lp.lm[2] + (size_t)frame * lp.lm_stride[2];
     s_lm[3] = lp.lm[3] + (size_t)frame * lp.lm_stride[3];
+    // Modalities are summed in ascending order of this frame's mean response: the modality with the lowest
+    // responses bounds the scores hardest, so the early exit of coarse_sweep fires for the most templates.
+    // Any order gives the same sums; the order only decides how much work the exit saves.
+    u32 key[MAX_MOD];
+    for (int m = 0; m < MAX_MOD; ++m) { s_ord[m] = m; key[m] = m < mp.M ? __ldg(lp.resp_sum + (size_t)frame * MAX_MOD + m) : 0xFFFFFFFFu; }
+    for (int i = 1; i < mp.M; ++i)
+      for (int j = i; j > 0 && key[s_ord[j]] < key[s_ord[j - 1]]; --j) { int t = s_ord[j]; s_ord[j] = s_ord[j - 1]; s_ord[j - 1] = t; }
   }
   __syncthreads();
-  const int isel = blockIdx.x * CW_WARPS + warp;
-  if (isel >= mp.nsel) return;
-  const int g = mp.sel[isel];
-  CoarseCtx cx;
-  cx.hdr = load_hdr(lp.hdr + g);
-  cx.M = mp.M; cx.T = lp.g.T; cx.W = lp.g.W; cx.H = lp.g.H; cx.HW = lp.g.W * lp.g.H;
-  cx.per_label = lp.g.per_label;
-  cx.nf_total = cx.hdr.nf_total();
-  cx.raw_thr = raw_threshold(cx.nf_total, mp.threshold);
-  if (cx.raw_thr > 0x7FFE) cx.raw_thr = 0x7FFE;  // nothing can exceed it anyway (scores <= 1008)
-  if (cx.raw_thr < 0) cx.raw_thr = -1;
-  cx.lst = s_off[warp];
-  cx.Pm = lp.hdr[g].P;
-  for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * COARSE_SLOTS + s);
-  __syncwarp();
-  if (cx.hdr.flags & 2u) coarse_template<true, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
-  else coarse_template<false, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
+  for (int it = 0; it < tpw; ++it) {  // a warp scores tpw templates: early exits even out over the sequence
+    const int isel = (blockIdx.x * tpw + it) * CW_WARPS + warp;
+    if (isel >= mp.nsel) return;
+    const int g = mp.sel[isel];
+    CoarseCtx cx;
+    cx.hdr = load_hdr(lp.hdr + g);
+    cx.M = mp.M; cx.T = lp.g.T; cx.W = lp.g.W; cx.H = lp.g.H; cx.HW = lp.g.W * lp.g.H;
+    cx.per_label = lp.g.per_label;
+    cx.nf_total = cx.hdr.nf_total();
+    cx.raw_thr = raw_threshold(cx.nf_total, mp.threshold);
+    if (cx.raw_thr > 0x7FFE) cx.raw_thr = 0x7FFE;  // nothing can exceed it anyway (scores <= 1008)
+    if (cx.raw_thr < 0) cx.raw_thr = -1;
+    cx.lst = s_off[warp];
+    cx.Pm = lp.hdr[g].P;
+    cx.ord = s_ord;
+    __syncwarp();  // the previous template's reads of s_off / s_queue are done
+    for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * COARSE_SLOTS + s);
+    __syncwarp();
+    if (cx.hdr.flags & 2u) coarse_template<true, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
+    else coarse_template<false, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
+  }
 }
 
 // wide: some template has 4*nf_total > 255 at the coarsest level (byte sums across modalities could carry)
 void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, bool wide, cudaStream_t st) {
   if (mp.nsel <= 0 || mp.frames <= 0) return;
-  dim3 grid((mp.nsel + CW_WARPS - 1) / CW_WARPS, mp.frames);
-  if (wide) similarity_coarse_kernel<true><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp);
-  else similarity_coarse_kernel<false><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp);
+  // templates per warp: 1 while the grid is a few waves of the machine (latency matters), up to CW_TPW for big batches
+  static int sm_count[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sm_count[dev]) { cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev); if (sm_count[dev] <= 0) sm_count[dev] = 148; }
+  const long long ctas1 = (long long)((mp.nsel + CW_WARPS - 1) / CW_WARPS) * mp.frames;
+  const long long wave = (long long)sm_count[dev] * CW_MINB;
+  int tpw = (int)(ctas1 / (4 * wave));
+  tpw = tpw < 1 ? 1 : (tpw > CW_TPW ? CW_TPW : tpw);
+  dim3 grid((mp.nsel + CW_WARPS * tpw - 1) / (CW_WARPS * tpw), mp.frames);
+  if (wide) similarity_coarse_kernel<true><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp, tpw);
+  else similarity_coarse_kernel<false><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp, tpw);
 }
 
-// Packs a byte linear memory (values 0..4) two positions per byte: out[q] = in[2q] | in[2q+1] << 4.
+// Packs a byte linear memory (values 0..4) two positions per byte: out[q] = in[2q] | in[2q+1] << 4.  The first warp
+// of every block also adds the responses it packs into resp_sum[frame]: a 1/8 sample of the linear memory, the
+// per-frame statistic that orders the modalities in the coarse kernel (one atomic per block).
 __global__ void __launch_bounds__(256) pack_nibbles_kernel(const u8* __restrict__ lm, size_t lm_stride, u8* __restrict__ lmn,
-                                                           size_t lmn_stride, u32 n_out8 /* 8-byte output groups */) {
+                                                           size_t lmn_stride, u32 n_out8 /* 8-byte output groups */,
+                                                           u32* __restrict__ resp_sum, int resp_stride) {
   const u32 i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n_out8) return;
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(lm + (size_t)blockIdx.y * lm_stride) + i);
-  const u32 t0 = v.x | (v.x >> 4), t1 = v.y | (v.y >> 4), t2 = v.z | (v.z >> 4), t3 = v.w | (v.w >> 4);
-  uint2 o;
-  o.x = __byte_perm(t0, t1, 0x6420);
-  o.y = __byte_perm(t2, t3, 0x6420);
-  reinterpret_cast<uint2*>(lmn + (size_t)blockIdx.y * lmn_stride)[i] = o;
+  u32 sum = 0;
+  if (i < n_out8) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(lm + (size_t)blockIdx.y * lm_stride) + i);
+    const u32 t0 = v.x | (v.x >> 4), t1 = v.y | (v.y >> 4), t2 = v.z | (v.z >> 4), t3 = v.w | (v.w >> 4);
+    uint2 o;
+    o.x = __byte_perm(t0, t1, 0x6420);
+    o.y = __byte_perm(t2, t3, 0x6420);
+    reinterpret_cast<uint2*>(lmn + (size_t)blockIdx.y * lmn_stride)[i] = o;
+    if (threadIdx.x < 32) sum = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+  }
+  if (threadIdx.x >= 32) return;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (threadIdx.x == 0 && sum) atomicAdd(resp_sum + (size_t)blockIdx.y * resp_stride, sum);
 }
 
-void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_stride, LevelGeom g, int frames, cudaStream_t st) {
+void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_stride, LevelGeom g, int frames,
+                         u32* resp_sum, int resp_stride, cudaStream_t st) {
   u32 n_out8 = g.per_label / 2;  // 8*per_label positions / 16 per thread
   dim3 grid((n_out8 + 255) / 256, frames);
-  pack_nibbles_kernel<<<grid, 256, 0, st>>>(lm, lm_stride, lmn, lmn_stride, n_out8);
+  pack_nibbles_kernel<<<grid, 256, 0, st>>>(lm, lm_stride, lmn, lmn_stride, n_out8, resp_sum, resp_stride);
 }
 
 // ---------------------------------------------------------------------------------------------
