@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblmb200.so")
+SO_PATH = os.environ.get("LMB200_SO") or os.path.join(_HERE, "liblmb200.so")  # LMB200_SO: A/B builds of the same library
 
 MAX_MOD, MAX_LEVELS = 4, 8
 T_8UC1, T_16UC1, T_8UC3 = 0, 2, 16

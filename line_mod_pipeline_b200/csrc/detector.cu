@@ -180,7 +180,7 @@ static int rebuild_templates(lmb200_detector* h) {
       }
     ALLOC(h->d_hdr[l], hdr.size() * sizeof(TplHdr));
     ALLOC(h->d_feat[l], feat.size() * sizeof(u32));
-    ALLOC(h->d_offs[l], (size_t)std::max(1, h->ntpl) * M * (l == L - 1 ? COARSE_SLOTS : FEAT_SLOTS) * sizeof(u32));
+    ALLOC(h->d_offs[l], (size_t)std::max(1, h->ntpl) * M * (l == L - 1 ? COARSE_SLOTS : 2 * FEAT_SLOTS) * sizeof(u32));
     CU(cudaMemcpy(h->d_hdr[l].p, hdr.data(), hdr.size() * sizeof(TplHdr), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_feat[l].p, feat.data(), feat.size() * sizeof(u32), cudaMemcpyHostToDevice));
   }
@@ -255,9 +255,13 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
       LevelBuffers& lb = h->levels[l];
       int T = h->cfg.T[l];
       lb.g.T = T; lb.g.rows = r; lb.g.cols = c; lb.g.W = c / T; lb.g.H = r / T;
-      lb.g.per_label = (u32)((size_t)r * c);
+      // coarsest level: upstream's flat linear memories; finer levels: 16-column strips (see LevelGeom)
+      lb.g.strips = l == L - 1 ? 0 : (lb.g.W + 15) / 16;
+      lb.g.plane = lb.g.strips ? (u32)lb.g.strips * lb.g.H * 16u : (u32)lb.g.W * lb.g.H;
+      lb.g.per_label = (u32)T * T * lb.g.plane;
       lb.q_stride = up256((size_t)r * c);
-      lb.lm_stride = up256((size_t)8 * r * c + LM_PAD);
+      lb.lm_stride = up256((size_t)8 * lb.g.per_label + LM_PAD + (lb.g.strips ? (size_t)lb.g.H * 16 : 0));  // + one strip column: the
+                                                                 // second chunk of a patch row in the last strip is loaded, never used
       lb.bgr_stride = l == 0 ? h->frame_bytes : up256((size_t)r * c * 3);
       for (int m = 0; m < M; ++m) {
         ALLOC(lb.q[m], lb.q_stride * S);
@@ -1102,7 +1106,20 @@ int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst
     LevelBuffers& lb = h->levels[index / M];
     int m = index % M;
     if (kind == LMB200_DBG_QUANTIZED) return give(lb.q[m].as<u8>() + (size_t)slot * lb.q_stride, (size_t)lb.g.rows * lb.g.cols);
-    return give(lb.lm[m].as<u8>() + (size_t)slot * lb.lm_stride, (size_t)8 * lb.g.rows * lb.g.cols);
+    if (!lb.g.strips) return give(lb.lm[m].as<u8>() + (size_t)slot * lb.lm_stride, (size_t)8 * lb.g.rows * lb.g.cols);
+    // strip layout -> upstream's flat layout
+    const size_t flat = (size_t)8 * lb.g.rows * lb.g.cols, capb = *n_bytes;
+    *n_bytes = flat;
+    if (!dst || capb < flat) return LMB200_E_TRUNCATED;
+    std::vector<u8> tmp((size_t)8 * lb.g.per_label);
+    CU(cudaMemcpy(tmp.data(), lb.lm[m].as<u8>() + (size_t)slot * lb.lm_stride, tmp.size(), cudaMemcpyDeviceToHost));
+    const int W = lb.g.W, H = lb.g.H, TT = lb.g.T * lb.g.T;
+    u8* o = (u8*)dst;
+    for (int lp = 0; lp < 8 * TT; ++lp)  // (label, phase) planes
+      for (int gy = 0; gy < H; ++gy)
+        for (int gx = 0; gx < W; ++gx)
+          o[((size_t)lp * H + gy) * W + gx] = tmp[(size_t)lp * lb.g.plane + (size_t)(gx >> 4) * H * 16 + (size_t)gy * 16 + (gx & 15)];
+    return LMB200_OK;
   }
   if (kind == LMB200_DBG_COARSE || kind == LMB200_DBG_UNSORTED) {
     int rc = run_matching(h, slot, 1, h->slot_threshold[slot], st, kind == LMB200_DBG_COARSE);

@@ -75,9 +75,15 @@ struct SlotCtr {
   unsigned long long local_bytes;     // algorithmic bytes gathered by similarityLocal (sum nf*256)
 };
 
+// Linear-memory layouts.  Coarsest level (strips == 0): upstream's flat rows, LM[label][phase][y/T * W + x/T], which the
+// coarse kernel needs (its reads run across grid rows exactly like upstream's).  Finer levels (strips > 0) are only
+// read as 16x16 patches by similarityLocal and are stored in 16-column strips, LM[label][phase][strip][row][16]:
+// the 16 rows of a patch are 256 contiguous bytes per strip, so a patch touches 4-6 cache lines instead of 16.
 struct LevelGeom {
   int T, rows, cols, W, H;            // quantized image size; W=cols/T, H=rows/T
-  u32 per_label;                      // T*T*W*H
+  u32 per_label;                      // bytes per label in the stored layout: T*T*plane
+  int strips;                         // 0: flat layout; else ceil(W/16)
+  u32 plane;                          // bytes per (label, phase) plane: W*H (flat) or strips*H*16
 };
 
 // ------------------------------------------------------------------ frame side

@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restr
   const int rowb = wpr * 4;
   u8* lmf = lm + (size_t)blockIdx.z * lm_stride;
   const u32 per = g.per_label;
-  const u32 plane = (u32)W * g.H;
+  const u32 plane = g.plane;
+  const u32 H16 = (u32)g.H * 16u;
   const int quads = (cw + 3) >> 2;
   const bool vec = ((W & 3) == 0);
   for (int idx = tid; idx < T * T * quads; idx += 256) {
@@ -446,7 +447,8 @@ __global__ void __launch_bounds__(256) spread_linearize_kernel(const u8* __restr
       if (p < cw) e = tab[sb[gy * rowb + p * T + gx]];
       lo[j] = e.x; hi[j] = e.y;
     }
-    u32 dstoff = (u32)cell * plane + (u32)i * W + c0 + 4 * k;
+    const u32 col = (u32)(c0 + 4 * k);  // 4 consecutive columns never straddle a 16-column strip
+    const u32 dstoff = (u32)cell * plane + (g.strips ? (col >> 4) * H16 + (u32)i * 16u + (col & 15u) : (u32)i * W + col);
     if (vec && 4 * k + 3 < cw) {
       // transpose 4 positions x 8 orientations -> one u32 (4 positions) per orientation
       u32 t01 = __byte_perm(lo[0], lo[1], 0x5140), t23 = __byte_perm(lo[2], lo[3], 0x5140);

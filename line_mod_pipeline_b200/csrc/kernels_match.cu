@@ -20,6 +20,7 @@ namespace lmk {
 // four bucket sizes in hdr.bkt[m]; features upstream's similarity() would skip are dropped.
 // hdr.flags: bit0 local-safe  : similarityLocal can never skip a feature or leave its plane
 //            bit1 coarse-safe : every feature row + template_positions stays inside its label's block
+//            bit2 one-P       : template_positions is the same for every modality
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restrict__ feat, u32* __restrict__ offs,
                                                             TplHdr* __restrict__ hdr, int ntpl, int M, LevelGeom g, int coarsest) {
@@ -31,13 +32,14 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
   const u32 lt = (1u << lane) - 1u;
   bool local_safe = h.width[0] >= 0 && h.height[0] >= 0 && h.width[0] <= g.cols - 16 * T && h.height[0] <= g.rows - 16 * T;
   bool coarse_safe = true;
+  int pmin = 0x7FFFFFFF, pmax = -0x7FFFFFFF;
   for (int m = 0; m < M; ++m) {
-    u32 off2[2];
+    u32 off2[2], gx2[2];
     int key2[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int k = lane + 32 * j;
-      u32 off = OFF_INVALID;
+      u32 off = OFF_INVALID, gx0 = 0;
       if (k < (int)hdr[warp].nf[m]) {
         u32 f = feat[((size_t)warp * M + m) * FEAT_SLOTS + k];
         int x = f & 0x3FFF, y = (f >> 14) & 0x3FFF, label = (f >> 28) & 7;
@@ -45,6 +47,10 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
         if (valid) {
           u32 base = (u32)((y % T) * T + (x % T)) * plane + (u32)(y / T) * W + (u32)(x / T);
           off = (u32)label * g.per_label + base;
+          if (!coarsest) {  // strip layout: byte offset of (label, phase, row y/T) without the column part, and the column
+            off = (u32)label * g.per_label + (u32)((y % T) * T + (x % T)) * g.plane + (u32)(y / T) * 16u;
+            gx0 = (u32)(x / T);
+          }
           int wf = (hdr[warp].width[m] - 1) / T + 1, hf = (hdr[warp].height[m] - 1) / T + 1;
           long long P = (long long)(H - hf) * W + (W - wf) + 1;
           if (P > (long long)plane) P = plane;
@@ -52,15 +58,15 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
         }
         if (!(f >> 31) || x > h.width[0] || y > h.height[0]) local_safe = false;
       }
-      off2[j] = off;
-      key2[j] = off == OFF_INVALID ? 4 : (int)((off >> (coarsest ? 3 : 2)) & 3);
+      off2[j] = off; gx2[j] = gx0;
+      key2[j] = off == OFF_INVALID ? 4 : (coarsest ? (int)((off >> 3) & 3) : 0);
     }
     // counting sort by key (0..3 valid buckets, 4 = dropped)
     const int slots = coarsest ? COARSE_SLOTS : FEAT_SLOTS;
     u32 start = 0, packed = 0;
     u32 dst[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-    u32* o = offs + ((size_t)warp * M + m) * slots;
-    for (int s0 = lane; s0 < slots; s0 += 32) o[s0] = OFF_INVALID;
+    u32* o = offs + ((size_t)warp * M + m) * slots * (coarsest ? 1 : 2);  // finer levels: (offset, column) pairs
+    for (int s0 = lane; s0 < slots * (coarsest ? 1 : 2); s0 += 32) o[s0] = OFF_INVALID;
     __syncwarp();
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -77,18 +83,23 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
       packed |= cnt << (8 * w);
       start += cnt;
     }
-    if (dst[0] != 0xFFFFFFFFu) o[dst[0]] = off2[0];
-    if (dst[1] != 0xFFFFFFFFu) o[dst[1]] = off2[1];
-    if (lane == 0) {
-      hdr[warp].bkt[m] = packed;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (dst[j] != 0xFFFFFFFFu) {
+        if (coarsest) o[dst[j]] = off2[j];
+        else { o[2 * dst[j]] = off2[j]; o[2 * dst[j] + 1] = gx2[j]; }
+      }
+    {
       int wf = (hdr[warp].width[m] - 1) / T + 1, hf = (hdr[warp].height[m] - 1) / T + 1;
       int P = (H - hf) * W + (W - wf) + 1;
-      hdr[warp].P[m] = P > (int)plane ? (int)plane : P;
+      P = P > (int)plane ? (int)plane : P;
+      pmin = min(pmin, P); pmax = max(pmax, P);
+      if (lane == 0) { hdr[warp].bkt[m] = packed; hdr[warp].P[m] = P; }
     }
   }
   local_safe = __all_sync(0xffffffffu, local_safe);
   coarse_safe = __all_sync(0xffffffffu, coarse_safe);
-  if (lane == 0) hdr[warp].flags = (local_safe ? 1u : 0u) | (coarse_safe ? 2u : 0u);
+  if (lane == 0) hdr[warp].flags = (local_safe ? 1u : 0u) | (coarse_safe ? 2u : 0u) | (pmin == pmax ? 4u : 0u);
 }
 
 void launch_build_offsets(const u32* feat, u32* offs, TplHdr* hdr, int ntpl, int M, LevelGeom g, bool coarsest, cudaStream_t st) {
@@ -160,13 +171,14 @@ struct NibAcc {
     b[6] += n3 & 0x0F0F0F0Fu; b[7] += (n3 >> 4) & 0x0F0F0F0Fu;
     n0 = n1 = n2 = n3 = 0u;
   }
-  // zero the byte sums of positions >= rem (0 < rem < 32): b[2i+par] byte t <-> position 8i + 2t + par
-  __device__ __forceinline__ void mask_tail(int rem) {
+  __device__ __forceinline__ void mask_tail(int rem) { mask_tail8(b, rem); }
+  // zero the byte sums of positions >= rem (0 < rem < 32): v[2i+par] byte t <-> position 8i + 2t + par
+  static __device__ __forceinline__ void mask_tail8(u32* v, int rem) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       int nb = (rem - 8 * (w >> 1) - (w & 1) + 1) >> 1;  // valid bytes in this word
       u32 m = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - nb))));
-      b[w] &= m;
+      v[w] &= m;
     }
   }
 };
@@ -247,6 +259,13 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
   int nhit = 0;
   int Pmax = 0;
   for (int m = 0; m < cx.M; ++m) Pmax = max(Pmax, cx.P(m));
+  // All modalities of a cropped pyramid share one template_positions (plan flag bit2): the row tail is then cut once,
+  // on the totals, after the early exit (which may look at the uncut sums: it only errs towards continuing).
+#ifdef CW_NO_TAIL_ONCE
+#define tail_once false
+#else
+#define tail_once (!WIDE && (cx.hdr.flags & 4u))
+#endif
   const int offset = cx.T / 2 + (cx.T % 2 - 1);
   const float denom = (float)(4 * cx.nf_total);
   const u32 K = (u32)(0x7FFF - cx.raw_thr) * 0x00010001u;  // field + K sets bit 15 iff field > raw_thr
@@ -273,7 +292,7 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       accum_bucket<1, SAFE>(lmb, lst, n0, n1, rem, pos0, P, cx.per_label, acc);
       accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, rem, pos0, P, cx.per_label, acc);
       accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, rem, pos0, P, cx.per_label, acc);
-      if (SAFE && rem > 0 && rem < 32) acc.mask_tail(rem);  // at most one lane per modality: the row tail
+      if (SAFE && !tail_once && rem > 0 && rem < 32) acc.mask_tail(rem);  // at most one lane per modality: the row tail
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
         if (WIDE) {
@@ -303,6 +322,10 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       }
     }
     if (dead) continue;
+    if (SAFE && tail_once) {
+      const int rem = Pmax - pos0;
+      if (rem > 0 && rem < 32) NibAcc::mask_tail8(tot, rem);
+    }
     u32 any = 0;
     if (WIDE) {
 #pragma unroll
@@ -351,6 +374,8 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
   }
   return nhit;
 }
+
+#undef tail_once
 
 template <bool SAFE, bool WIDE>
 __device__ __forceinline__ void coarse_template(const MatchParams& mp, const CoarseCtx& cx, const u8* const* s_lm, u32* queue,
@@ -487,7 +512,7 @@ void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_str
 // Local refinement: one CTA (4 warps) per candidate, the template's features are split across the warps and the
 // four partial 16x16 maps are added through shared memory (a 4x shorter dependent-load chain per candidate:
 // small batches are latency-bound); lane = (row 0..15, half 0..1) owns 8 of the 16x16 sums.
-// Fast path (hdr.flags bit0): offsets are the plan offsets shifted by the candidate's patch origin.
+// Fast path (hdr.flags bit0): plan entries (strip-layout offset, column) shifted by the candidate's patch origin.
 // Slow path: upstream's per-feature bounds checks with guarded byte loads (malformed / oversized
 // templates — N4 in SURVEY.md — where upstream itself is undefined; semantics = oracle's).
 // ---------------------------------------------------------------------------------------------
@@ -498,7 +523,8 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
   const int n = min(mp.ctr[frame].cand_count, mp.cand_cap);
   const int T = lp.g.T, W = lp.g.W, M = mp.M;
   const int border = 8 * T, offset = T / 2 + (T % 2 - 1);
-  const u32 plane = (u32)W * lp.g.H;
+  const u32 plane = (u32)W * lp.g.H;   // upstream's flat plane (slow path semantics)
+  const u32 H16 = (u32)lp.g.H * 16u;
   Cand* cands = mp.cand + (size_t)frame * mp.cand_cap;
   const int rr = lane >> 1, hh = lane & 1;
   __shared__ const u8* s_lm[MAX_MOD];
@@ -509,6 +535,7 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
     s_lm[3] = lp.lm[3] + (size_t)frame * lp.lm_stride[3];
   }
   __shared__ uint4 s_part[4][32];
+  __shared__ uint2 s_ent[4][16];
   __syncthreads();
 
   for (int c = blockIdx.x; c < n; c += gridDim.x) {
@@ -529,32 +556,29 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       u32 a0 = 0, a1 = 0;
       const u8* lmb = s_lm[m];
       if (hdr.flags & 1u) {
-        // One aligned LDG.128 per lane: the lane pair (hh = 0,1) of a patch row loads the two 16 B chunks of
-        // the 32 B window that contains the row's 16 unaligned bytes, swaps the two words the partner
-        // needs (2 SHFL) and realigns its own 8 bytes with selects + two funnel shifts.  16 rows = 16 lines
-        // = 16 L1 wavefronts per feature, half of what two loads per lane cost.
-        const int shift = (cyT + rr) * W + cxT;
-        const u32* offp = lp.offs + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
+        // Strip layout: the lane's 8 bytes of patch row rr (columns g .. g+7, g = feature column + 8*hh) lie in the
+        // 16 B window of two 8 B-aligned chunks: chunk k8 = g >> 3 sits in strip k8 >> 1 at byte (k8 & 1) * 8 of
+        // row cyT + rr, the next chunk 8 B further or at the start of the next strip's row.  Two LDG.64, one
+        // word select and two funnel shifts realign them; a warp's load touches the 4-6 lines of the patch.
+        const u32 yrow = (u32)(cyT + rr) * 16u, xh = (u32)cxT + 8u * (u32)hh;
+        const uint2* offp = reinterpret_cast<const uint2*>(lp.offs) + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
         const int q = (nf + 3) >> 2, kb = warp * q, ke = min(nf, kb + q);  // this warp's quarter of the features (<= 16)
-        {
-          u32 myoff = (kb + lane < ke) ? __ldg(offp + kb + lane) : 0u;
-          const int kn = ke - kb;
+        const int kn = ke - kb;
+        __syncwarp();  // the previous modality's reads of s_ent are done
+        if (lane < kn) s_ent[warp][lane] = __ldg(offp + kb + lane);
+        __syncwarp();
 #pragma unroll 4
-          for (int kk = 0; kk < kn; ++kk) {
-            const u32 a = __shfl_sync(0xffffffffu, myoff, kk) + (u32)shift;
-            const uint4 c = __ldg(reinterpret_cast<const uint4*>(lmb + (a & ~15u)) + hh);
-            const u32 r0 = __shfl_xor_sync(0xffffffffu, hh ? c.x : c.z, 1);
-            const u32 r1 = __shfl_xor_sync(0xffffffffu, hh ? c.y : c.w, 1);
-            // this lane's byte stream (24 B) and the offset of its 8 bytes in it is (a & 15) for both halves
-            const u32 e0 = hh ? r0 : c.x, e1 = hh ? r1 : c.y, e2 = hh ? c.x : c.z, e3 = hh ? c.y : c.w;
-            const u32 e4 = hh ? c.z : r0, e5 = hh ? c.w : r1;
-            const bool s2 = (a & 8u) != 0, s1 = (a & 4u) != 0;
-            const u32 u0 = s2 ? e2 : e0, u1 = s2 ? e3 : e1, u2 = s2 ? e4 : e2, u3 = s2 ? e5 : e3;
-            const u32 v0 = s1 ? u1 : u0, v1 = s1 ? u2 : u1, v2 = s1 ? u3 : u2;
-            const u32 sh = (a & 3u) * 8u;
-            a0 += __funnelshift_r(v0, v1, sh);
-            a1 += __funnelshift_r(v1, v2, sh);
-          }
+        for (int kk = 0; kk < kn; ++kk) {
+          const uint2 e = s_ent[warp][kk];  // (byte offset of label/phase/row, column) of the feature: broadcast read
+          const u32 gcol = e.y + xh, k8 = gcol >> 3, odd = k8 & 1u;
+          const u8* p0 = lmb + (e.x + yrow + (k8 >> 1) * H16 + odd * 8u);
+          const uint2 lo = __ldg(reinterpret_cast<const uint2*>(p0));
+          const uint2 hi = __ldg(reinterpret_cast<const uint2*>(p0 + (odd ? H16 - 8u : 8u)));
+          const bool s1 = (gcol & 4u) != 0;
+          const u32 v0 = s1 ? lo.y : lo.x, v1 = s1 ? hi.x : lo.y, v2 = s1 ? hi.y : hi.x;
+          const u32 sh = (gcol & 3u) * 8u;
+          a0 += __funnelshift_r(v0, v1, sh);
+          a1 += __funnelshift_r(v1, v2, sh);
         }
       } else if (warp == 0) {
         const u32* fp = lp.feat + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
@@ -567,9 +591,14 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
           long long base = (long long)((fy % T) * T + (fx % T)) * plane + (long long)(fy / T) * W + fx / T;
           const u8* lml = lmb + (size_t)label * lp.g.per_label;
           long long rb = base + (long long)rr * W + hh * 8;
+          const long long flat_label = (long long)T * T * plane;  // upstream's flat index space of one label
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
-            u32 v = (rb + b < (long long)lp.g.per_label) ? (u32)lml[rb + b] : 0u;
+            u32 v = 0u;
+            if (rb + b < flat_label) {  // flat index -> (phase, row, column) -> strip layout
+              const u32 f = (u32)(rb + b), ph = f / plane, rem = f - ph * plane, gy = rem / (u32)W, gx = rem - gy * (u32)W;
+              v = (u32)lml[(size_t)ph * lp.g.plane + (gx >> 4) * H16 + gy * 16u + (gx & 15u)];
+            }
             if (b < 4) a0 += v << (8 * b); else a1 += v << (8 * (b - 4));
           }
         }
