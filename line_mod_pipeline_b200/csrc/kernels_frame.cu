@@ -21,42 +21,92 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// cv::pyrDown 5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum+128)>>8, dst = (rows/2, cols/2)
+// cv::pyrDown 5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum+128)>>8, dst = (rows/2, cols/2).
+// Separable on the interleaved byte stream (the horizontal taps of a channel are 3 bytes apart, so no
+// de-interleave is needed): a CTA stages the 19 source rows of an 8 x 64 output tile as 32-bit words,
+// sums them vertically two bytes per 32-bit lane (sums <= 16*255 fit 16 bits), then takes the five
+// horizontal taps from the 16-bit row.  The integer sum is the same in either order: bit-exact.
 // ---------------------------------------------------------------------------------------------
+constexpr int PD_TW = 64, PD_TH = 8;
+constexpr int PD_IR = 2 * PD_TH + 3;             // source rows per tile
+constexpr int PD_WORDS = (6 * PD_TW + 8 + 4 + 3) / 4;  // source words per row: bytes [6*x0 - 8, 6*x0 + 6*TW + 3]
+constexpr int PD_WP = PD_WORDS + 1;
+
 __global__ void __launch_bounds__(256) pyrdown_bgr_kernel(const u8* __restrict__ src, size_t src_stride,
                                                           u8* __restrict__ dst, size_t dst_stride,
                                                           int rows, int cols, int drows, int dcols) {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if (x >= dcols || y >= drows) return;
+  __shared__ u32 s_in[PD_IR][PD_WP];
+  __shared__ u32 s_v[PD_TH][2 * PD_WP];  // four 16-bit vertical sums per source word
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * PD_TW, y0 = blockIdx.y * PD_TH;
   const u8* s = src + (size_t)blockIdx.z * src_stride;
-  const int w[5] = {1, 4, 6, 4, 1};
-  int xs[5];
+  const int rowb = cols * 3;
+  const int gb0 = 6 * x0 - 8;  // source byte (within a row) of staged byte 0; negative in the first tile
+  const bool al_in = ((reinterpret_cast<size_t>(s) & 3) == 0) && ((rowb & 3) == 0);
+  for (int idx = tid; idx < PD_IR * PD_WORDS; idx += 256) {  // (a warp per row measured slower: 19 rows on 8 warps)
+    const int r = idx / PD_WORDS, w = idx - r * PD_WORDS;
+    const u8* rp = s + (size_t)reflect101(2 * y0 - 2 + r, rows) * rowb;
+    const int gb = gb0 + 4 * w;
+    u32 v = 0;
+    if (al_in && gb >= 0 && gb + 3 < rowb) {
+      v = *reinterpret_cast<const u32*>(rp + gb);
+    } else {  // words that touch the left/right border: reflect the pixel column byte by byte
 #pragma unroll
-  for (int j = 0; j < 5; ++j) xs[j] = reflect101(2 * x + j - 2, cols) * 3;
-  int acc0 = 0, acc1 = 0, acc2 = 0;
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const u8* row = s + (size_t)reflect101(2 * y + i - 2, rows) * cols * 3;
-    int r0 = 0, r1 = 0, r2 = 0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      r0 += w[j] * row[xs[j]];
-      r1 += w[j] * row[xs[j] + 1];
-      r2 += w[j] * row[xs[j] + 2];
+      for (int k = 0; k < 4; ++k) {
+        const int g = gb + k;
+        const int c = (g + 9) / 3 - 3, ch = g - 3 * c;  // floor division (g >= -8)
+        v |= (u32)rp[reflect101(c, cols) * 3 + ch] << (8 * k);
+      }
     }
-    acc0 += w[i] * r0; acc1 += w[i] * r1; acc2 += w[i] * r2;
+    s_in[r][w] = v;
   }
-  u8* d = dst + (size_t)blockIdx.z * dst_stride + ((size_t)y * dcols + x) * 3;
-  d[0] = (u8)((acc0 + 128) >> 8);
-  d[1] = (u8)((acc1 + 128) >> 8);
-  d[2] = (u8)((acc2 + 128) >> 8);
+  __syncthreads();
+  for (int idx = tid; idx < PD_TH * PD_WORDS; idx += 256) {
+    const int oy = idx / PD_WORDS, w = idx - oy * PD_WORDS;
+    const u32 v0 = s_in[2 * oy][w], v1 = s_in[2 * oy + 1][w], v2 = s_in[2 * oy + 2][w], v3 = s_in[2 * oy + 3][w],
+              v4 = s_in[2 * oy + 4][w];
+    const u32 m = 0x00FF00FFu;
+    const u32 e = (v0 & m) + (v4 & m) + 4u * ((v1 & m) + (v3 & m)) + 6u * (v2 & m);                              // bytes 0, 2
+    const u32 o = ((v0 >> 8) & m) + ((v4 >> 8) & m) + 4u * (((v1 >> 8) & m) + ((v3 >> 8) & m)) + 6u * ((v2 >> 8) & m);  // bytes 1, 3
+    s_v[oy][2 * w] = (e & 0xFFFFu) | (o << 16);
+    s_v[oy][2 * w + 1] = (e >> 16) | (o & 0xFFFF0000u);
+  }
+  __syncthreads();
+  const u16* sv = reinterpret_cast<const u16*>(&s_v[0][0]);
+  u8* d = dst + (size_t)blockIdx.z * dst_stride;
+  const int drowb = dcols * 3;
+  const bool al_out = ((reinterpret_cast<size_t>(d) & 3) == 0) && ((drowb & 3) == 0);
+  constexpr int QPR = PD_TW * 3 / 4;  // 4-byte output groups per tile row
+  for (int idx = tid; idx < PD_TH * QPR; idx += 256) {
+    const int oy = idx / QPR, q = idx - oy * QPR;
+    const int y = y0 + oy;
+    if (y >= drows) continue;
+    const u16* vr = sv + oy * (4 * PD_WP);
+    u32 pack = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ob = 4 * q + k, ox = ob / 3, ch = ob - 3 * ox;
+      const u16* vp = vr + 6 * ox + ch + 2;  // staged byte of source column 2*(x0+ox) - 2, channel ch
+      const int sum = (int)vp[0] + (int)vp[12] + 4 * ((int)vp[3] + (int)vp[9]) + 6 * (int)vp[6];
+      pack |= (u32)((sum + 128) >> 8) << (8 * k);
+    }
+    const int ob0 = x0 * 3 + 4 * q;  // first output byte of the group within the row
+    u8* o = d + (size_t)y * drowb + ob0;
+    if (al_out && ob0 + 3 < drowb) {
+      *reinterpret_cast<u32*>(o) = pack;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ob0 + k < drowb) o[k] = (u8)(pack >> (8 * k));
+    }
+  }
 }
 
 void launch_pyrdown_bgr(const u8* src, size_t src_stride, u8* dst, size_t dst_stride, int rows, int cols,
                         int frames, cudaStream_t st) {
   int drows = rows / 2, dcols = cols / 2;
-  dim3 grid((dcols + 31) / 32, (drows + 7) / 8, frames), block(32, 8);
-  pyrdown_bgr_kernel<<<grid, block, 0, st>>>(src, src_stride, dst, dst_stride, rows, cols, drows, dcols);
+  dim3 grid((dcols + PD_TW - 1) / PD_TW, (drows + PD_TH - 1) / PD_TH, frames);
+  pyrdown_bgr_kernel<<<grid, 256, 0, st>>>(src, src_stride, dst, dst_stride, rows, cols, drows, dcols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,10 +115,12 @@ void launch_pyrdown_bgr(const u8* src, size_t src_stride, u8* dst, size_t dst_st
 //   -> Sobel 3x3 on the blurred image (replicate border ON THE BLURRED IMAGE)
 //   -> channel with max dx^2+dy^2 (ties: B, then G) -> fastAtan2 degrees -> *16/360 round-half-even
 //   -> border zero, &7 -> 3x3 vote (>=5 of 9, first max), magnitude > weak^2 (strict).
-// Tile 64x16 output pixels, 256 threads, halo 5 (3 blur + 1 Sobel + 1 vote), planar smem staging.
+// Tile 64x16 output pixels, 256 threads, halo 5 (3 blur + 1 Sobel + 1 vote).  The blur runs on the interleaved byte
+// stream: vertical pass first on whole words (two bytes per 32-bit lane), then the horizontal taps 3 sums apart.
 // ---------------------------------------------------------------------------------------------
 constexpr int CG_TW = 64, CG_TH = 16;
-constexpr int CG_SR = CG_TH + 10, CG_SC = CG_TW + 10, CG_SCP = CG_SC + 2;  // source tile (halo 5)
+constexpr int CG_SR = CG_TH + 10, CG_SC = CG_TW + 10;                      // source tile (halo 5)
+constexpr int CG_SWU = (3 * CG_SC + 1 + 3) / 4, CG_SW = CG_SWU + 1;          // ... as words per row (used, padded)
 constexpr int CG_HC = CG_TW + 4, CG_BR = CG_TH + 4;                        // blurred region R2 (halo 2)
 constexpr int CG_QR = CG_TH + 2, CG_QC = CG_TW + 2, CG_QCP = CG_QC + 2;    // orientation region R1 (halo 1)
 
@@ -95,49 +147,70 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
                                                           u8* __restrict__ qout, size_t q_stride,
                                                           float* __restrict__ mag_out, size_t mag_stride,
                                                           int rows, int cols, float weak_sq) {
-  __shared__ u8 s_src[3][CG_SR][CG_SCP];
-  __shared__ u16 s_h[3][CG_SR][CG_HC];
+  __shared__ u32 s_srcw[CG_SR][CG_SW];  // interleaved BGR bytes of the source tile, staged as aligned words
+  __shared__ u32 s_vw[CG_BR][2 * CG_SW];  // vertical blur sums, one u16 per staged source byte
   __shared__ u8 s_b[3][CG_BR][CG_HC];
-  __shared__ u8 s_q[CG_QR][CG_QCP];
+  __shared__ u32 s_q[CG_QR][CG_QCP];  // orientation code as a vote: 1 << (4 * code)
   __shared__ int s_m[CG_QR][CG_QCP];
 
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * CG_TW, y0 = blockIdx.y * CG_TH;
   const u8* src = bgr + (size_t)blockIdx.z * bgr_stride;
 
-  // 1. source tile, replicate-clamped (the blur's border mode acts on the source)
-  for (int idx = tid; idx < CG_SR * CG_SC; idx += 256) {
-    int ty = idx / CG_SC, tx = idx - ty * CG_SC;
-    int gy = clampi(y0 - 5 + ty, 0, rows - 1), gx = clampi(x0 - 5 + tx, 0, cols - 1);
-    const u8* p = src + ((size_t)gy * cols + gx) * 3;
-    s_src[0][ty][tx] = p[0]; s_src[1][ty][tx] = p[1]; s_src[2][ty][tx] = p[2];
+  // 1. source tile, replicate-clamped (the blur's border mode acts on the source).  The interleaved bytes are
+  //    staged as they lie in memory: staged byte 0 = row byte 3*x0 - 16 (word aligned), so pixel tx (image column
+  //    x0 - 5 + tx) channel ch is staged byte 3*tx + ch + 1.  Words inside the row are one 32-bit load; words that
+  //    touch the left/right border are assembled byte by byte from the clamped pixel column.
+  const int rowb = cols * 3;
+  const bool al_in = ((reinterpret_cast<size_t>(src) & 3) == 0) && ((rowb & 3) == 0);
+  for (int ty = tid >> 5; ty < CG_SR; ty += 8) {  // a warp per source row
+    const u8* rp = src + (size_t)clampi(y0 - 5 + ty, 0, rows - 1) * rowb;
+    for (int w = tid & 31; w < CG_SWU; w += 32) {
+      const int gb = 3 * x0 - 16 + 4 * w;
+      u32 v = 0;
+      if (al_in && gb >= 0 && gb + 3 < rowb) {
+        v = *reinterpret_cast<const u32*>(rp + gb);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = gb + k;
+          const int c = (g + 18) / 3 - 6, ch = g - 3 * c;  // floor division (g >= -16)
+          v |= (u32)rp[clampi(c, 0, cols - 1) * 3 + ch] << (8 * k);
+        }
+      }
+      s_srcw[ty][w] = v;
+    }
   }
   __syncthreads();
+  const u8* s_srcb = reinterpret_cast<const u8*>(&s_srcw[0][0]);
 
-  // 2. horizontal blur sums at the CLAMPED centre column (so out-of-image R2 columns replicate the
-  //    blurred border column, which is what Sobel's BORDER_REPLICATE sees)
-  for (int idx = tid; idx < CG_SR * CG_HC; idx += 256) {
-    int ty = idx / CG_HC, tx2 = idx - ty * CG_HC;
-    int cx = clampi(x0 - 2 + tx2, 0, cols - 1);
-    int tc = cx - (x0 - 5);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const u8* r = &s_src[ch][ty][tc - 3];
-      int s = 8 * (r[0] + r[6]) + 28 * (r[1] + r[5]) + 56 * (r[2] + r[4]) + 72 * r[3];
-      s_h[ch][ty][tx2] = (u16)s;
+  // 2. vertical blur sums at the CLAMPED centre row (so out-of-image R2 rows replicate the blurred border row, which
+  //    is what Sobel's BORDER_REPLICATE sees).  Two bytes per 32-bit lane: a 16-bit lane holds at most 256*255.
+  for (int ty2 = tid >> 5; ty2 < CG_BR; ty2 += 8) {
+    const int tr = clampi(y0 - 2 + ty2, 0, rows - 1) - (y0 - 5);
+    for (int w = tid & 31; w < CG_SWU; w += 32) {
+      const u32 v0 = s_srcw[tr - 3][w], v1 = s_srcw[tr - 2][w], v2 = s_srcw[tr - 1][w], v3 = s_srcw[tr][w],
+                v4 = s_srcw[tr + 1][w], v5 = s_srcw[tr + 2][w], v6 = s_srcw[tr + 3][w];
+      const u32 m = 0x00FF00FFu;
+      const u32 e = 8u * ((v0 & m) + (v6 & m)) + 28u * ((v1 & m) + (v5 & m)) + 56u * ((v2 & m) + (v4 & m)) + 72u * (v3 & m);
+      const u32 o = 8u * (((v0 >> 8) & m) + ((v6 >> 8) & m)) + 28u * (((v1 >> 8) & m) + ((v5 >> 8) & m)) +
+                    56u * (((v2 >> 8) & m) + ((v4 >> 8) & m)) + 72u * ((v3 >> 8) & m);
+      s_vw[ty2][2 * w] = (e & 0xFFFFu) | (o << 16);          // staged bytes 4w, 4w+1
+      s_vw[ty2][2 * w + 1] = (e >> 16) | (o & 0xFFFF0000u);  // staged bytes 4w+2, 4w+3
     }
   }
   __syncthreads();
 
-  // 3. vertical pass at the clamped centre row -> blurred u8 on R2
+  // 3. horizontal pass at the clamped centre column -> blurred u8 on R2 (taps of one channel are 3 sums apart)
+  const u16* s_v = reinterpret_cast<const u16*>(&s_vw[0][0]);
   for (int idx = tid; idx < CG_BR * CG_HC; idx += 256) {
     int ty2 = idx / CG_HC, tx2 = idx - ty2 * CG_HC;
-    int cy = clampi(y0 - 2 + ty2, 0, rows - 1);
-    int tr = cy - (y0 - 5);
+    int cx = clampi(x0 - 2 + tx2, 0, cols - 1);
+    int tc = cx - (x0 - 5);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      int s = 8 * ((int)s_h[ch][tr - 3][tx2] + s_h[ch][tr + 3][tx2]) + 28 * ((int)s_h[ch][tr - 2][tx2] + s_h[ch][tr + 2][tx2]) +
-              56 * ((int)s_h[ch][tr - 1][tx2] + s_h[ch][tr + 1][tx2]) + 72 * (int)s_h[ch][tr][tx2];
+      const u16* r = s_v + ty2 * (4 * CG_SW) + 3 * (tc - 3) + ch + 1;
+      int s = 8 * ((int)r[0] + r[18]) + 28 * ((int)r[3] + r[15]) + 56 * ((int)r[6] + r[12]) + 72 * (int)r[9];
       s_b[ch][ty2][tx2] = (u8)((s + 32768) >> 16);
     }
   }
@@ -147,7 +220,7 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
   for (int idx = tid; idx < CG_QR * CG_QC; idx += 256) {
     int ty1 = idx / CG_QC, tx1 = idx - ty1 * CG_QC;
     int gy = y0 - 1 + ty1, gx = x0 - 1 + tx1;
-    u8 q = 0;
+    int q = 0;
     int mag = 0;
     if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
       int by = ty1 + 1, bx = tx1 + 1;  // R2 index of this pixel
@@ -167,10 +240,10 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
         float ang = fast_atan2_deg((float)best_dy, (float)best_dx);
         int r = __float2int_rn(__fmul_rn(ang, (float)(16.0 / 360.0)));
         r = r < 0 ? 0 : (r > 255 ? 255 : r);
-        q = (u8)(r & 7);
+        q = r & 7;
       }
     }
-    s_q[ty1][tx1] = q;
+    s_q[ty1][tx1] = 1u << (4 * q);
     s_m[ty1][tx1] = mag;
   }
   __syncthreads();
@@ -184,18 +257,15 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
     int mag = s_m[ty + 1][tx + 1];
     u8 out = 0;
     if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1 && (float)mag > weak_sq) {
-      u32 hist = 0;  // 8 x 4-bit counters
+      u32 hist = 0;  // 8 x 4-bit counters (9 votes)
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) hist += 1u << (4 * s_q[ty + i][tx + j]);
-      int max_votes = 0, index = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        int v = (hist >> (4 * b)) & 15;
-        if (max_votes < v) { max_votes = v; index = b; }
-      }
-      if (max_votes >= 5) out = (u8)(1u << index);
+        for (int j = 0; j < 3; ++j) hist += s_q[ty + i][tx + j];
+      // upstream takes the first bin with the most votes and accepts it with >= 5 of 9: at most one bin can
+      // have 5, so "first max" never matters — +3 carries every counter >= 5 into its bit 3.
+      const u32 five = (hist + 0x33333333u) & 0x88888888u;
+      if (five) out = (u8)(1u << ((__ffs((int)five) - 1) >> 2));
     }
     qo[(size_t)gy * cols + gx] = out;
     if (mag_out) mag_out[(size_t)blockIdx.z * mag_stride + (size_t)gy * cols + gx] = (float)mag;
