@@ -180,7 +180,7 @@ static int rebuild_templates(lmb200_detector* h) {
       }
     ALLOC(h->d_hdr[l], hdr.size() * sizeof(TplHdr));
     ALLOC(h->d_feat[l], feat.size() * sizeof(u32));
-    ALLOC(h->d_offs[l], (size_t)std::max(1, h->ntpl) * M * (l == L - 1 ? COARSE_SLOTS : 2 * FEAT_SLOTS) * sizeof(u32));
+    ALLOC(h->d_offs[l], (size_t)std::max(1, h->ntpl) * M * 2 * (l == L - 1 ? COARSE_SLOTS : FEAT_SLOTS) * sizeof(u32));  // (offset, shift | column) pairs
     CU(cudaMemcpy(h->d_hdr[l].p, hdr.data(), hdr.size() * sizeof(TplHdr), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_feat[l].p, feat.data(), feat.size() * sizeof(u32), cudaMemcpyHostToDevice));
   }

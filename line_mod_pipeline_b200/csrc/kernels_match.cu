@@ -65,8 +65,10 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
     const int slots = coarsest ? COARSE_SLOTS : FEAT_SLOTS;
     u32 start = 0, packed = 0;
     u32 dst[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-    u32* o = offs + ((size_t)warp * M + m) * slots * (coarsest ? 1 : 2);  // finer levels: (offset, column) pairs
-    for (int s0 = lane; s0 < slots * (coarsest ? 1 : 2); s0 += 32) o[s0] = OFF_INVALID;
+    // entries are pairs: coarsest level (16 B chunk byte offset in the nibble-packed LM, funnel shift in bits);
+    // finer levels (strip-layout byte offset without the column part, column)
+    u32* o = offs + ((size_t)warp * M + m) * slots * 2;
+    for (int s0 = lane; s0 < slots * 2; s0 += 32) o[s0] = OFF_INVALID;
     __syncwarp();
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
       u32 cnt = c0 + c1;
       if (coarsest) {  // pad to a multiple of 3 with rows of the zero tail that have this bucket's word shift
         u32 padded = (cnt + 2) / 3 * 3;
-        if (lane < (int)(padded - cnt)) o[start + cnt + lane] = 8u * g.per_label + 8u * (u32)w;
+        if (lane < (int)(padded - cnt)) { o[2 * (start + cnt + lane)] = 4u * g.per_label; o[2 * (start + cnt + lane) + 1] = 0u; }
         cnt = padded;
       }
       packed |= cnt << (8 * w);
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(128) build_offsets_kernel(const u32* __restric
 #pragma unroll
     for (int j = 0; j < 2; ++j)
       if (dst[j] != 0xFFFFFFFFu) {
-        if (coarsest) o[dst[j]] = off2[j];
+        if (coarsest) { o[2 * dst[j]] = (off2[j] >> 1) & ~15u; o[2 * dst[j] + 1] = (off2[j] & 7u) * 4u; }
         else { o[2 * dst[j]] = off2[j]; o[2 * dst[j] + 1] = gx2[j]; }
       }
     {
@@ -184,8 +186,7 @@ struct NibAcc {
 };
 
 template <int WS, bool MASK>
-__device__ __forceinline__ void realign_add(const uint4& A, const uint4& B, u32 off, int nv, NibAcc& acc) {
-  const u32 sh = (off & 7u) * 4u;
+__device__ __forceinline__ void realign_add(const uint4& A, const uint4& B, u32 sh, int nv, NibAcc& acc) {
   u32 w0, w1, w2, w3;
   if (WS == 0) {
     w0 = __funnelshift_r(A.x, A.y, sh); w1 = __funnelshift_r(A.y, A.z, sh);
@@ -208,25 +209,26 @@ __device__ __forceinline__ void realign_add(const uint4& A, const uint4& B, u32 
 // all loads first (6 x LDG.128 in flight per lane), then realign + one 3-input add per word (3*4 = 12 fits a
 // nibble), then the spill into byte sums.
 template <int WS, bool SAFE>
-__device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u32* __restrict__ lst, int k0, int n, int rem,
+__device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const uint2* __restrict__ lst, int k0, int n,
                                              int pos0, int P, u32 per_label, NibAcc& acc) {
   for (int k = k0; k < k0 + n; k += 3) {
-    u32 off[3];
+    uint2 e[3];  // (chunk byte offset, funnel shift) straight from the plan: no per-row address arithmetic
     uint4 A[3], B[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) off[j] = lst[k + j];
-    if (rem > 0) {
+    for (int j = 0; j < 3; ++j) e[j] = lst[k + j];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const uint4* p = reinterpret_cast<const uint4*>(lmb + ((off[j] >> 1) & ~15u));
-        A[j] = __ldg(p); B[j] = __ldg(p + 1);
-      }
+    for (int j = 0; j < 3; ++j) {
+      const uint4* p = reinterpret_cast<const uint4*>(lmb + e[j].x);
+      A[j] = __ldg(p); B[j] = __ldg(p + 1);
+    }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        int nv = 32;
-        if (!SAFE) nv = min(P, (int)(per_label - off[j] % per_label)) - pos0;  // positions past the label block contribute 0
-        if (SAFE || nv > 0) realign_add<WS, !SAFE>(A[j], B[j], off[j], nv, acc);
+    for (int j = 0; j < 3; ++j) {
+      int nv = 32;
+      if (!SAFE) {  // positions past the label block contribute 0
+        const u32 off = 2u * e[j].x + 8u * WS + (e[j].y >> 2);  // the row's nibble offset
+        nv = min(P, (int)(per_label - off % per_label)) - pos0;
       }
+      if (SAFE || nv > 0) realign_add<WS, !SAFE>(A[j], B[j], e[j].y, nv, acc);
     }
     acc.spill();
   }
@@ -234,7 +236,7 @@ __device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u
 
 struct CoarseCtx {
   HdrR hdr;
-  const u32* lst;                    // this warp's staged offsets [M][COARSE_SLOTS] (shared memory)
+  const uint2* lst;                  // this warp's staged plan rows [M][COARSE_SLOTS] (shared memory)
   int M, T, W, H, HW, raw_thr, nf_total;
   u32 per_label;
   const int* Pm;                     // plan: upstream's template_positions per modality
@@ -287,11 +289,13 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       const u8* lmb = s_lm[m] + (pos0 >> 1);
       const u32 bk = cx.hdr.bkt(m);
       const int n0 = bk & 255, n1 = (bk >> 8) & 255, n2 = (bk >> 16) & 255, n3 = bk >> 24;
-      const u32* lst = cx.lst + m * COARSE_SLOTS;
-      accum_bucket<0, SAFE>(lmb, lst, 0, n0, rem, pos0, P, cx.per_label, acc);
-      accum_bucket<1, SAFE>(lmb, lst, n0, n1, rem, pos0, P, cx.per_label, acc);
-      accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, rem, pos0, P, cx.per_label, acc);
-      accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, rem, pos0, P, cx.per_label, acc);
+      const uint2* lst = cx.lst + m * COARSE_SLOTS;
+      if (rem > 0) {  // lanes past template_positions sit the modality out (one branch, not one per group)
+        accum_bucket<0, SAFE>(lmb, lst, 0, n0, pos0, P, cx.per_label, acc);
+        accum_bucket<1, SAFE>(lmb, lst, n0, n1, pos0, P, cx.per_label, acc);
+        accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, pos0, P, cx.per_label, acc);
+        accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, pos0, P, cx.per_label, acc);
+      }
       if (SAFE && !tail_once && rem > 0 && rem < 32) acc.mask_tail(rem);  // at most one lane per modality: the row tail
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kern
   __shared__ const u8* s_lm[MAX_MOD];
   __shared__ int s_ord[MAX_MOD];
   __shared__ u32 s_queue[CW_WARPS][CW_QCAP];
-  __shared__ u32 s_off[CW_WARPS][MAX_MOD * COARSE_SLOTS];
+  __shared__ uint2 s_off[CW_WARPS][MAX_MOD * COARSE_SLOTS];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {  // lp.lm = nibble-packed linear memories of the coarsest level
@@ -453,7 +457,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kern
     cx.Pm = lp.hdr[g].P;
     cx.ord = s_ord;
     __syncwarp();  // the previous template's reads of s_off / s_queue are done
-    for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32) s_off[warp][s] = __ldg(lp.offs + (size_t)g * cx.M * COARSE_SLOTS + s);
+    for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32)
+      s_off[warp][s] = __ldg(reinterpret_cast<const uint2*>(lp.offs) + (size_t)g * cx.M * COARSE_SLOTS + s);
     __syncwarp();
     if (cx.hdr.flags & 2u) coarse_template<true, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
     else coarse_template<false, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
