@@ -78,6 +78,7 @@ struct BatchTicket {
   lmk::SlotCtr* b_ctr = nullptr; lmk::Cand* b_out = nullptr;
   int cap_frames = 0, head = 0, head_used = 0;
   long long generation = 0;               // buffer_generation at enqueue time
+  bool streaming = false;                 // submitted through submit/collect (throughput) rather than the blocking call
 };
 
 }  // namespace lmh
@@ -136,6 +137,7 @@ struct lmb200_detector {
   lmh::BatchTicket tickets[2];
   std::vector<cudaEvent_t> group_done; std::vector<char> group_used; int b_groups = 0;
   long long chunk_seq = 0, buffer_generation = 0;
+  bool blocking_submit = false;           // lmb200_match_batch is running its own submit
   lmh::ResidentMark resident_marks[4]; unsigned resident_next = 0;
 
   // profiling
