@@ -123,6 +123,8 @@ constexpr int CG_SR = CG_TH + 10, CG_SC = CG_TW + 10;                      // so
 constexpr int CG_SWU = (3 * CG_SC + 1 + 3) / 4, CG_SW = CG_SWU + 1;          // ... as words per row (used, padded)
 constexpr int CG_HC = CG_TW + 4, CG_BR = CG_TH + 4;                        // blurred region R2 (halo 2)
 constexpr int CG_QR = CG_TH + 2, CG_QC = CG_TW + 2, CG_QCP = CG_QC + 2;    // orientation region R1 (halo 1)
+constexpr int CG_BW = CG_HC / 4 + 1, CG_QG = (CG_QC + 3) / 4;              // blurred row in words (+1 spare), R1 pixel quads per row
+static_assert(CG_HC % 4 == 0, "blurred rows are read as words");
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   // OpenCV hal::fastAtan32f, fused polynomial (bit-exact with the cv2 wheel)
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
                                                           int rows, int cols, float weak_sq) {
   __shared__ u32 s_srcw[CG_SR][CG_SW];  // interleaved BGR bytes of the source tile, staged as aligned words
   __shared__ u32 s_vw[CG_BR][2 * CG_SW];  // vertical blur sums, one u16 per staged source byte
-  __shared__ u8 s_b[3][CG_BR][CG_HC];
+  __shared__ u32 s_bw[3][CG_BR][CG_BW];  // blurred planes, 4 pixels per word (CG_HC = 68 columns + one spare word)
   __shared__ u32 s_q[CG_QR][CG_QCP];  // orientation code as a vote: 1 << (4 * code)
   __shared__ int s_m[CG_QR][CG_QCP];
 
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
 
   // 3. horizontal pass at the clamped centre column -> blurred u8 on R2 (taps of one channel are 3 sums apart)
   const u16* s_v = reinterpret_cast<const u16*>(&s_vw[0][0]);
+  u8* s_bb = reinterpret_cast<u8*>(&s_bw[0][0][0]);
   for (int idx = tid; idx < CG_BR * CG_HC; idx += 256) {
     int ty2 = idx / CG_HC, tx2 = idx - ty2 * CG_HC;
     int cx = clampi(x0 - 2 + tx2, 0, cols - 1);
@@ -211,40 +214,61 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
     for (int ch = 0; ch < 3; ++ch) {
       const u16* r = s_v + ty2 * (4 * CG_SW) + 3 * (tc - 3) + ch + 1;
       int s = 8 * ((int)r[0] + r[18]) + 28 * ((int)r[3] + r[15]) + 56 * ((int)r[6] + r[12]) + 72 * (int)r[9];
-      s_b[ch][ty2][tx2] = (u8)((s + 32768) >> 16);
+      s_bb[(ch * CG_BR + ty2) * (4 * CG_BW) + tx2] = (u8)((s + 32768) >> 16);
     }
   }
   __syncthreads();
 
-  // 4. Sobel + channel select + orientation code on R1
-  for (int idx = tid; idx < CG_QR * CG_QC; idx += 256) {
-    int ty1 = idx / CG_QC, tx1 = idx - ty1 * CG_QC;
-    int gy = y0 - 1 + ty1, gx = x0 - 1 + tx1;
-    int q = 0;
-    int mag = 0;
-    if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-      int by = ty1 + 1, bx = tx1 + 1;  // R2 index of this pixel
-      int best_dx = 0, best_dy = 0, best_m = -1;
+  // 4. Sobel + channel select + orientation code on R1, four pixels per thread.  The 3x3 Sobel sums of four
+  //    neighbouring pixels are formed two per 32-bit word (16-bit lanes, biased by 1024 so a lane never borrows):
+  //    E/O = even/odd columns of the word, X = the two columns after it.
+  for (int idx = tid; idx < CG_QR * CG_QG; idx += 256) {
+    const int ty1 = idx / CG_QG, k = idx - ty1 * CG_QG;
+    const int gy = y0 - 1 + ty1;
+    int bdx[4], bdy[4], bm[4] = {-1, -1, -1, -1};
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        int a00 = s_b[ch][by - 1][bx - 1], a01 = s_b[ch][by - 1][bx], a02 = s_b[ch][by - 1][bx + 1];
-        int a10 = s_b[ch][by][bx - 1], a12 = s_b[ch][by][bx + 1];
-        int a20 = s_b[ch][by + 1][bx - 1], a21 = s_b[ch][by + 1][bx], a22 = s_b[ch][by + 1][bx + 1];
-        int dx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
-        int dy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
-        int m = dx * dx + dy * dy;
-        if (m > best_m) { best_m = m; best_dx = dx; best_dy = dy; }  // strict >: earlier channel wins ties (B, G, R)
-      }
-      mag = best_m;
-      if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1) {
-        float ang = fast_atan2_deg((float)best_dy, (float)best_dx);
-        int r = __float2int_rn(__fmul_rn(ang, (float)(16.0 / 360.0)));
-        r = r < 0 ? 0 : (r > 255 ? 255 : r);
-        q = r & 7;
+    for (int ch = 0; ch < 3; ++ch) {
+      const u32* r0 = &s_bw[ch][ty1][k];  // R2 rows ty1, ty1+1, ty1+2 = image rows gy-1, gy, gy+1; word k = R2 columns 4k..4k+3
+      const u32 a0 = r0[0], b0 = r0[1], a1 = r0[CG_BW], b1 = r0[CG_BW + 1], a2 = r0[2 * CG_BW], b2 = r0[2 * CG_BW + 1];
+      const u32 m = 0x00FF00FFu;
+      const u32 E0 = a0 & m, O0 = (a0 >> 8) & m, X0 = __byte_perm(b0, 0u, 0x4140);
+      const u32 E1 = a1 & m, O1 = (a1 >> 8) & m, X1 = __byte_perm(b1, 0u, 0x4140);
+      const u32 E2 = a2 & m, O2 = (a2 >> 8) & m, X2 = __byte_perm(b2, 0u, 0x4140);
+      // dx: vertical [1 2 1] per column, then right column - left column
+      const u32 VE = E0 + 2u * E1 + E2, VO = O0 + 2u * O1 + O2, VX = X0 + 2u * X1 + X2;  // columns (4k,4k+2) (4k+1,4k+3) (4k+4,4k+5)
+      const u32 VE2 = (VE >> 16) | (VX << 16);          // columns (4k+2, 4k+4)
+      const u32 VO2 = (VO >> 16) | (VX & 0xFFFF0000u);  // columns (4k+3, 4k+5)
+      const u32 dxE = VE2 + 0x04000400u - VE, dxO = VO2 + 0x04000400u - VO;  // pixels (0,2) and (1,3), + 1024
+      // dy: bottom row - top row per column (+256), then horizontal [1 2 1] (+1024)
+      const u32 TE = E2 + 0x01000100u - E0, TO = O2 + 0x01000100u - O0, TX = X2 + 0x01000100u - X0;
+      const u32 TE2 = (TE >> 16) | (TX << 16), TO2 = (TO >> 16) | (TX & 0xFFFF0000u);
+      const u32 dyE = TE + 2u * TO + TE2, dyO = TO + 2u * TE2 + TO2;
+      const int dx[4] = {(int)(dxE & 0xFFFFu) - 1024, (int)(dxO & 0xFFFFu) - 1024, (int)(dxE >> 16) - 1024, (int)(dxO >> 16) - 1024};
+      const int dy[4] = {(int)(dyE & 0xFFFFu) - 1024, (int)(dyO & 0xFFFFu) - 1024, (int)(dyE >> 16) - 1024, (int)(dyO >> 16) - 1024};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int mm = dx[p] * dx[p] + dy[p] * dy[p];
+        if (mm > bm[p]) { bm[p] = mm; bdx[p] = dx[p]; bdy[p] = dy[p]; }  // strict >: earlier channel wins ties (B, G, R)
       }
     }
-    s_q[ty1][tx1] = 1u << (4 * q);
-    s_m[ty1][tx1] = mag;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int tx1 = 4 * k + p;
+      if (tx1 >= CG_QC) break;
+      const int gx = x0 - 1 + tx1;
+      int q = 0, mag = 0;
+      if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+        mag = bm[p];
+        if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1) {
+          float ang = fast_atan2_deg((float)bdy[p], (float)bdx[p]);
+          int r = __float2int_rn(__fmul_rn(ang, (float)(16.0 / 360.0)));
+          r = r < 0 ? 0 : (r > 255 ? 255 : r);
+          q = r & 7;
+        }
+      }
+      s_q[ty1][tx1] = 1u << (4 * q);
+      s_m[ty1][tx1] = mag;
+    }
   }
   __syncthreads();
 
