@@ -418,7 +418,9 @@ def main():
     roofline = {"kernel": "similarity_coarse_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4) if peak else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels.get(dom, {}).get("alg_bytes_per_launch"),
-                "note": "linear memories are L2-resident: the gather is bounded by L2, HBM copy bandwidth is the reported denominator"}
+                "note": "achieved = algorithmic bytes (sum nf*P, SURVEY 8d) / kernel time. The linear memories are L2-resident (the "
+                        "gather is bounded by L2; HBM copy bandwidth is the reported denominator), and the kernel's exact early exit "
+                        "(a pass ends once no position can still exceed the threshold) skips part of the algorithmic reads"}
     sim_ms = prof["ms"]["sim_coarse"] + prof["ms"]["sim_local"]
     sim_gbps = (prof["bytes_coarse"] + prof["bytes_local"]) / (sim_ms * 1e-3) / 1e9 if sim_ms > 0 else None
 
