@@ -169,7 +169,7 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
                  lmb200_image* quantized_out, const lmb200_image* masks);
 
 /* Streams n_frames frames (frames[f*n_sources + m]) through the same path: chunked H2D copies,
- * kernels and D2H of the match lists overlap on two CUDA streams.  Per-frame results are written
+ * kernels and D2H of the match lists overlap on one copy and three compute streams.  Per-frame results are written
  * at out[offsets[f] .. offsets[f+1]) (offsets has n_frames+1 entries).  Use pinned host memory
  * (lmb200_host_alloc) for the frames to get asynchronous copies. */
 int lmb200_match_batch(lmb200_handle h, const lmb200_image* frames, int n_frames, int n_sources, float threshold,
