@@ -125,6 +125,15 @@ int lmb200_add_templates(lmb200_handle h, const char* class_id, int n_views, con
 int lmb200_add_synthetic_template(lmb200_handle h, const char* class_id, const lmb200_template* templates,
                                   int n, int* template_id);
 int lmb200_clear_templates(lmb200_handle h);
+/* Names of SURVEY.md 8b for the same entry points: lmb200_add_template_images == lmb200_add_template,
+ * lmb200_add_template_pyramid == lmb200_add_synthetic_template.  lmb200_upload_templates packs the template set and
+ * copies it to the device now (tables + plan for the last frame size) instead of at the next match; optional, the
+ * match calls do it whenever the set has changed. */
+int lmb200_add_template_images(lmb200_handle h, const char* class_id, const lmb200_image* sources, int n_sources,
+                               const lmb200_image* object_mask /* nullable */, int* bb4, int* template_id);
+int lmb200_add_template_pyramid(lmb200_handle h, const char* class_id, const lmb200_template* templates, int n,
+                                int* template_id);
+int lmb200_upload_templates(lmb200_handle h);
 
 /* ---- persistence (OpenCV FileStorage YAML 1.0, optional .gz) ------------------------ */
 /* lmb200_write: what HighLevelLineMOD::writeLinemod puts in linemod_templates.yml.gz

@@ -69,6 +69,9 @@ SIGNATURES = {
     "lmb200_num_templates": (C.c_int, [_H, C.c_char_p]),
     "lmb200_get_template": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_int, _P(Template)]),
     "lmb200_add_template": (C.c_int, [_H, C.c_char_p, _P(Image), C.c_int, _P(Image), _P(C.c_int), _P(C.c_int)]),
+    "lmb200_add_template_images": (C.c_int, [_H, C.c_char_p, _P(Image), C.c_int, _P(Image), _P(C.c_int), _P(C.c_int)]),
+    "lmb200_add_template_pyramid": (C.c_int, [_H, C.c_char_p, _P(Template), C.c_int, _P(C.c_int)]),
+    "lmb200_upload_templates": (C.c_int, [_H]),
     "lmb200_add_templates": (C.c_int, [_H, C.c_char_p, C.c_int, _P(Image), C.c_int, _P(Image), _P(C.c_int), _P(C.c_int)]),
     "lmb200_add_synthetic_template": (C.c_int, [_H, C.c_char_p, _P(Template), C.c_int, _P(C.c_int)]),
     "lmb200_clear_templates": (C.c_int, [_H]),

@@ -120,7 +120,6 @@ void lmb200_destroy(lmb200_handle h) {
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < LMB200_LANES; ++i) {
-      if (h->lanes[i].done) cudaEventDestroy(h->lanes[i].done);
       if (h->lanes[i].stream) cudaStreamDestroy(h->lanes[i].stream);
     }
   }
@@ -172,6 +171,20 @@ int lmb200_add_template(lmb200_handle h, const char* class_id, const lmb200_imag
                         const lmb200_image* object_mask, int* bb4, int* template_id) {
   if (!h || !class_id || !sources || !template_id) return LMB200_E_INVALID;
   return add_template_gpu(h, class_id, sources, n_sources, object_mask, bb4, template_id);
+}
+
+int lmb200_add_template_images(lmb200_handle h, const char* class_id, const lmb200_image* sources, int n_sources,
+                               const lmb200_image* object_mask, int* bb4, int* template_id) {
+  return lmb200_add_template(h, class_id, sources, n_sources, object_mask, bb4, template_id);
+}
+
+int lmb200_add_template_pyramid(lmb200_handle h, const char* class_id, const lmb200_template* templates, int n, int* template_id) {
+  return lmb200_add_synthetic_template(h, class_id, templates, n, template_id);
+}
+
+int lmb200_upload_templates(lmb200_handle h) {
+  if (!h) return LMB200_E_INVALID;
+  return upload_templates_now(h);
 }
 
 int lmb200_add_templates(lmb200_handle h, const char* class_id, int n_views, const lmb200_image* sources, int n_sources,

@@ -78,7 +78,6 @@ int ensure_device(lmb200_detector* h) {
   h->device = dev;
   for (int i = 0; i < LMB200_LANES; ++i) {
     CU(cudaStreamCreateWithFlags(&h->lanes[i].stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&h->lanes[i].done, cudaEventDisableTiming));
   }
   h->device_ready = true;
   return LMB200_OK;
@@ -213,6 +212,16 @@ static int alloc_match_buffers(lmb200_detector* h) {
   CU(cudaHostAlloc((void**)&h->h_out, (size_t)S * h->out_cap * sizeof(Cand), cudaHostAllocDefault));
   h->slot_threshold.assign(S, 0.f);
   return LMB200_OK;
+}
+
+static int ensure_plan(lmb200_detector* h, int rows, int cols);
+
+// lmb200_upload_templates: device tables now; the plan too when a frame size is already known
+int upload_templates_now(lmb200_detector* h) {
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  if (h->rows > 0 && h->cols > 0) return ensure_plan(h, h->rows, h->cols);
+  return rebuild_templates(h);
 }
 
 // Frame plan: per-level geometry + every per-slot device buffer.  Re-planned when the frame size changes.

@@ -59,7 +59,6 @@ struct LevelBuffers {
 
 struct Lane {
   cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
 };
 
 struct ProfRec { int family; cudaEvent_t a, b; };
@@ -131,7 +130,6 @@ struct lmb200_detector {
   // pinned host mirrors
   lmk::SlotCtr* h_ctr = nullptr;
   lmk::Cand* h_out = nullptr; int h_head = 0;      // first h_head records of every slot
-  void* h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for pageable/strided inputs
   std::vector<float> slot_threshold;
   // batches in flight (lmb200_match_batch_submit / _collect)
   lmh::BatchTicket tickets[2];
@@ -160,6 +158,7 @@ namespace lmh {
 // detector.cu
 int ensure_device(lmb200_detector* h);
 int set_error(lmb200_detector* h, int code, const std::string& msg);
+int upload_templates_now(lmb200_detector* h);
 int add_template_gpu(lmb200_detector* h, const char* class_id, const lmb200_image* sources, int n_sources,
                      const lmb200_image* object_mask, int* bb4, int* template_id);
 int add_templates_bulk(lmb200_detector* h, const char* class_id, int n, const lmb200_image* sources, int n_sources,

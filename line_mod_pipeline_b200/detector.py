@@ -179,6 +179,10 @@ class Detector:
         self._check(self._L.lmb200_add_synthetic_template(self._h, class_id.encode(), arr, len(templates), C.byref(tid)))
         return tid.value
 
+    def uploadTemplates(self):
+        """Pack the template set and copy it to the device now (the match calls do it on demand otherwise)."""
+        self._check(self._L.lmb200_upload_templates(self._h))
+
     def clearTemplates(self):
         self._check(self._L.lmb200_clear_templates(self._h))
 

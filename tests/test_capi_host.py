@@ -82,7 +82,9 @@ def test_compute_fails_loudly_without_gpu():
     bgr, depth = synth.make_frame(0, 96, 160, n_shapes=4)
     for call in (lambda: d.match([bgr, depth], 80.0),
                  lambda: d.addTemplate([bgr, depth], "x", None),
+                 lambda: d.addTemplates([[bgr, depth], [bgr, depth]], "x", [None, None]),
                  lambda: d.uploadFrames([[bgr, depth]]),
+                 lambda: d.uploadTemplates(),
                  lambda: d.matchBatch([[bgr, depth]], 80.0)):
         with pytest.raises(lm.LinemodError) as e:
             call()

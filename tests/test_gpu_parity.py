@@ -453,3 +453,17 @@ def test_three_modalities():
     frames = [[f[0], f[1], np.ascontiguousarray(f[0][:, ::-1])] for f in (synth.make_frame(i) for i in range(9, 14))]
     for i, b in enumerate(det.matchBatch(frames, 60.0)):
         assert_same_matches(b, ora.match(frames[i], 60.0, threads=8).matches(0), "3-modality batch frame %d" % i)
+
+
+def test_upload_templates_eagerly():
+    """lmb200_upload_templates before the first match and again after the set changed: same matches as the
+    on-demand upload, i.e. as the oracle."""
+    bgr, depth = synth.make_frame(3)
+    det, ora = make_pair()
+    add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(3)[:10])
+    add_random(det, ora, 60)
+    det.uploadTemplates()                                   # no frame size known yet: tables only
+    assert_same_matches(det.match([bgr, depth], 70.0), ora.match([bgr, depth], 70.0).matches(0), "eager upload")
+    add_random(det, ora, 40, class_id="more", seed=5)
+    det.uploadTemplates()                                   # frame size known: tables + plan
+    assert_same_matches(det.match([bgr, depth], 70.0), ora.match([bgr, depth], 70.0).matches(0), "eager upload after change")
