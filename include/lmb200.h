@@ -145,6 +145,12 @@ int lmb200_read(const char* path, int device, lmb200_handle* out);
 /* Detector::writeClasses / readClasses with format("templates_%s.yml.gz", class_id). */
 int lmb200_write_classes(lmb200_handle h, const char* format);
 int lmb200_read_classes(lmb200_handle h, const char* const* class_ids, int n, const char* format);
+/* Detector::writeClass(class_id, fs) / readClass(fn, class_id_override) on a file of their own: one
+ * {class_id, modalities, pyramid_levels, template_pyramids} map at the root.  readClass checks modality names and
+ * pyramid_levels against the detector and refuses a class that is already present (upstream CV_Asserts); with a
+ * non-empty override the entry is inserted under that name (an existing entry wins, like std::map::insert). */
+int lmb200_write_class(lmb200_handle h, const char* class_id, const char* path);
+int lmb200_read_class(lmb200_handle h, const char* path, const char* class_id_override /* nullable */);
 
 /* Fast binary cache of the whole detector (config + every template pyramid, 5 bytes per feature): parsing the
  * YAML of a 20 000-template set takes seconds, the cache loads in milliseconds.  Not an interchange format. */

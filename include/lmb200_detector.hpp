@@ -207,6 +207,11 @@ class Detector {
     if (rc) throw Error(rc, lmb200_last_error(nullptr));
     return std::unique_ptr<Detector>(new Detector(h));
   }
+  // Detector::writeClass / readClass (upstream takes a FileStorage / FileNode; here the class has a file of its own)
+  void writeClass(const std::string& class_id, const std::string& path) const { check(lmb200_write_class(h_, class_id.c_str(), path.c_str())); }
+  void readClass(const std::string& path, const std::string& class_id_override = "") {
+    check(lmb200_read_class(h_, path.c_str(), class_id_override.empty() ? nullptr : class_id_override.c_str()));
+  }
   void writeClasses(const std::string& format = "templates_%s.yml.gz") const { check(lmb200_write_classes(h_, format.c_str())); }
   void readClasses(const std::vector<std::string>& class_ids, const std::string& format = "templates_%s.yml.gz") {
     std::vector<const char*> ids;

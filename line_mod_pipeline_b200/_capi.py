@@ -77,6 +77,8 @@ SIGNATURES = {
     "lmb200_clear_templates": (C.c_int, [_H]),
     "lmb200_write": (C.c_int, [_H, C.c_char_p]),
     "lmb200_read": (C.c_int, [C.c_char_p, C.c_int, _P(_H)]),
+    "lmb200_write_class": (C.c_int, [_H, C.c_char_p, C.c_char_p]),
+    "lmb200_read_class": (C.c_int, [_H, C.c_char_p, C.c_char_p]),
     "lmb200_write_classes": (C.c_int, [_H, C.c_char_p]),
     "lmb200_read_classes": (C.c_int, [_H, _P(C.c_char_p), C.c_int, C.c_char_p]),
     "lmb200_write_cache": (C.c_int, [_H, C.c_char_p]),

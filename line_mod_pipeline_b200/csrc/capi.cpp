@@ -232,6 +232,16 @@ int lmb200_read(const char* path, int device, lmb200_handle* out) {
   if (rc) g_create_error = err;
   return rc;
 }
+int lmb200_write_class(lmb200_handle h, const char* class_id, const char* path) {
+  if (!h || !class_id || !path) return LMB200_E_INVALID;
+  return write_class_file(h, class_id, path);
+}
+int lmb200_read_class(lmb200_handle h, const char* path, const char* class_id_override) {
+  if (!h || !path) return LMB200_E_INVALID;
+  std::string err;
+  int rc = read_class_file(h, path, err, class_id_override);
+  return rc ? set_error(h, rc, err) : LMB200_OK;
+}
 int lmb200_write_classes(lmb200_handle h, const char* format) {
   if (!h) return LMB200_E_INVALID;
   const char* fmt = format ? format : "templates_%s.yml.gz";

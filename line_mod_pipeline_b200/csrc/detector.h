@@ -175,7 +175,7 @@ void resize_nn_host(const uint8_t* src, int rows, int cols, uint8_t* dst, int dr
 int write_detector_file(lmb200_detector* h, const char* path);
 int read_detector_file(const char* path, int device, lmb200_handle* out, std::string& err);
 int write_class_file(lmb200_detector* h, const std::string& class_id, const char* path);
-int read_class_file(lmb200_detector* h, const char* path, std::string& err);
+int read_class_file(lmb200_detector* h, const char* path, std::string& err, const char* override_id = nullptr);
 int write_cache_file(lmb200_detector* h, const char* path);
 int read_cache_file(const char* path, int device, lmb200_handle* out, std::string& err);
 void set_create_error(const std::string& msg);

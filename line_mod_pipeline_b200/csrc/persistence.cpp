@@ -365,13 +365,13 @@ int read_detector_file(const char* path, int device, lmb200_handle* out, std::st
   return LMB200_OK;
 }
 
-int read_class_file(lmb200_detector* h, const char* path, std::string& err) {
+int read_class_file(lmb200_detector* h, const char* path, std::string& err, const char* override_id) {
   ParseState S;
   int rc = parse_file(path, S, err);
   if (rc) return rc;
   if (S.classes.empty()) { err = std::string(path) + ": no class found"; return LMB200_E_IO; }
   for (auto& c : S.classes) {
-    rc = add_parsed_class(h, c, nullptr, err);
+    rc = add_parsed_class(h, c, override_id, err);
     if (rc) return rc;
   }
   return LMB200_OK;

@@ -211,6 +211,12 @@ class Detector:
             raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode())
         return cls(_handle=h)
 
+    def writeClass(self, class_id, path):
+        self._check(self._L.lmb200_write_class(self._h, class_id.encode(), str(path).encode()))
+
+    def readClass(self, path, class_id_override=""):
+        self._check(self._L.lmb200_read_class(self._h, str(path).encode(), class_id_override.encode() if class_id_override else None))
+
     def writeClasses(self, fmt="templates_%s.yml.gz"):
         self._check(self._L.lmb200_write_classes(self._h, fmt.encode()))
 

@@ -137,6 +137,36 @@ def test_write_read_classes(tmp_path):
     assert err.value.code == K.E_IO
 
 
+def test_write_read_single_class(tmp_path):
+    """Detector::writeClass / readClass(fn, class_id_override): one class per file, override semantics of upstream."""
+    d = lm.getDefaultLINEMOD()
+    _fill(d)
+    path = str(tmp_path / "one_class.yml")
+    d.writeClass("other obj", path)
+    e = lm.getDefaultLINEMOD()
+    e.readClass(path)
+    assert e.classIds() == ["other obj"] and e.numTemplates() == d.numTemplates("other obj")
+    for t in range(e.numTemplates("other obj")):
+        for a, b in zip(e.getTemplates("other obj", t), d.getTemplates("other obj", t)):
+            assert (a["width"], a["height"], a["pyramid_level"]) == (b["width"], b["height"], b["pyramid_level"])
+            assert np.array_equal(a["features"], b["features"])
+    with pytest.raises(lm.LinemodError) as err:      # upstream: CV_Assert(class not already present)
+        e.readClass(path)
+    assert err.value.code == K.E_CLASS
+    e.readClass(path, "renamed")                     # override: stored under the new name
+    assert e.classIds() == ["other obj", "renamed"] and e.numTemplates("renamed") == e.numTemplates("other obj")
+    n = e.numTemplates()
+    e.readClass(path, "renamed")                     # override onto an existing entry: std::map::insert keeps the old one
+    assert e.numTemplates() == n
+    with pytest.raises(lm.LinemodError) as err:
+        d.writeClass("no such class", path)
+    assert err.value.code == K.E_CLASS
+    cv2 = pytest.importorskip("cv2")
+    f = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)  # real OpenCV parses the single-class file
+    assert f.getNode("class_id").string() == "other obj" and int(f.getNode("pyramid_levels").real()) == 2
+    f.release()
+
+
 def test_config1_template_file_loads():
     """The committed config-1 template set (reference file layout) parses into 1 950 pyramids of 63/63/31/31 features."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagergehaeuse_templates.yml.gz")
