@@ -18,6 +18,12 @@ int main(int argc, char** argv) {
   auto back = lm::Detector::read(path);
   auto t = back->getTemplates("lagergehaeuse.ply", 1);
   if (t.size() != 4 || t[3].features.size() != 10 || t[3].features[9].y != 18 || t[2].width != 50) return 4;
+  // writeClass / readClass with a class_id override (host only)
+  std::string cpath = std::string(argc > 1 ? argv[1] : "/tmp") + "/cpp_surface_class.yml";
+  det->writeClass("lagergehaeuse.ply", cpath);
+  back->readClass(cpath, "copy");
+  if (back->numClasses() != 2 || back->numTemplates("copy") != 2) return 6;
+  try { back->readClass(cpath); return 7; } catch (const lm::Error& e) { if (e.code != LMB200_E_CLASS) return 8; }
   // match without a GPU must throw the loud no-device error; with a GPU it must return an (empty-ish) list
   std::vector<unsigned char> bgr(480 * 640 * 3, 0);
   std::vector<unsigned short> depth(480 * 640, 0);
@@ -29,6 +35,14 @@ int main(int argc, char** argv) {
   } catch (const lm::Error& e) {
     if (e.code != LMB200_E_NODEVICE) { std::printf("unexpected: %s\n", e.what()); return 5; }
     std::printf("no GPU: %s\n", e.what());
+  }
+  // bulk addTemplates: same rule (two views of the blank frame: extraction fails, ids are -1, on a GPU)
+  try {
+    std::vector<lm::ImageView> view = {lm::ImageView(bgr.data(), 480, 640, LMB200_8UC3), lm::ImageView(depth.data(), 480, 640, LMB200_16UC1)};
+    std::vector<int> ids = det->addTemplates({view, view}, "blank");
+    if (ids.size() != 2 || ids[0] != -1 || ids[1] != -1) return 9;
+  } catch (const lm::Error& e) {
+    if (e.code != LMB200_E_NODEVICE) { std::printf("unexpected: %s\n", e.what()); return 10; }
   }
   std::printf("CPP_SURFACE_OK\n");
   return 0;
