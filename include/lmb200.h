@@ -271,6 +271,37 @@ enum { LMB200_DBG_QUANTIZED = 0, LMB200_DBG_LINMEM = 1, LMB200_DBG_COARSE = 2, L
  * COARSE/UNSORTED return lmb200_match_rec arrays (generation order).  *n_bytes in: capacity, out: size. */
 int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst, size_t* n_bytes);
 
+/* ---- headless view synthesis (host code) --------------------------------------------
+ * Replaces the SDL + OpenGL offscreen passes the reference renders template views and benchmark images with
+ * (OpenGLRender::renderDepthToFrontBuff / renderColorToFrontBuff + getDepthImgFromBuff / getColorImgFromBuff,
+ * src/OpenglRender.cpp:33-141, shader/depth.fs): a z-buffer rasteriser, one view per host thread.
+ * Camera space: looking down -z, +y up; u = cx + fx*x/z, v = cy - fy*y/z (the image after the reference's vertical
+ * flip).  Depth: nearest surface in millimetres (u16, 0 = background).  Colour: 255 on the model, 0 elsewhere
+ * (the reference draws models without vertex colours white and thresholds the image to binary at once). */
+typedef struct {
+  const double* vertices;  /* [n_vertices][3] model coordinates (mm) */
+  int n_vertices;
+  const int* triangles;    /* [n_triangles][3] vertex indices */
+  int n_triangles;
+} lmb200_mesh;
+typedef struct {
+  int width, height;
+  double fx, fy, cx, cy;   /* the reference uses fy for both axes and the image centre (OpenglRender.cpp:3-12) */
+  double near_mm, far_mm;  /* 100 / 10000 in the reference (OpenglRender.cpp:10-11); far only bounds the u16 range */
+} lmb200_camera;
+/* n_views cameras at eyes[i] looking at the origin with +Y up (glm::lookAt(eye, 0, up), OpenglRender.cpp:334-345).
+ * depth_out [n_views][height][width] u16 and/or colour_out [n_views][height][width][3] u8 (either may be NULL).
+ * threads <= 0: all host threads. */
+int lmb200_render_lookat(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* eyes, int n_views,
+                         uint16_t* depth_out, uint8_t* colour_out, int threads);
+/* The same with explicit model-view transforms x_cam = R*x + t (rotations [n][9] row-major, translations [n][3]):
+ * the overloads the benchmark uses (OpenglRender.cpp:69-94,:116-141). */
+int lmb200_render_pose(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* rotations,
+                       const double* translations, int n_views, uint16_t* depth_out, uint8_t* colour_out, int threads);
+/* ASCII PLY loader (models/*.ply of the reference; polygons become triangle fans).  Free both arrays with lmb200_free. */
+int lmb200_load_ply(const char* path, double** vertices, int* n_vertices, int** triangles, int* n_triangles);
+void lmb200_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

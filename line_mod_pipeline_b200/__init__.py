@@ -8,7 +8,8 @@ Detector interface.  There is no CPU fallback.
 from .detector import (Detector, ColorGradient, DepthNormal, getDefaultLINE, getDefaultLINEMOD, LinemodError,
                        MATCH_DTYPE, merge_matches, shard_plan, comm_unique_id, read_pose_sidecar, write_pose_sidecar, POSE_DTYPE)
 from . import _capi as capi
+from . import render
 
 __all__ = ["Detector", "ColorGradient", "DepthNormal", "getDefaultLINE", "getDefaultLINEMOD", "LinemodError",
            "MATCH_DTYPE", "merge_matches", "shard_plan", "comm_unique_id", "read_pose_sidecar", "write_pose_sidecar",
-           "POSE_DTYPE", "capi"]
+           "POSE_DTYPE", "capi", "render"]

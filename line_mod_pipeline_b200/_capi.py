@@ -50,10 +50,24 @@ class Profile(C.Structure):
                 ("matches", C.c_longlong)]
 
 
+class Mesh(C.Structure):
+    _fields_ = [("vertices", C.POINTER(C.c_double)), ("n_vertices", C.c_int), ("triangles", C.POINTER(C.c_int)),
+                ("n_triangles", C.c_int)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double),
+                ("cy", C.c_double), ("near_mm", C.c_double), ("far_mm", C.c_double)]
+
+
 # every entry point include/lmb200.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 _P = C.POINTER
 SIGNATURES = {
+    "lmb200_render_lookat": (C.c_int, [_P(Mesh), _P(Camera), _P(C.c_double), C.c_int, _P(C.c_uint16), _P(C.c_uint8), C.c_int]),
+    "lmb200_render_pose": (C.c_int, [_P(Mesh), _P(Camera), _P(C.c_double), _P(C.c_double), C.c_int, _P(C.c_uint16), _P(C.c_uint8), C.c_int]),
+    "lmb200_load_ply": (C.c_int, [C.c_char_p, _P(_P(C.c_double)), _P(C.c_int), _P(_P(C.c_int)), _P(C.c_int)]),
+    "lmb200_free": (None, [C.c_void_p]),
     "lmb200_default_modality": (None, [C.c_int, _P(Modality)]),
     "lmb200_default_config": (None, [_P(Config), C.c_int]),
     "lmb200_create": (C.c_int, [_P(Config), _P(_H)]),
