@@ -230,4 +230,42 @@ class Detector {
 inline std::unique_ptr<Detector> getDefaultLINE() { return std::unique_ptr<Detector>(new Detector({ColorGradient()}, {5, 8})); }
 inline std::unique_ptr<Detector> getDefaultLINEMOD() { return std::unique_ptr<Detector>(new Detector({ColorGradient(), DepthNormal()}, {5, 8})); }
 
+// Headless stand-in for the reference's OpenGLRender (src/OpenglRender.cpp): model + pinhole camera -> depth (u16, mm)
+// and colour (BGR8, white on black) images of n views, rendered on the host threads.
+struct Mesh {
+  std::vector<double> vertices;  // xyz per vertex (mm)
+  std::vector<int> triangles;    // three indices per triangle
+  static Mesh loadPly(const std::string& path) {
+    double* v = nullptr; int* t = nullptr; int nv = 0, nt = 0;
+    int rc = lmb200_load_ply(path.c_str(), &v, &nv, &t, &nt);
+    if (rc) throw Error(rc, "cannot load " + path);
+    Mesh m;
+    m.vertices.assign(v, v + 3 * (size_t)nv);
+    m.triangles.assign(t, t + 3 * (size_t)nt);
+    lmb200_free(v); lmb200_free(t);
+    return m;
+  }
+};
+struct RenderedViews {
+  int n = 0, width = 0, height = 0;
+  std::vector<uint16_t> depth;   // [n][height][width]
+  std::vector<uint8_t> colour;   // [n][height][width][3]
+};
+inline lmb200_camera referenceCamera(int width = 640, int height = 480, double f = 1045.69141) {
+  lmb200_camera c; c.width = width; c.height = height; c.fx = f; c.fy = f; c.cx = width / 2.0; c.cy = height / 2.0; c.near_mm = 100.0; c.far_mm = 10000.0;
+  return c;
+}
+// OpenGLRender::renderDepthToFrontBuff / renderColorToFrontBuff(model, camPosition) for many camera positions (xyz each)
+inline RenderedViews renderLookAt(const Mesh& mesh, const lmb200_camera& cam, const std::vector<double>& eyes_xyz, int threads = 0) {
+  RenderedViews out;
+  out.n = (int)(eyes_xyz.size() / 3); out.width = cam.width; out.height = cam.height;
+  out.depth.resize((size_t)out.n * cam.width * cam.height);
+  out.colour.resize(out.depth.size() * 3);
+  lmb200_mesh m; m.vertices = mesh.vertices.data(); m.n_vertices = (int)(mesh.vertices.size() / 3);
+  m.triangles = mesh.triangles.data(); m.n_triangles = (int)(mesh.triangles.size() / 3);
+  int rc = lmb200_render_lookat(&m, &cam, eyes_xyz.data(), out.n, out.depth.data(), out.colour.data(), threads);
+  if (rc) throw Error(rc, "lmb200_render_lookat");
+  return out;
+}
+
 }  // namespace lm

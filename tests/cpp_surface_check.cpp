@@ -24,6 +24,16 @@ int main(int argc, char** argv) {
   back->readClass(cpath, "copy");
   if (back->numClasses() != 2 || back->numTemplates("copy") != 2) return 6;
   try { back->readClass(cpath); return 7; } catch (const lm::Error& e) { if (e.code != LMB200_E_CLASS) return 8; }
+  // headless renderer: a tetrahedron seen from +z
+  {
+    lm::Mesh mesh;
+    mesh.vertices = {-50, -50, 0, 50, -50, 0, 0, 60, 0, 0, 0, 80};
+    mesh.triangles = {0, 1, 2, 0, 1, 3, 1, 2, 3, 2, 0, 3};
+    lm::RenderedViews rv = lm::renderLookAt(mesh, lm::referenceCamera(), {0, 0, 600, 0, 0, 900});
+    const int d0 = rv.depth[(size_t)240 * 640 + 320], d1 = rv.depth[(size_t)640 * 480 + (size_t)240 * 640 + 320];  // just off the apex
+    if (rv.n != 2 || d0 < 520 || d0 > 523 || d1 < 820 || d1 > 823) { std::printf("render: %d %d\n", d0, d1); return 11; }
+    if (rv.colour[3 * ((size_t)240 * 640 + 320)] != 255 || rv.depth[0] != 0) return 12;
+  }
   // match without a GPU must throw the loud no-device error; with a GPU it must return an (empty-ish) list
   std::vector<unsigned char> bgr(480 * 640 * 3, 0);
   std::vector<unsigned short> depth(480 * 640, 0);
