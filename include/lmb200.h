@@ -295,7 +295,9 @@ typedef struct {
 int lmb200_render_lookat(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* eyes, int n_views,
                          uint16_t* depth_out, uint8_t* colour_out, int threads);
 /* The same with explicit model-view transforms x_cam = R*x + t (rotations [n][9] row-major, translations [n][3]):
- * the overloads the benchmark uses (OpenglRender.cpp:69-94,:116-141). */
+ * the overloads the benchmark uses (OpenglRender.cpp:69-94,:116-141), which build `view` from in_rotMat and put
+ * (in_traVec.x, -in_traVec.y, -in_traVec.z) into its translation column: pass R = the upper-left 3x3 of in_rotMat
+ * (glm is column-major: R[3*i+j] = in_rotMat[j][i]) and t = (tx, -ty, -tz). */
 int lmb200_render_pose(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* rotations,
                        const double* translations, int n_views, uint16_t* depth_out, uint8_t* colour_out, int threads);
 /* ASCII PLY loader (models/*.ply of the reference; polygons become triangle fans).  Free both arrays with lmb200_free. */
