@@ -300,7 +300,7 @@ int lmb200_render_lookat(const lmb200_mesh* mesh, const lmb200_camera* cam, cons
  * (glm is column-major: R[3*i+j] = in_rotMat[j][i]) and t = (tx, -ty, -tz). */
 int lmb200_render_pose(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* rotations,
                        const double* translations, int n_views, uint16_t* depth_out, uint8_t* colour_out, int threads);
-/* ASCII PLY loader (models/*.ply of the reference; polygons become triangle fans).  Free both arrays with lmb200_free. */
+/* ASCII PLY loader (the .ply models of the reference; polygons become triangle fans).  Free both arrays with lmb200_free. */
 int lmb200_load_ply(const char* path, double** vertices, int* n_vertices, int** triangles, int* n_triangles);
 void lmb200_free(void* p);
 

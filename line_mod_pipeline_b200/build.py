@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(log[-1])
             raise RuntimeError("nvcc failed on " + s)
         objs.append(o)
-    cmd = [nvcc(), "-shared", "-o", SO] + objs + ["-lz", "-ldl", "-cudart", "static"]
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-lz", "-ldl", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:

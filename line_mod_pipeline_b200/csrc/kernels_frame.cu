@@ -184,7 +184,6 @@ __global__ void __launch_bounds__(256) cg_quantize_kernel(const u8* __restrict__
     }
   }
   __syncthreads();
-  const u8* s_srcb = reinterpret_cast<const u8*>(&s_srcw[0][0]);
 
   // 2. vertical blur sums at the CLAMPED centre row (so out-of-image R2 rows replicate the blurred border row, which
   //    is what Sobel's BORDER_REPLICATE sees).  Two bytes per 32-bit lane: a 16-bit lane holds at most 256*255.

@@ -444,7 +444,7 @@ int read_cache_file(const char* path, int device, lmb200_handle* out, std::strin
         tm.width = w; tm.height = hh; tm.pyramid_level = lv;
         tm.features.resize(nf);
         for (uint32_t i = 0; i < nf; ++i) {
-          int16_t x, y; uint8_t l;
+          int16_t x = 0, y = 0; uint8_t l = 0;
           get(b, p, x); get(b, p, y); get(b, p, l);
           tm.features[i] = Feature{x, y, l};
         }
