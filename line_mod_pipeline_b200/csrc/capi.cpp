@@ -228,7 +228,12 @@ int lmb200_write(lmb200_handle h, const char* path) { return (h && path) ? write
 int lmb200_read(const char* path, int device, lmb200_handle* out) {
   if (!path || !out) return LMB200_E_INVALID;
   std::string err;
-  int rc = read_detector_file(path, device, out, err);
+  int rc;
+  try {  // no exception may cross the C ABI (a hostile file can still exhaust memory)
+    rc = read_detector_file(path, device, out, err);
+  } catch (const std::exception& e) {
+    rc = LMB200_E_IO; err = std::string(path) + ": " + e.what();
+  }
   if (rc) g_create_error = err;
   return rc;
 }
@@ -239,7 +244,12 @@ int lmb200_write_class(lmb200_handle h, const char* class_id, const char* path) 
 int lmb200_read_class(lmb200_handle h, const char* path, const char* class_id_override) {
   if (!h || !path) return LMB200_E_INVALID;
   std::string err;
-  int rc = read_class_file(h, path, err, class_id_override);
+  int rc;
+  try {
+    rc = read_class_file(h, path, err, class_id_override);
+  } catch (const std::exception& e) {
+    rc = LMB200_E_IO; err = std::string(path) + ": " + e.what();
+  }
   return rc ? set_error(h, rc, err) : LMB200_OK;
 }
 int lmb200_write_classes(lmb200_handle h, const char* format) {
@@ -260,7 +270,12 @@ int lmb200_read_classes(lmb200_handle h, const char* const* class_ids, int n, co
     char path[4096];
     std::snprintf(path, sizeof path, fmt, class_ids[i]);
     std::string err;
-    int rc = read_class_file(h, path, err);
+    int rc;
+    try {
+      rc = read_class_file(h, path, err);
+    } catch (const std::exception& e) {
+      rc = LMB200_E_IO; err = std::string(path) + ": " + e.what();
+    }
     if (rc) return set_error(h, rc, err);
   }
   return LMB200_OK;

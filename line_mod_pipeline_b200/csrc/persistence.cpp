@@ -285,8 +285,9 @@ int parse_file(const char* path, ParseState& S, std::string& err) {
         const char* p = val.c_str();
         std::vector<long> nums;
         while (*p) {
-          if ((*p >= '0' && *p <= '9') || *p == '-') { char* e; nums.push_back(std::strtol(p, &e, 10)); p = e; }
-          else ++p;
+          char* e = const_cast<char*>(p);
+          if ((*p >= '0' && *p <= '9') || *p == '-') { long v = std::strtol(p, &e, 10); if (e != p) nums.push_back(v); }
+          p = e != p ? e : p + 1;  // a '-' that starts no number must not stall the scan
         }
         for (size_t i = 0; i + 2 < nums.size(); i += 3) tpl->features.push_back(Feature{(int)nums[i], (int)nums[i + 1], (int)nums[i + 2]});
       }
@@ -433,6 +434,9 @@ int read_cache_file(const char* path, int device, lmb200_handle* out, std::strin
     std::string id = b.substr(p, len);
     p += len;
     if (!get(b, p, nt)) { lmb200_destroy(h); err = "truncated cache"; return LMB200_E_IO; }
+    if (per <= 0 || (unsigned long long)nt * (unsigned long long)per * 16ull > b.size() - p) {  // 16 B = an empty template record
+      lmb200_destroy(h); err = "corrupt cache (template count)"; return LMB200_E_IO;
+    }
     std::vector<TemplatePyramid>& tps = h->classes[id];
     tps.resize(nt);
     for (uint32_t t = 0; t < nt; ++t) {
@@ -464,7 +468,12 @@ int lmb200_write_cache(lmb200_handle h, const char* path) { return (h && path) ?
 int lmb200_read_cache(const char* path, int device, lmb200_handle* out) {
   if (!path || !out) return LMB200_E_INVALID;
   std::string err;
-  int rc = lmh::read_cache_file(path, device, out, err);
+  int rc;
+  try {  // no exception may cross the C ABI
+    rc = lmh::read_cache_file(path, device, out, err);
+  } catch (const std::exception& e) {
+    rc = LMB200_E_IO; err = std::string(path) + ": " + e.what();
+  }
   if (rc) lmh::set_create_error(err);
   return rc;
 }

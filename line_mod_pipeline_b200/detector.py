@@ -32,6 +32,15 @@ def DepthNormal(distance_threshold=2000, difference_threshold=50, num_features=6
                 num_features=num_features, extract_threshold=extract_threshold)
 
 
+def _enc(s):
+    """class ids are byte strings in the C ABI; arbitrary bytes round-trip through surrogateescape"""
+    return s.encode("utf-8", "surrogateescape")
+
+
+def _dec(b):
+    return b.decode("utf-8", "surrogateescape")
+
+
 def _image(a):
     """numpy array -> (lmb200_image, keepalive)."""
     if a is None:
@@ -51,7 +60,7 @@ def _image(a):
 
 def _cstr_array(ids):
     ids = list(ids or [])
-    arr = (C.c_char_p * max(1, len(ids)))(*[s.encode() for s in ids])
+    arr = (C.c_char_p * max(1, len(ids)))(*[_enc(s) for s in ids])
     return arr, len(ids)
 
 
@@ -78,12 +87,12 @@ class Detector:
         cfg.candidate_capacity = candidate_capacity
         rc = self._L.lmb200_create(C.byref(cfg), C.byref(self._h))
         if rc:
-            raise LinemodError(rc, (self._L.lmb200_last_error(None) or b"").decode())
+            raise LinemodError(rc, (self._L.lmb200_last_error(None) or b"").decode("utf-8", "replace"))
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc, allow=()):
         if rc and rc not in allow:
-            raise LinemodError(rc, (self._L.lmb200_last_error(self._h) or b"").decode())
+            raise LinemodError(rc, (self._L.lmb200_last_error(self._h) or b"").decode("utf-8", "replace"))
         return rc
 
     def close(self):
@@ -120,10 +129,10 @@ class Detector:
         return self._L.lmb200_num_classes(self._h)
 
     def classIds(self):
-        return [self._L.lmb200_class_id(self._h, i).decode() for i in range(self.numClasses())]
+        return [_dec(self._L.lmb200_class_id(self._h, i)) for i in range(self.numClasses())]
 
     def numTemplates(self, class_id=None):
-        return self._L.lmb200_num_templates(self._h, class_id.encode() if class_id is not None else None)
+        return self._L.lmb200_num_templates(self._h, _enc(class_id) if class_id is not None else None)
 
     def getTemplates(self, class_id, template_id):
         """-> list (level*M+modality) of dict(width,height,pyramid_level,features=int32[n,3])."""
@@ -131,7 +140,7 @@ class Detector:
         out = []
         for i in range(n):
             t = K.Template()
-            self._check(self._L.lmb200_get_template(self._h, class_id.encode(), template_id, i, C.byref(t)))
+            self._check(self._L.lmb200_get_template(self._h, _enc(class_id), template_id, i, C.byref(t)))
             f = np.zeros((t.num_features, 3), np.int32)
             if t.num_features:
                 f[:] = np.ctypeslib.as_array(C.cast(t.features, C.POINTER(C.c_int)), shape=(t.num_features, 3))
@@ -146,7 +155,7 @@ class Detector:
         mimg, mkeep = _image(object_mask)
         bb = (C.c_int * 4)()
         tid = C.c_int(-1)
-        self._check(self._L.lmb200_add_template(self._h, class_id.encode(), arr, len(imgs),
+        self._check(self._L.lmb200_add_template(self._h, _enc(class_id), arr, len(imgs),
                                                 C.byref(mimg) if object_mask is not None else None, bb, C.byref(tid)))
         return tid.value, tuple(bb)
 
@@ -165,7 +174,7 @@ class Detector:
             marr = (K.Image * n)(*[m[0] for m in mkeep])
         bb = (C.c_int * (4 * n))()
         tids = (C.c_int * n)()
-        self._check(self._L.lmb200_add_templates(self._h, class_id.encode(), n, arr, M, marr, bb, tids))
+        self._check(self._L.lmb200_add_templates(self._h, _enc(class_id), n, arr, M, marr, bb, tids))
         return [(tids[i], tuple(bb[4 * i:4 * i + 4])) for i in range(n)]
 
     def addSyntheticTemplate(self, templates, class_id):
@@ -176,7 +185,7 @@ class Detector:
             keep.append(f)
             arr[i] = K.Template(t["width"], t["height"], t["pyramid_level"], len(f), C.cast(f.ctypes.data, C.POINTER(K.Feature)))
         tid = C.c_int(-1)
-        self._check(self._L.lmb200_add_synthetic_template(self._h, class_id.encode(), arr, len(templates), C.byref(tid)))
+        self._check(self._L.lmb200_add_synthetic_template(self._h, _enc(class_id), arr, len(templates), C.byref(tid)))
         return tid.value
 
     def uploadTemplates(self):
@@ -196,7 +205,7 @@ class Detector:
         h = K._H()
         rc = L.lmb200_read(str(path).encode(), device, C.byref(h))
         if rc:
-            raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode())
+            raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode("utf-8", "replace"))
         return cls(_handle=h)
 
     def writeCache(self, path):
@@ -208,14 +217,14 @@ class Detector:
         h = K._H()
         rc = L.lmb200_read_cache(str(path).encode(), device, C.byref(h))
         if rc:
-            raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode())
+            raise LinemodError(rc, (L.lmb200_last_error(None) or b"").decode("utf-8", "replace"))
         return cls(_handle=h)
 
     def writeClass(self, class_id, path):
-        self._check(self._L.lmb200_write_class(self._h, class_id.encode(), str(path).encode()))
+        self._check(self._L.lmb200_write_class(self._h, _enc(class_id), str(path).encode()))
 
     def readClass(self, path, class_id_override=""):
-        self._check(self._L.lmb200_read_class(self._h, str(path).encode(), class_id_override.encode() if class_id_override else None))
+        self._check(self._L.lmb200_read_class(self._h, str(path).encode(), _enc(class_id_override) if class_id_override else None))
 
     def writeClasses(self, fmt="templates_%s.yml.gz"):
         self._check(self._L.lmb200_write_classes(self._h, fmt.encode()))
@@ -457,7 +466,7 @@ def comm_unique_id():
     uid = np.zeros(128, np.uint8)
     rc = K.lib().lmb200_comm_unique_id(uid.ctypes.data)
     if rc:
-        raise LinemodError(rc, (K.lib().lmb200_last_error(None) or b"").decode())
+        raise LinemodError(rc, (K.lib().lmb200_last_error(None) or b"").decode("utf-8", "replace"))
     return uid
 
 

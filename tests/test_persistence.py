@@ -216,3 +216,57 @@ def test_pose_sidecar_round_trip(tmp_path):
         assert np.array_equal(a.tobytes(), b.tobytes())
     with pytest.raises(lm.LinemodError):
         lm.read_pose_sidecar(p, 7)
+
+
+def test_corrupted_files_fail_cleanly(tmp_path):
+    """Truncated / mutated template files and caches either load or raise LinemodError — never crash — and whatever
+    loads can be queried (hand-written parsers: persistence.cpp)."""
+    import random
+    d = lm.getDefaultLINEMOD()
+    _fill(d)
+    yml, cache = str(tmp_path / "ok.yml"), str(tmp_path / "ok.bin")
+    d.write(yml)
+    d.writeCache(cache)
+    txt, blob = open(yml, "rb").read(), open(cache, "rb").read()
+    rng = random.Random(0)
+    outcomes = {"yaml_ok": 0, "yaml_err": 0, "cache_ok": 0, "cache_err": 0}
+    for it in range(160):
+        b = bytearray(txt)
+        mode = it % 4
+        if mode == 0:
+            b = b[:rng.randrange(len(b))]
+        elif mode == 1:
+            for _ in range(rng.randrange(1, 6)):
+                b[rng.randrange(len(b))] = rng.randrange(32, 127)
+        elif mode == 2:
+            i = rng.randrange(len(b)); del b[i:min(len(b), i + rng.randrange(1, 200))]
+        else:
+            i = rng.randrange(len(b)); b[i:i] = bytes(rng.randrange(32, 127) for _ in range(rng.randrange(1, 50)))
+        p = str(tmp_path / "m.yml")
+        open(p, "wb").write(bytes(b))
+        try:
+            e = lm.Detector.read(p)
+            for cid in e.classIds():
+                for t in range(e.numTemplates(cid)):
+                    e.getTemplates(cid, t)
+            e.close()
+            outcomes["yaml_ok"] += 1
+        except lm.LinemodError:
+            outcomes["yaml_err"] += 1
+    for it in range(120):
+        b = bytearray(blob)
+        if it % 2 == 0:
+            b = b[:rng.randrange(len(b))]
+        else:
+            for _ in range(rng.randrange(1, 6)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        p = str(tmp_path / "m.bin")
+        open(p, "wb").write(bytes(b))
+        try:
+            e = lm.Detector.readCache(p)
+            e.numTemplates()
+            e.close()
+            outcomes["cache_ok"] += 1
+        except lm.LinemodError:
+            outcomes["cache_err"] += 1
+    assert outcomes["yaml_err"] > 10 and outcomes["cache_err"] > 10, outcomes
