@@ -486,10 +486,15 @@ int lmb200_read_pose_sidecar(const char* path, int class_index, lmb200_template_
   if (!fp) return LMB200_E_IO;
   uint32_t ncls = 0;
   int rc = LMB200_E_IO;
+  std::fseek(fp, 0, SEEK_END);
+  const long long file_size = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
   if (std::fread(&ncls, sizeof ncls, 1, fp) == 1) {
     for (uint32_t c = 0; c < ncls; ++c) {
       uint64_t n = 0;
       if (std::fread(&n, sizeof n, 1, fp) != 1) break;
+      const long long here = std::ftell(fp);
+      if (here < 0 || n > (uint64_t)(file_size - here) / sizeof(lmb200_template_pose)) break;  // count beyond the file: corrupt
       if ((int)c == class_index) {
         *n_out = (size_t)n;
         size_t take = n < cap ? (size_t)n : cap;

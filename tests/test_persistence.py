@@ -270,3 +270,12 @@ def test_corrupted_files_fail_cleanly(tmp_path):
         except lm.LinemodError:
             outcomes["cache_err"] += 1
     assert outcomes["yaml_err"] > 10 and outcomes["cache_err"] > 10, outcomes
+    # pose sidecar: a count field beyond the file must be an error, not an allocation request
+    side = str(tmp_path / "poses.bin")
+    lm.write_pose_sidecar(side, [np.zeros(5, lm.POSE_DTYPE), np.zeros(3, lm.POSE_DTYPE)])
+    blob = bytearray(open(side, "rb").read())
+    blob[4:12] = (2 ** 60).to_bytes(8, "little")
+    open(side, "wb").write(bytes(blob))
+    for ci in (0, 1):
+        with pytest.raises(lm.LinemodError):
+            lm.read_pose_sidecar(side, ci)
