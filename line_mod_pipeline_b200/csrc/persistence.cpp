@@ -401,7 +401,11 @@ int write_cache_file(lmb200_detector* h, const char* path) {
     for (auto& tp : kv.second)
       for (auto& t : tp) {
         put(b, (int32_t)t.width); put(b, (int32_t)t.height); put(b, (int32_t)t.pyramid_level); put(b, (uint32_t)t.features.size());
-        for (auto& f : t.features) { put(b, (int16_t)f.x); put(b, (int16_t)f.y); put(b, (uint8_t)f.label); }
+        for (auto& f : t.features) {
+          if (f.x < -32768 || f.x > 32767 || f.y < -32768 || f.y > 32767 || f.label < 0 || f.label > 255)
+            return set_error(h, LMB200_E_INVALID, "feature outside the cache's 16-bit coordinate range (use lmb200_write)");
+          put(b, (int16_t)f.x); put(b, (int16_t)f.y); put(b, (uint8_t)f.label);
+        }
       }
   }
   FILE* fp = std::fopen(path, "wb");

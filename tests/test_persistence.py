@@ -194,6 +194,19 @@ def test_binary_cache_round_trip_and_speed(tmp_path):
     assert err.value.code == K.E_IO
 
 
+def test_cache_refuses_what_it_cannot_hold(tmp_path):
+    """The binary cache stores coordinates in 16 bits: a (synthetic) feature outside that range is refused, the YAML
+    writer keeps it."""
+    d = lm.getDefaultLINEMOD()
+    tps = [dict(width=100, height=80, pyramid_level=i // 2, features=np.array([[70000, 3, 1]], np.int32)) for i in range(4)]
+    d.addSyntheticTemplate(tps, "far")
+    with pytest.raises(lm.LinemodError) as err:
+        d.writeCache(str(tmp_path / "c.bin"))
+    assert err.value.code == K.E_INVALID
+    d.write(str(tmp_path / "c.yml"))
+    assert lm.Detector.read(str(tmp_path / "c.yml")).getTemplates("far", 0)[0]["features"][0][0] == 70000
+
+
 def test_pose_sidecar_round_trip(tmp_path):
     """linemod_tempPosFile.bin: u32 class count, per class u64 n + n x 48-byte HighLevelLineMOD::Template records."""
     import struct
