@@ -467,3 +467,31 @@ def test_upload_templates_eagerly():
     add_random(det, ora, 40, class_id="more", seed=5)
     det.uploadTemplates()                                   # frame size known: tables + plan
     assert_same_matches(det.match([bgr, depth], 70.0), ora.match([bgr, depth], 70.0).matches(0), "eager upload after change")
+
+
+def test_non_default_modality_parameters():
+    """ColorGradient(weak, num_features, strong) and DepthNormal(distance, difference, num_features, extract) away from
+    their defaults: parameter plumbing end to end, fewer features per template, and the 64-bit instantiation of the
+    DepthNormal kernel (difference_threshold > 200)."""
+    cgp = dict(weak_threshold=20.0, num_features=40, strong_threshold=30.0)
+    dnp = dict(distance_threshold=1500, difference_threshold=300, num_features=50, extract_threshold=3)
+    det = lm.Detector([lm.ColorGradient(**cgp), lm.DepthNormal(**dnp)], [5, 8])
+    ora = O.Detector([dict(type=O.CG, **cgp), dict(type=O.DN, **dnp)], [5, 8],
+                     sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
+    bgr, depth = synth.make_frame(11)
+    ok = 0
+    for m in synth.object_masks(11)[:10]:
+        tid, bb = det.addTemplate([bgr, depth], "obj", m)
+        otid, obb = ora.add_template([bgr, depth], "obj", m)
+        assert tid == otid
+        if tid >= 0:
+            ok += 1
+            assert tuple(bb) == tuple(obb)
+            for a, b in zip(det.getTemplates("obj", tid), O.decode_pyramid(ora.get_template_flat("obj", tid))):
+                assert np.array_equal(a["features"], b["features"])
+    assert ok >= 3
+    assert len(det.getTemplates("obj", 0)[0]["features"]) == 40 and len(det.getTemplates("obj", 0)[1]["features"]) == 50
+    for thr in (80.0, 60.0):
+        got, ref = _check_frame_side(det, ora, [bgr, depth], thr, n_maps=4)
+        assert_same_matches(got, ref.matches(0), "non-default parameters thr=%g" % thr)
+    assert len(got) > 0
