@@ -118,3 +118,17 @@ def test_cpp_surface_header_compiles_and_runs(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0 and "CPP_SURFACE_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/lmb200.h is the drop-in boundary: it must compile as C99 (cgo / JNI / FFI generators read it) and link."""
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "lmb200.h"\n'
+                   'int main(void) { lmb200_config c; lmb200_default_config(&c, 1);\n'
+                   '  return (c.num_modalities == 2 && c.pyramid_levels == 2 && lmb200_version() != 0) ? 0 : 1; }\n')
+    exe = str(tmp_path / "cabi")
+    so_dir = os.path.dirname(K.SO_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", exe, "-L", so_dir, "-llmb200", "-Wl,-rpath," + so_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([exe]).returncode == 0
