@@ -132,3 +132,23 @@ def test_header_is_plain_c(tmp_path):
                         "-o", exe, "-L", so_dir, "-llmb200", "-Wl,-rpath," + so_dir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_c_example_builds_and_fails_loudly_without_gpu(tmp_path):
+    """examples/detect.c (the reference's detection loop on the C ABI) builds as C99, loads the committed config-1
+    template file and, on a box without a GPU, stops at lmb200_match with the no-device error."""
+    exe = str(tmp_path / "detect")
+    so_dir = os.path.dirname(K.SO_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "detect.c"), "-o", exe, "-L", so_dir, "-llmb200", "-Wl,-rpath," + so_dir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fixture_frame.npz"))
+    z["bgr"].tofile(str(tmp_path / "f.bgr")); z["depth"].tofile(str(tmp_path / "f.depth"))
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "lagergehaeuse_templates.yml.gz"), str(tmp_path / "f.bgr"),
+                        str(tmp_path / "f.depth"), "640", "480", "80"], capture_output=True, text=True)
+    assert "1 classes, 1950 templates, 2 modalities, T0 = 5" in r.stdout
+    if _has_gpu():
+        assert r.returncode == 0 and "matches" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
