@@ -444,10 +444,11 @@ void launch_resize_nn(const u8* src, size_t src_stride, int rows, int cols, u8* 
 // [iT, iT+2T-1)) x SL_CW decimated columns.  The band is staged in shared memory with its
 // (T-1) right/bottom halo (zero outside the image: OR identity), OR-reduced vertically then
 // horizontally, looked up in a 256 x 8-byte table (all 8 orientations of one spread byte at once)
-// and written straight into the T-strided linear memories:
-//     LM[ori][ (y%T*T + x%T) * W*H + (y/T)*W + x/T ]
+// and written straight into the T-strided linear memories (LevelGeom: flat rows on the coarsest level,
+//     LM[ori][ (y%T*T + x%T) * W*H + (y/T)*W + x/T ],
+// 16-column strips LM[ori][cell][x/T/16][y/T][16] on the finer ones).
 // Each thread produces 4 consecutive decimated positions of one grid cell for all 8 orientations,
-// i.e. eight 32-bit stores; a warp writes contiguous 128 B runs per (ori, grid cell).
+// i.e. eight 32-bit stores; a warp writes 64 B runs (flat) or 16 B runs (strips) per (ori, grid cell).
 // ---------------------------------------------------------------------------------------------
 constexpr int SL_CW = 64;
 

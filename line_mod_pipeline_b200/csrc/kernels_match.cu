@@ -15,9 +15,11 @@ namespace lmk {
 // ---------------------------------------------------------------------------------------------
 // Plan kernel: one warp per template.  For every modality the valid feature offsets
 //   off = label*per_label + grid_index*W*H + lm_index            (accessLinearMemory)
-// are written contiguously, SORTED by their word shift (off>>key_shift)&3 — key_shift 3 for the nibble-packed
-// coarsest level (8 positions per word), 2 otherwise — (warp-level counting sort), with the
-// four bucket sizes in hdr.bkt[m]; features upstream's similarity() would skip are dropped.
+// become 8-byte plan rows.  Coarsest level: rows SORTED by the word shift (off>>3)&3 of their start in the
+// nibble-packed memory (warp-level counting sort), every bucket padded to a multiple of 3 with rows of the zero
+// tail, the four bucket sizes in hdr.bkt[m]; a row = (byte offset of its 16 B chunk, funnel shift in bits).
+// Finer levels (strip layout): a row = (offset of label/cell/grid-row, grid column).
+// Features upstream's similarity() would skip are dropped.
 // hdr.flags: bit0 local-safe  : similarityLocal can never skip a feature or leave its plane
 //            bit1 coarse-safe : every feature row + template_positions stays inside its label's block
 //            bit2 one-P       : template_positions is the same for every modality
