@@ -438,11 +438,11 @@ def main():
         ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
         copy_templates_to_oracle(det, ora)
         threads = O.max_threads()
-        nfr = args.cpu_frames or 96
+        nfr = args.cpu_frames or 4 * B            # ~20 thread-seconds of CPU work (the step's frames, cycled)
         fps, dt, nm = cpu_sample(ora, nfr, args.threshold, threads, lambda i: frames[i % B])
         fps1, _, _ = cpu_sample(ora, 2, args.threshold, 1, lambda i: frames[i % B])   # upstream's matchClass is serial
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "%d of the step's frames x %d templates, oracle C++ port, %d frames in flight (one per host thread), %.1f s" % (nfr, n_tpl, threads, dt),
+               "sample": "%d frames (the step's frames, cycled) x %d templates, oracle C++ port, %d frames in flight (one per host thread), %.1f s" % (nfr, n_tpl, threads, dt),
                "single_thread_value": fps1}
 
     line = {"metric": "rgbd_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
