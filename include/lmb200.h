@@ -65,7 +65,14 @@ typedef struct {
   int device;               /* CUDA ordinal; -1 = current device */
   int max_batch;            /* frames resident per batch call; 0 = default (64) */
   int candidate_capacity;   /* coarse candidates per frame; 0 = default (16384); grows on overflow */
+  int similarity_lut;       /* LMB200_SIMLUT_CIRCULAR (0, default: upstream's table) | LMB200_SIMLUT_LINEAR */
 } lmb200_config;
+
+/* The two SIMILARITY_LUT variants (the table is data: lmb200_set_similarity_lut takes any other).
+ * CIRCULAR: response = 4 - min(|ori-j|, 8-|ori-j|), sum 628 — SURVEY.md 8c G6; upstream's literal as recalled
+ *           (tests/golden/similarity_lut_recalled.json) is byte-identical.  Default.
+ * LINEAR  : response = 4 - |ori-j|, sum 528 — round 1's default, kept selectable. */
+enum { LMB200_SIMLUT_CIRCULAR = 0, LMB200_SIMLUT_LINEAR = 1 };
 
 typedef struct {
   const void* data;
@@ -217,14 +224,24 @@ int lmb200_host_alloc(size_t bytes, void** out);                /* cudaHostAlloc
 int lmb200_host_free(void* p);
 
 /* ---- tables --------------------------------------------------------------------------- */
-/* 256-byte SIMILARITY_LUT (layout of upstream's table: [32*ori + 16*half + nibble]).
- * Default = the table upstream ships (non-circular |ori-j| distance). */
+/* 256-byte SIMILARITY_LUT (layout of upstream's table: [32*ori + 16*half + nibble]); entries <= 4.
+ * Default = lmb200_config.similarity_lut (circular distance, see LMB200_SIMLUT_*). */
 int lmb200_set_similarity_lut(lmb200_handle h, const uint8_t* lut256);
 int lmb200_get_similarity_lut(lmb200_handle h, uint8_t* lut256);
 /* 8000-byte NORMAL_LUT[20][20][20] (index [v3][v2][v1]); entries must be 0 or one-hot.
  * Default = documented stand-in generator (upstream normal_lut.i is not redistributable here). */
 int lmb200_set_normal_lut(lmb200_handle h, const uint8_t* lut8000);
 int lmb200_get_normal_lut(lmb200_handle h, uint8_t* lut8000);
+/* Loads NORMAL_LUT from a file: either upstream's `normal_lut.i` (C initialiser text: the first 8000 integer
+ * literals after the first '{' are taken in order [v3][v2][v1]) or a raw 8000-byte binary. */
+int lmb200_load_normal_lut(lmb200_handle h, const char* path);
+/* 1 while the detector still uses the built-in stand-in NORMAL_LUT (DepthNormal labels then differ from
+ * cv::linemod's by construction), 0 once lmb200_set_normal_lut / lmb200_load_normal_lut supplied a table. */
+int lmb200_normal_lut_is_standin(lmb200_handle h);
+/* Non-fatal diagnostics accumulated by the handle (e.g. "DepthNormal modality is running on the stand-in
+ * NORMAL_LUT"); empty string when there are none.  The stand-in warning is also printed once to stderr unless
+ * the environment variable LMB200_QUIET is set. */
+const char* lmb200_warnings(lmb200_handle h);
 
 /* ---- multi-GPU (one process per GPU) -------------------------------------------------- */
 /* Template sharding: this handle scores only shard `rank` of `world`.  Shards are interleaved over the
@@ -266,9 +283,12 @@ int lmb200_set_profiling(lmb200_handle h, int enabled);        /* CUDA events ar
 int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset);
 
 enum { LMB200_DBG_QUANTIZED = 0, LMB200_DBG_LINMEM = 1, LMB200_DBG_COARSE = 2, LMB200_DBG_UNSORTED = 3,
-       LMB200_DBG_MAGNITUDE = 4, LMB200_DBG_DN_INDICES = 5 };
+       LMB200_DBG_MAGNITUDE = 4, LMB200_DBG_DN_INDICES = 5, LMB200_DBG_SIMILARITY = 6 };
 /* Copies an intermediate of the LAST match on `slot` to host: QUANTIZED/LINMEM take index=level*M+modality;
- * COARSE/UNSORTED return lmb200_match_rec arrays (generation order).  *n_bytes in: capacity, out: size. */
+ * COARSE/UNSORTED return lmb200_match_rec arrays (generation order).  SIMILARITY: index = global template index
+ * (classes in classIds() order, template_id ascending); returns the u16 [H*W] coarse-level map upstream's
+ * similarity() + addSimilarities() produce for that template, computed by the production kernel with its early
+ * exit disabled.  *n_bytes in: capacity, out: size. */
 int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst, size_t* n_bytes);
 
 /* ---- headless view synthesis (host code) --------------------------------------------

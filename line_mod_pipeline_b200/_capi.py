@@ -8,10 +8,11 @@ SO_PATH = os.environ.get("LMB200_SO") or os.path.join(_HERE, "liblmb200.so")  # 
 MAX_MOD, MAX_LEVELS = 4, 8
 T_8UC1, T_16UC1, T_8UC3 = 0, 2, 16
 COLOR_GRADIENT, DEPTH_NORMAL = 0, 1
+SIMLUT_CIRCULAR, SIMLUT_LINEAR = 0, 1
 OK, E_INVALID, E_SOURCES, E_SIZE, E_FEATURES, E_CLASS, E_IO, E_CUDA, E_TRUNCATED, E_COMM, E_NODEVICE = range(0, -11, -1)
 K_NAMES = ["upload", "pyrdown", "cg_quantize", "dn_quantize", "median", "decimate", "linearize",
            "sim_coarse", "sim_local", "pack"]
-DBG_QUANTIZED, DBG_LINMEM, DBG_COARSE, DBG_UNSORTED, DBG_MAGNITUDE, DBG_DN_INDICES = range(6)
+DBG_QUANTIZED, DBG_LINMEM, DBG_COARSE, DBG_UNSORTED, DBG_MAGNITUDE, DBG_DN_INDICES, DBG_SIMILARITY = range(7)
 
 
 class Modality(C.Structure):
@@ -23,7 +24,7 @@ class Modality(C.Structure):
 class Config(C.Structure):
     _fields_ = [("num_modalities", C.c_int), ("modalities", Modality * MAX_MOD), ("pyramid_levels", C.c_int),
                 ("T", C.c_int * MAX_LEVELS), ("device", C.c_int), ("max_batch", C.c_int),
-                ("candidate_capacity", C.c_int)]
+                ("candidate_capacity", C.c_int), ("similarity_lut", C.c_int)]
 
 
 class Image(C.Structure):
@@ -116,6 +117,9 @@ SIGNATURES = {
     "lmb200_host_free": (C.c_int, [C.c_void_p]),
     "lmb200_set_similarity_lut": (C.c_int, [_H, C.c_void_p]),
     "lmb200_get_similarity_lut": (C.c_int, [_H, C.c_void_p]),
+    "lmb200_load_normal_lut": (C.c_int, [_H, C.c_char_p]),
+    "lmb200_normal_lut_is_standin": (C.c_int, [_H]),
+    "lmb200_warnings": (C.c_char_p, [_H]),
     "lmb200_set_normal_lut": (C.c_int, [_H, C.c_void_p]),
     "lmb200_get_normal_lut": (C.c_int, [_H, C.c_void_p]),
     "lmb200_set_template_shard": (C.c_int, [_H, C.c_int, C.c_int]),

@@ -2,7 +2,10 @@
 // introspection, template store, tables, persistence wrappers.  (Compute entry points live in
 // detector.cu, multi-GPU plumbing in comm.cpp.)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
+#include <vector>
 
 #include "detector.h"
 
@@ -12,8 +15,10 @@ namespace lmh {
 int add_template_gpu(lmb200_detector* h, const char* class_id, const lmb200_image* sources, int n_sources,
                      const lmb200_image* object_mask, int* bb4, int* template_id);
 
-// SIMILARITY_LUT as shipped upstream: max over set bits j of max(0, 4 - |ori - j|) (non-circular).
-void default_similarity_lut(uint8_t* out) {
+// SIMILARITY_LUT: max over set bits j of max(0, 4 - dist(ori, j)).
+// circular (default): dist = min(|ori-j|, 8-|ori-j|) — SURVEY.md 8c G6 (sum 628); upstream's literal table as recalled
+// in round 2 is byte-identical (tests/golden/similarity_lut_recalled.json).  linear: dist = |ori-j| (sum 528).
+void similarity_lut_variant(int linear, uint8_t* out) {
   for (int ori = 0; ori < 8; ++ori)
     for (int half = 0; half < 2; ++half)
       for (int nib = 0; nib < 16; ++nib) {
@@ -22,11 +27,13 @@ void default_similarity_lut(uint8_t* out) {
           if (nib & (1 << b)) {
             int d = ori - (b + 4 * half);
             if (d < 0) d = -d;
+            if (!linear && 8 - d < d) d = 8 - d;
             if (4 - d > best) best = 4 - d;
           }
         out[32 * ori + 16 * half + nib] = (uint8_t)best;
       }
 }
+void default_similarity_lut(uint8_t* out) { similarity_lut_variant(0, out); }
 
 // Stand-in for upstream's NORMAL_LUT[20][20][20] (normal_lut.i is not available offline).
 // Cell (v3,v2,v1) -> direction (x,y) = (2*v1-19, 2*v2-19); label = the 45-degree sector of atan2(y,x)
@@ -85,11 +92,16 @@ int lmb200_create(const lmb200_config* cfg, lmb200_handle* out) {
     }
   for (int l = 0; l < cfg->pyramid_levels; ++l)
     if (cfg->T[l] < 1 || cfg->T[l] > 32) { g_create_error = "T must be in 1..32"; return LMB200_E_INVALID; }
+  if (cfg->similarity_lut != LMB200_SIMLUT_CIRCULAR && cfg->similarity_lut != LMB200_SIMLUT_LINEAR) {
+    g_create_error = "similarity_lut must be LMB200_SIMLUT_CIRCULAR or LMB200_SIMLUT_LINEAR";
+    return LMB200_E_INVALID;
+  }
   lmb200_detector* h = new lmb200_detector();
   h->cfg = *cfg;
   std::memset(&h->prof, 0, sizeof(h->prof));
-  default_similarity_lut(h->sim_lut);
+  similarity_lut_variant(cfg->similarity_lut == LMB200_SIMLUT_LINEAR, h->sim_lut);
   default_normal_lut(h->normal_lut);
+  h->normal_lut_standin = true;
   *out = h;
   return LMB200_OK;
 }
@@ -302,8 +314,43 @@ int lmb200_set_normal_lut(lmb200_handle h, const uint8_t* lut8000) {
   }
   std::memcpy(h->normal_lut, lut8000, 8000);
   h->luts_dirty = true;
+  h->normal_lut_standin = false;
   return LMB200_OK;
 }
+int lmb200_load_normal_lut(lmb200_handle h, const char* path) {
+  if (!h || !path) return LMB200_E_INVALID;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return set_error(h, LMB200_E_IO, std::string("cannot open ") + path);
+  std::string buf;
+  char tmp[65536];
+  size_t n;
+  while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) {
+    buf.append(tmp, n);
+    if (buf.size() > (64u << 20)) break;
+  }
+  std::fclose(f);
+  if (buf.size() == 8000) return lmb200_set_normal_lut(h, (const uint8_t*)buf.data());
+  // normal_lut.i: C initialiser text.  Comments are skipped; integer literals after the first '{' are the entries.
+  std::vector<uint8_t> lut;
+  size_t i = buf.find('{');
+  if (i == std::string::npos) return set_error(h, LMB200_E_IO, std::string(path) + ": neither 8000 raw bytes nor a C initialiser");
+  for (; i < buf.size() && lut.size() < 8000; ++i) {
+    const char c = buf[i];
+    if (c == '/' && i + 1 < buf.size() && buf[i + 1] == '/') { while (i < buf.size() && buf[i] != '\n') ++i; continue; }
+    if (c == '/' && i + 1 < buf.size() && buf[i + 1] == '*') { size_t e = buf.find("*/", i + 2); if (e == std::string::npos) break; i = e + 1; continue; }
+    if (c >= '0' && c <= '9') {
+      char* end = nullptr;
+      unsigned long v = std::strtoul(buf.c_str() + i, &end, 0);  // decimal, 0x.., or octal literals
+      if (v > 255) return set_error(h, LMB200_E_IO, std::string(path) + ": entry does not fit a byte");
+      lut.push_back((uint8_t)v);
+      i = (size_t)(end - buf.c_str()) - 1;
+    }
+  }
+  if (lut.size() != 8000) return set_error(h, LMB200_E_IO, std::string(path) + ": expected 8000 NORMAL_LUT entries, found " + std::to_string(lut.size()));
+  return lmb200_set_normal_lut(h, lut.data());
+}
+int lmb200_normal_lut_is_standin(lmb200_handle h) { return h ? (h->normal_lut_standin ? 1 : 0) : LMB200_E_INVALID; }
+const char* lmb200_warnings(lmb200_handle h) { return h ? h->warnings.c_str() : ""; }
 int lmb200_get_normal_lut(lmb200_handle h, uint8_t* lut8000) {
   if (!h || !lut8000) return LMB200_E_INVALID;
   std::memcpy(lut8000, h->normal_lut, 8000);

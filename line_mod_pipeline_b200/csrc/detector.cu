@@ -122,7 +122,23 @@ static void collect_profile(lmb200_detector* h) {
 }
 
 // ---------------------------------------------------------------- tables
+// First use of a DepthNormal modality on the built-in stand-in NORMAL_LUT: say so (ADVICE r1 — the labels cannot
+// equal cv::linemod's until upstream's normal_lut.i is supplied through lmb200_load_normal_lut / _set_normal_lut).
+static void warn_standin_normal_lut(lmb200_detector* h) {
+  if (h->standin_warned || !h->normal_lut_standin) return;
+  bool dn = false;
+  for (int m = 0; m < h->cfg.num_modalities; ++m) dn |= h->cfg.modalities[m].type == LMB200_DEPTH_NORMAL;
+  if (!dn) return;
+  h->standin_warned = true;
+  const char* msg = "DepthNormal modality is running on the built-in stand-in NORMAL_LUT: quantized normals (and templates "
+                    "extracted from them) differ from cv::linemod's; supply upstream's normal_lut.i with lmb200_load_normal_lut";
+  if (!h->warnings.empty()) h->warnings += "; ";
+  h->warnings += msg;
+  if (!std::getenv("LMB200_QUIET")) std::fprintf(stderr, "[lmb200 warning] %s\n", msg);
+}
+
 static int upload_luts(lmb200_detector* h) {
+  warn_standin_normal_lut(h);
   if (!h->luts_dirty) return LMB200_OK;
   uint2 table[256];
   for (int s = 0; s < 256; ++s) {
@@ -210,7 +226,9 @@ static int alloc_match_buffers(lmb200_detector* h) {
   h->h_head = std::min(h->out_cap, 1024);
   CU(cudaHostAlloc((void**)&h->h_ctr, (size_t)S * sizeof(SlotCtr), cudaHostAllocDefault));
   CU(cudaHostAlloc((void**)&h->h_out, (size_t)S * h->out_cap * sizeof(Cand), cudaHostAllocDefault));
-  h->slot_threshold.assign(S, 0.f);
+  // thresholds survive a reallocation (grow_capacity): ranges matched earlier are re-run with them at fetch time
+  if ((int)h->slot_threshold.size() != S) h->slot_threshold.assign(S, 0.f);
+  h->slot_gen.assign(S, -1);              // every slot's device results are gone
   return LMB200_OK;
 }
 
@@ -558,7 +576,7 @@ static int run_matching(lmb200_detector* h, int first, int count, float threshol
     launch_pack(mp, h->d_out.as<Cand>() + (size_t)first * h->out_cap, h->out_cap, st);
   }
   CU(cudaGetLastError());
-  for (int i = 0; i < count; ++i) h->slot_threshold[first + i] = threshold;
+  for (int i = 0; i < count; ++i) { h->slot_threshold[first + i] = threshold; h->slot_gen[first + i] = h->buffer_generation; }
   h->prof.frames += count;
   h->prof.bytes_coarse += (long long)count * h->sel_bytes_coarse;
   return LMB200_OK;
@@ -606,7 +624,26 @@ static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, 
 }
 
 // Single-lane fetch: on overflow grow the stores and redo the template side of [first, first+count).
+// Slots whose results were computed into stores that have since been reallocated (another range overflowed and
+// grew them) are matched again before they are read: the linear memories are still resident.
+static int revalidate_slots(lmb200_detector* h, int first, int count) {
+  for (int i = 0; i < count;) {
+    if (h->slot_gen[first + i] == h->buffer_generation) { ++i; continue; }
+    int j = i + 1;  // maximal stale run with one threshold
+    while (j < count && h->slot_gen[first + j] != h->buffer_generation && h->slot_threshold[first + j] == h->slot_threshold[first + i]) ++j;
+    int rc = run_matching(h, first + i, j - i, h->slot_threshold[first + i], h->lanes[0].stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->lanes[0].stream));
+    i = j;
+  }
+  return LMB200_OK;
+}
+
 static int fetch_grow(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out) {
+  {
+    int rc = revalidate_slots(h, first, count);
+    if (rc) return rc;
+  }
   for (;;) {
     int rc = fetch_raw(h, first, count, st, out);
     if (rc <= 0) return rc;
@@ -623,6 +660,7 @@ static void to_matches(lmb200_detector* h, const std::vector<Cand>& raw, std::ve
   m.resize(raw.size());
   for (size_t i = 0; i < raw.size(); ++i) {
     int g = raw[i].tsel;
+    if (g < 0 || g >= h->ntpl) { m[i] = Match{raw[i].x, raw[i].y, raw[i].sim, -1, -1}; continue; }  // never index with a bad record
     m[i] = Match{raw[i].x, raw[i].y, raw[i].sim, h->g_class[g], h->g_tid[g]};
   }
 }
@@ -1158,7 +1196,7 @@ int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst
     LevelBuffers& lb = h->levels[0];
     size_t n = (size_t)lb.g.rows * lb.g.cols;
     ALLOC(h->d_mag, n * sizeof(float));
-    DevBuf tmpq;
+    ScopedDevBuf tmpq;
     ALLOC(tmpq, n);
     const lmb200_modality& mod = h->cfg.modalities[index];
     launch_cg_quantize(lb.bgr[index].as<u8>() + (size_t)slot * lb.bgr_stride, lb.bgr_stride, tmpq.as<u8>(), n,
@@ -1173,7 +1211,7 @@ int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst
     LevelBuffers& lb = h->levels[0];
     size_t n = (size_t)lb.g.rows * lb.g.cols;
     ALLOC(h->d_dnidx, 3 * n);
-    DevBuf tmpq;
+    ScopedDevBuf tmpq;
     ALLOC(tmpq, n);
     const lmb200_modality& mod = h->cfg.modalities[index];
     launch_dn_quantize(h->d_depth[index].as<u16>() + (size_t)slot * h->depth_stride, h->depth_stride, tmpq.as<u8>(), n,
@@ -1183,6 +1221,24 @@ int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst
     int rc = give(h->d_dnidx.p, 3 * n);
     tmpq.release();
     return rc;
+  }
+  if (kind == LMB200_DBG_SIMILARITY) {
+    // index = global template index (classes in map order, template_id ascending); the map is computed by the
+    // production coarse kernel (DUMP instantiation: same plan, realignment and packed adds, early exit off)
+    if (index < 0 || index >= h->ntpl) return set_error(h, LMB200_E_INVALID, "bad template index");
+    if (h->plan_dirty || h->templates_dirty) return set_error(h, LMB200_E_INVALID, "template set changed since the last match");
+    const LevelGeom& g = h->levels[L - 1].g;
+    const size_t n = (size_t)g.W * g.H * sizeof(u16);
+    ScopedDevBuf d_map, d_one;
+    ALLOC(d_map, n);
+    ALLOC(d_one, sizeof(int));
+    CU(cudaMemcpyAsync(d_one.p, &index, sizeof(int), cudaMemcpyHostToDevice, st));
+    MatchParams mp = make_match_params(h, slot, 1, h->slot_threshold[slot]);
+    mp.sel = d_one.as<int>(); mp.nsel = 1;
+    launch_similarity_map(mp, make_level_params(h, L - 1, slot, true), 4 * h->max_nf_coarse > 255, d_map.as<u16>(), st);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return give(d_map.p, n);
   }
   return set_error(h, LMB200_E_INVALID, "unknown debug kind");
 }
@@ -1220,7 +1276,7 @@ int add_template_gpu(lmb200_detector* h, const char* class_id, const lmb200_imag
   *template_id = -1;
 
   size_t n0 = (size_t)rows * cols;
-  DevBuf d_src, d_src2, d_q, d_raw, d_mag;
+  ScopedDevBuf d_src, d_src2, d_q, d_raw, d_mag;
   auto cleanup = [&]() { d_src.release(); d_src2.release(); d_q.release(); d_raw.release(); d_mag.release(); };
   std::vector<u8> hq(n0), hmask, hmask_next;
   std::vector<float> hmag(n0);
@@ -1464,6 +1520,10 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double tt[5] = {now(), 0, 0, 0, 0};
   // 1. local overflow check (a rank that overflowed redoes its own template side; no collective involved)
+  {
+    int rc = revalidate_slots(h, first_slot, count);
+    if (rc) return rc;
+  }
   for (;;) {
     CU(cudaMemcpyAsync(h->h_ctr + first_slot, h->d_ctr.as<SlotCtr>() + first_slot, sizeof(SlotCtr) * count, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -47,6 +47,14 @@ struct DevBuf {
   template <typename T> T* as() const { return (T*)p; }
 };
 
+// function-local device buffer: released on every return path (the CU/ALLOC macros return early on errors)
+struct ScopedDevBuf : DevBuf {
+  ScopedDevBuf() = default;
+  ScopedDevBuf(const ScopedDevBuf&) = delete;
+  ScopedDevBuf& operator=(const ScopedDevBuf&) = delete;
+  ~ScopedDevBuf() { release(); }
+};
+
 struct LevelBuffers {
   lmk::LevelGeom g;
   size_t q_stride = 0, lm_stride = 0, bgr_stride = 0, lmn_stride = 0;
@@ -87,6 +95,9 @@ struct lmb200_detector {
   std::string err;
   uint8_t sim_lut[256];
   uint8_t normal_lut[8000];
+  bool normal_lut_standin = true;   // still the built-in stand-in table (capi.cpp:default_normal_lut)
+  bool standin_warned = false;
+  std::string warnings;
 
   // ---- template store (host truth) ----
   std::map<std::string, std::vector<lmh::TemplatePyramid>> classes;
@@ -131,6 +142,7 @@ struct lmb200_detector {
   lmk::SlotCtr* h_ctr = nullptr;
   lmk::Cand* h_out = nullptr; int h_head = 0;      // first h_head records of every slot
   std::vector<float> slot_threshold;
+  std::vector<long long> slot_gen;        // buffer_generation the slot's match results were computed under (-1: none)
   // batches in flight (lmb200_match_batch_submit / _collect)
   lmh::BatchTicket tickets[2];
   std::vector<cudaEvent_t> group_done; std::vector<char> group_used; int b_groups = 0;

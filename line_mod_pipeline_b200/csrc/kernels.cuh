@@ -139,6 +139,8 @@ struct LevelParams {
 
 void launch_similarity_coarse(const MatchParams& mp, const LevelParams& lp, bool wide, cudaStream_t st);
 void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaStream_t st);
+// debug: full u16 coarse similarity map of the single template mp.sel[0] on one frame, early exit disabled
+void launch_similarity_map(const MatchParams& mp, const LevelParams& lp, bool wide, u16* map, cudaStream_t st);
 // Ordered compaction: out[frame][0..n) in generation order, count[frame] = n (may exceed cap -> overflow).
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st);
 

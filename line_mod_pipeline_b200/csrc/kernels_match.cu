@@ -243,6 +243,7 @@ struct CoarseCtx {
   u32 per_label;
   const int* Pm;                     // plan: upstream's template_positions per modality
   const int* ord;                    // this frame's modality order (shared memory)
+  u16* dump;                         // DUMP instantiation: the template's full u16 similarity map [H*W] (pre-zeroed)
   __device__ __forceinline__ int P(int m) const { return __ldg(Pm + m); }
 };
 
@@ -258,7 +259,9 @@ __device__ __forceinline__ int hit_val(const u32* t, int p) {
 // WIDE=true : per-modality byte sums are widened into u16 totals (upstream's addSimilarities).
 // direct=false: count hits and queue them (entries beyond CW_QCAP are dropped, the count continues);
 // direct=true : write Cand records at out[0..) in raster order.
-template <bool SAFE, bool WIDE>
+// DUMP=true (lmb200_debug_fetch(LMB200_DBG_SIMILARITY)): the same accumulation with the early exit switched off; every
+// position's total is written to cx.dump instead of being thresholded (upstream's similarity() + addSimilarities()).
+template <bool SAFE, bool WIDE, bool DUMP = false>
 __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const* s_lm, u32* queue, Cand* out, bool direct, int isel, int lane) {
   int nhit = 0;
   int Pmax = 0;
@@ -314,7 +317,7 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       int later = 0;  // features of the modalities still to come
       for (int k = mi + 1; k < cx.M; ++k) later += cx.hdr.nf(cx.ord[k]);
       const int bound = cx.raw_thr - 4 * later;
-      if (mi + 1 < cx.M && bound >= 0) {  // warp-uniform
+      if (!DUMP && mi + 1 < cx.M && bound >= 0) {  // warp-uniform
         const u32 Kb = (u32)(0x7FFF - bound) * 0x00010001u;
         u32 alive = 0;
         if (WIDE) {
@@ -331,6 +334,12 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
     if (SAFE && tail_once) {
       const int rem = Pmax - pos0;
       if (rem > 0 && rem < 32) NibAcc::mask_tail8(tot, rem);
+    }
+    if (DUMP) {
+#pragma unroll
+      for (int p = 0; p < 32; ++p)
+        if (pos0 + p < cx.HW) cx.dump[pos0 + p] = (u16)hit_val<WIDE>(tot, p);
+      continue;
     }
     u32 any = 0;
     if (WIDE) {
@@ -421,8 +430,8 @@ __device__ __forceinline__ void coarse_template(const MatchParams& mp, const Coa
   }
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kernel(MatchParams mp, LevelParams lp, int tpw) {
+template <bool WIDE, bool DUMP = false>
+__global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kernel(MatchParams mp, LevelParams lp, int tpw, u16* dump = nullptr) {
   __shared__ const u8* s_lm[MAX_MOD];
   __shared__ int s_ord[MAX_MOD];
   __shared__ u32 s_queue[CW_WARPS][CW_QCAP];
@@ -458,13 +467,28 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kern
     cx.lst = s_off[warp];
     cx.Pm = lp.hdr[g].P;
     cx.ord = s_ord;
+    cx.dump = dump;
     __syncwarp();  // the previous template's reads of s_off / s_queue are done
     for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32)
       s_off[warp][s] = __ldg(reinterpret_cast<const uint2*>(lp.offs) + (size_t)g * cx.M * COARSE_SLOTS + s);
     __syncwarp();
+    if (DUMP) {  // one template, no candidate bookkeeping
+      if (cx.hdr.flags & 2u) coarse_sweep<true, WIDE, true>(cx, s_lm, nullptr, nullptr, false, isel, lane);
+      else coarse_sweep<false, WIDE, true>(cx, s_lm, nullptr, nullptr, false, isel, lane);
+      return;
+    }
     if (cx.hdr.flags & 2u) coarse_template<true, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
     else coarse_template<false, WIDE>(mp, cx, s_lm, s_queue[warp], isel, frame, lane);
   }
+}
+
+// Debug path: the production accumulation of ONE template (mp.sel points at its entry, mp.nsel == 1, one frame) with the
+// early exit disabled, totals written to map[H*W] (u16, zero where upstream's similarity() leaves dst untouched).
+void launch_similarity_map(const MatchParams& mp, const LevelParams& lp, bool wide, u16* map, cudaStream_t st) {
+  cudaMemsetAsync(map, 0, (size_t)lp.g.W * lp.g.H * sizeof(u16), st);
+  dim3 grid(1, 1);
+  if (wide) similarity_coarse_kernel<true, true><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp, 1, map);
+  else similarity_coarse_kernel<false, true><<<grid, CW_WARPS * 32, 0, st>>>(mp, lp, 1, map);
 }
 
 // wide: some template has 4*nf_total > 255 at the coarsest level (byte sums across modalities could carry)

@@ -23,6 +23,7 @@ struct Writer {
   gzFile gz = nullptr;
   FILE* fp = nullptr;
   std::string buf;
+  bool failed = false;  // a short write or a failing close: the caller reports LMB200_E_IO
   bool open(const char* path) {
     size_t n = std::strlen(path);
     if (n > 3 && std::strcmp(path + n - 3, ".gz") == 0) gz = gzopen(path, "wb6");
@@ -31,19 +32,20 @@ struct Writer {
   }
   void flush() {
     if (buf.empty()) return;
-    if (gz) gzwrite(gz, buf.data(), (unsigned)buf.size());
-    else std::fwrite(buf.data(), 1, buf.size(), fp);
+    if (gz) { if (gzwrite(gz, buf.data(), (unsigned)buf.size()) != (int)buf.size()) failed = true; }
+    else if (std::fwrite(buf.data(), 1, buf.size(), fp) != buf.size()) failed = true;
     buf.clear();
   }
   void put(const std::string& s) {
     buf += s;
     if (buf.size() > (1u << 20)) flush();
   }
-  void close() {
+  bool close() {  // true when every byte reached the file
     flush();
-    if (gz) gzclose(gz);
-    if (fp) std::fclose(fp);
+    if (gz && gzclose(gz) != Z_OK) failed = true;
+    if (fp && std::fclose(fp) != 0) failed = true;
     gz = nullptr; fp = nullptr;
+    return !failed;
   }
 };
 
@@ -173,7 +175,7 @@ struct ParseState {
   std::vector<int> T;
   std::vector<lmb200_modality> mods;
   // classes
-  struct Cls { std::string id; std::vector<std::string> mod_names; int pyramid_levels = -1; std::vector<TemplatePyramid> tps; };
+  struct Cls { std::string id; bool have_id = false; std::vector<std::string> mod_names; int pyramid_levels = -1; std::vector<TemplatePyramid> tps; };
   std::vector<Cls> classes;
 };
 
@@ -207,19 +209,21 @@ int parse_file(const char* path, ParseState& S, std::string& err) {
       if (s.empty()) continue;
     }
     // flow sequences may wrap over several lines
-    if (s.find('[') != std::string::npos && s.find(']') == std::string::npos) {
-      std::string more;
-      while (s.find(']') == std::string::npos && rd.next(more)) { ++lineno; s += " " + trim(more); }
-    }
     size_t colon = s.find(':');
     if (colon == std::string::npos) continue;
     std::string key = trim(s.substr(0, colon)), val = trim(s.substr(colon + 1));
+    // flow sequences may wrap over several lines: only an unquoted value that opens with '[' continues
+    if (!val.empty() && val[0] == '[' && val.find(']') == std::string::npos) {
+      std::string more;
+      while (val.find(']') == std::string::npos && rd.next(more)) { ++lineno; val += " " + trim(more); }
+    }
     if (key == "classes") { in_classes = true; in_root_modalities = false; continue; }
     if (key == "class_id") {
       in_classes = true; in_root_modalities = false;
-      S.classes.emplace_back();
-      cls = &S.classes.back(); tpl = nullptr;
-      cls->id = unquote(val);
+      // a bare class file may have listed `modalities` first: that pending entry (no id, no templates yet) is this class
+      if (!(cls && cls->id.empty() && !cls->have_id && cls->tps.empty())) { S.classes.emplace_back(); cls = &S.classes.back(); }
+      tpl = nullptr;
+      cls->id = unquote(val); cls->have_id = true;
       continue;
     }
     if (key == "modalities") {
@@ -298,6 +302,16 @@ int parse_file(const char* path, ParseState& S, std::string& err) {
   return LMB200_OK;
 }
 
+int validate_pyramid(const TemplatePyramid& tp, const std::string& what, std::string& err) {
+  for (const Template& t : tp) {
+    if (t.features.size() > 63) { err = what + ": template has more than 63 features (upstream CV_Assert)"; return LMB200_E_FEATURES; }
+    if (t.width < 0 || t.height < 0 || t.width > 32767 || t.height > 32767) { err = what + ": template width/height out of range"; return LMB200_E_IO; }
+    for (const Feature& f : t.features)
+      if (f.label < 0 || f.label > 7) { err = what + ": feature label must be 0..7"; return LMB200_E_IO; }
+  }
+  return LMB200_OK;
+}
+
 int add_parsed_class(lmb200_detector* h, ParseState::Cls& c, const char* override_id, std::string& err) {
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
   if ((int)c.mod_names.size() != M) { err = "class '" + c.id + "': modality count differs from the detector's (upstream CV_Assert)"; return LMB200_E_CLASS; }
@@ -306,8 +320,11 @@ int add_parsed_class(lmb200_detector* h, ParseState::Cls& c, const char* overrid
   if (c.pyramid_levels != L) { err = "class '" + c.id + "': pyramid_levels differs from the detector's"; return LMB200_E_CLASS; }
   std::string id = (override_id && *override_id) ? override_id : c.id;
   if (!(override_id && *override_id) && h->classes.count(id)) { err = "class '" + id + "' already present (upstream CV_Assert)"; return LMB200_E_CLASS; }
-  for (auto& tp : c.tps)
+  for (auto& tp : c.tps) {
     if ((int)tp.size() != M * L) { err = "class '" + id + "': template pyramid has " + std::to_string(tp.size()) + " templates, expected " + std::to_string(M * L); return LMB200_E_IO; }
+    int rc = validate_pyramid(tp, "class '" + id + "'", err);   // the same limits lmb200_add_synthetic_template enforces
+    if (rc) return rc;
+  }
   if (!h->classes.count(id)) h->classes[id] = std::move(c.tps);  // std::map::insert semantics: existing entry wins
   h->templates_dirty = true;
   return LMB200_OK;
@@ -324,7 +341,7 @@ int write_detector_file(lmb200_detector* h, const char* path) {
     w.put("   -\n");
     write_class(w, h, kv.first, kv.second, 6);
   }
-  w.close();
+  if (!w.close()) return set_error(h, LMB200_E_IO, std::string("write error on ") + path + " (disk full?)");
   return LMB200_OK;
 }
 
@@ -335,7 +352,7 @@ int write_class_file(lmb200_detector* h, const std::string& class_id, const char
   if (!w.open(path)) return set_error(h, LMB200_E_IO, std::string("cannot open ") + path + " for writing");
   w.put("%YAML:1.0\n---\n");
   write_class(w, h, it->first, it->second, 0);
-  w.close();
+  if (!w.close()) return set_error(h, LMB200_E_IO, std::string("write error on ") + path + " (disk full?)");
   return LMB200_OK;
 }
 
@@ -411,8 +428,8 @@ int write_cache_file(lmb200_detector* h, const char* path) {
   FILE* fp = std::fopen(path, "wb");
   if (!fp) return set_error(h, LMB200_E_IO, std::string("cannot open ") + path + " for writing");
   size_t w = std::fwrite(b.data(), 1, b.size(), fp);
-  std::fclose(fp);
-  return w == b.size() ? LMB200_OK : set_error(h, LMB200_E_IO, "short write");
+  const bool closed = std::fclose(fp) == 0;
+  return (w == b.size() && closed) ? LMB200_OK : set_error(h, LMB200_E_IO, "short write");
 }
 
 int read_cache_file(const char* path, int device, lmb200_handle* out, std::string& err) {
@@ -449,11 +466,13 @@ int read_cache_file(const char* path, int device, lmb200_handle* out, std::strin
         int32_t w, hh, lv; uint32_t nf;
         if (!get(b, p, w) || !get(b, p, hh) || !get(b, p, lv) || !get(b, p, nf) || nf > 63 || p + 5ull * nf > b.size()) { lmb200_destroy(h); err = "corrupt cache"; return LMB200_E_IO; }
         Template& tm = tps[t][k];
+        if (w < 0 || hh < 0 || w > 32767 || hh > 32767) { lmb200_destroy(h); err = "corrupt cache (template size)"; return LMB200_E_IO; }
         tm.width = w; tm.height = hh; tm.pyramid_level = lv;
         tm.features.resize(nf);
         for (uint32_t i = 0; i < nf; ++i) {
           int16_t x = 0, y = 0; uint8_t l = 0;
           get(b, p, x); get(b, p, y); get(b, p, l);
+          if (l > 7) { lmb200_destroy(h); err = "corrupt cache (feature label > 7)"; return LMB200_E_IO; }
           tm.features[i] = Feature{x, y, l};
         }
       }
@@ -519,14 +538,14 @@ int lmb200_write_pose_sidecar(const char* path, const lmb200_template_pose* cons
   FILE* fp = std::fopen(path, "wb");
   if (!fp) return LMB200_E_IO;
   uint32_t ncls = (uint32_t)n_classes;
-  std::fwrite(&ncls, sizeof ncls, 1, fp);
-  for (int c = 0; c < n_classes; ++c) {
+  bool ok = std::fwrite(&ncls, sizeof ncls, 1, fp) == 1;
+  for (int c = 0; c < n_classes && ok; ++c) {
     uint64_t n = counts[c];
-    std::fwrite(&n, sizeof n, 1, fp);
-    if (n) std::fwrite(per_class[c], sizeof(lmb200_template_pose), (size_t)n, fp);
+    ok = std::fwrite(&n, sizeof n, 1, fp) == 1;
+    if (ok && n) ok = std::fwrite(per_class[c], sizeof(lmb200_template_pose), (size_t)n, fp) == (size_t)n;
   }
-  std::fclose(fp);
-  return LMB200_OK;
+  if (std::fclose(fp) != 0) ok = false;
+  return ok ? LMB200_OK : LMB200_E_IO;
 }
 
 }  // extern "C"

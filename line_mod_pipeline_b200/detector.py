@@ -67,7 +67,8 @@ def _cstr_array(ids):
 class Detector:
     """Detector(modalities, T_pyramid) — see getDefaultLINE / getDefaultLINEMOD for the reference's two wirings."""
 
-    def __init__(self, modalities=None, T_pyramid=(5, 8), device=-1, max_batch=0, candidate_capacity=0, _handle=None):
+    def __init__(self, modalities=None, T_pyramid=(5, 8), device=-1, max_batch=0, candidate_capacity=0, similarity_lut=0,
+                 _handle=None):
         self._L = K.lib()
         self._h = K._H()
         if _handle is not None:
@@ -85,6 +86,7 @@ class Detector:
         cfg.device = device
         cfg.max_batch = max_batch
         cfg.candidate_capacity = candidate_capacity
+        cfg.similarity_lut = similarity_lut     # K.SIMLUT_CIRCULAR (default, upstream's table) | K.SIMLUT_LINEAR
         rc = self._L.lmb200_create(C.byref(cfg), C.byref(self._h))
         if rc:
             raise LinemodError(rc, (self._L.lmb200_last_error(None) or b"").decode("utf-8", "replace"))
@@ -419,7 +421,30 @@ class Detector:
             return buf.view(np.float32)
         if kind == K.DBG_DN_INDICES:
             return buf.view(np.int8)
+        if kind == K.DBG_SIMILARITY:
+            return buf.view(np.uint16)
         return buf
+
+    def similarityMap(self, class_id, template_id, slot=0):
+        """u16 coarse-level similarity map (upstream similarity() + addSimilarities()) of one template on the frame last
+        matched in `slot`, from the production kernel with its early exit disabled (LMB200_DBG_SIMILARITY)."""
+        g = 0
+        for cid in self.classIds():
+            if cid == class_id:
+                break
+            g += self.numTemplates(cid)
+        else:
+            raise KeyError(class_id)
+        return self.debugFetch(K.DBG_SIMILARITY, slot, g + int(template_id))
+
+    def normalLutIsStandin(self):
+        return bool(self._L.lmb200_normal_lut_is_standin(self._h))
+
+    def loadNormalLut(self, path):
+        self._check(self._L.lmb200_load_normal_lut(self._h, str(path).encode()))
+
+    def warnings(self):
+        return (self._L.lmb200_warnings(self._h) or b"").decode()
 
 
 def getDefaultLINE(**kw):

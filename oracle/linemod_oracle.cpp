@@ -419,10 +419,11 @@ static void spread(const u8* src, int rows, int cols, int T, u8* dst) {
 
 // SIMILARITY_LUT[32*ori + nibble] (low nibble = orientations 0..3) and [32*ori+16+nibble]
 // (high nibble = orientations 4..7): max over set bits j of max(0, 4 - dist(ori, j)).
-// circular=0: dist = |ori-j|  — the table upstream ships (as recalled: ori 0 has an all-zero
-//             high-nibble half, ori 7 an all-zero low-nibble half).  DEFAULT.
-// circular=1: dist = min(|ori-j|, 8-|ori-j|) — the formula SURVEY.md §8c G6 hashed; kept so the
-//             survey's G3/G4 response/linear-memory hashes can be reproduced.
+// circular=1: dist = min(|ori-j|, 8-|ori-j|) — DEFAULT.  The formula SURVEY.md §8c G6 hashed (sum 628, sha1
+//             de1dd710...); the 256-entry literal of upstream's table as recalled independently in round 2
+//             (tests/golden/similarity_lut_recalled.json) is byte-identical to it: orientations are angles
+//             modulo 180 degrees, so bins 0 and 7 are neighbours.
+// circular=0: dist = |ori-j| (sum 528) — round 1's default; kept selectable (lmb200_config.similarity_lut = 1).
 static void similarity_lut(int circular, u8* out) {
   for (int ori = 0; ori < 8; ++ori)
     for (int half = 0; half < 2; ++half)
@@ -1016,7 +1017,7 @@ void* lmo_create(int n_mod, const int* types, const float* fparams, const int* i
   d->levels = levels;
   d->T.assign(T, T + levels);
   if (sim_lut) std::memcpy(d->sim_lut, sim_lut, 256);
-  else similarity_lut(0, d->sim_lut);
+  else similarity_lut(1, d->sim_lut);
   if (normal_lut) d->normal_lut.assign(normal_lut, normal_lut + 8000);
   d->fused_atan = fused_atan;
   return d;
@@ -1106,6 +1107,31 @@ void lmo_result_stats(void* r, double* out5) {
   out5[0] = R->t_frame; out5[1] = R->t_match; out5[2] = R->t_sort;
   out5[3] = (double)R->bytes_coarse; out5[4] = (double)R->bytes_local;
 }
+// [UP] similarity() per modality + addSimilarities() at the coarsest level: the full u16 map matchClass thresholds
+// (SURVEY.md 8d parity gate "similarity maps").  Needs a result of lmo_match(..., debug=1) (linear memories kept).
+// out: [H*W] u16, returns H*W; -1 unknown class/template, -2 result holds no linear memories.
+long lmo_result_similarity_map(void* h, void* r, const char* class_id, int template_id, u16* out) {
+  Detector* d = (Detector*)h;
+  MatchResult* R = (MatchResult*)r;
+  auto it = d->classes.find(class_id);
+  if (it == d->classes.end() || template_id < 0 || template_id >= (int)it->second.size()) return -1;
+  const int M = (int)d->modalities.size(), Lc = d->levels - 1;
+  if ((int)R->mems.size() != d->levels * M || R->mems[(size_t)Lc * M].lm.empty()) return -2;
+  const TemplatePyramid& tp = it->second[template_id];
+  const LevelMem& L0 = R->mems[(size_t)Lc * M];
+  const size_t n = (size_t)L0.W * L0.H;
+  if (!out) return (long)n;
+  std::vector<u8> sim(n);
+  std::fill(out, out + n, (u16)0);
+  for (int m = 0; m < M; ++m) {
+    std::fill(sim.begin(), sim.end(), 0);
+    similarity(R->mems[(size_t)Lc * M + m], tp[(size_t)Lc * M + m], sim.data());
+    for (size_t j = 0; j < n; ++j) out[j] = (u16)(out[j] + sim[j]);
+  }
+  return (long)n;
+}
+void lmo_get_similarity_lut(void* h, u8* out256) { std::memcpy(out256, ((Detector*)h)->sim_lut, 256); }
+
 int lmo_max_threads() {
   unsigned n = std::thread::hardware_concurrency();
   return n ? (int)n : 1;

@@ -277,6 +277,21 @@ class Detector:
         self._L.lmo_get_template_flat(C.c_void_p(self._h), class_id.encode(), template_id, _p(out), n)
         return out
 
+    def similarity_lut(self):
+        out = np.empty(256, np.uint8)
+        self._L.lmo_get_similarity_lut(C.c_void_p(self._h), _p(out))
+        return out
+
+    def similarity_map(self, result, class_id, template_id):
+        """u16 [H, W] coarse-level map of `similarity` + `addSimilarities` for one template (result of match(debug=True))."""
+        self._L.lmo_result_similarity_map.restype = C.c_long
+        n = self._L.lmo_result_similarity_map(C.c_void_p(self._h), C.c_void_p(result._r), class_id.encode(), int(template_id), None)
+        if n < 0:
+            raise KeyError((class_id, template_id, n))
+        out = np.empty(n, np.uint16)
+        self._L.lmo_result_similarity_map(C.c_void_p(self._h), C.c_void_p(result._r), class_id.encode(), int(template_id), _p(out))
+        return out
+
     def match(self, sources, threshold, class_ids=(), masks=None, threads=1, debug=False):
         arrs, ptrs = self._srcs(sources)
         r, c = arrs[0].shape[:2]

@@ -65,15 +65,49 @@ def test_detector_surface_host_side():
 def test_tables():
     d = lm.getDefaultLINEMOD()
     lut = d.getSimilarityLut()
-    assert lut[:16].tolist() == [0, 4, 3, 4, 2, 4, 3, 4, 1, 4, 3, 4, 2, 4, 3, 4] and int(lut.sum()) == 528
+    # default = circular distance (sum 628); the linear variant is explicit in lmb200_config
+    assert lut[:16].tolist() == [0, 4, 3, 4, 2, 4, 3, 4, 1, 4, 3, 4, 2, 4, 3, 4] and int(lut.sum()) == 628
+    assert lut[16:32].tolist() == [0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3]
+    dl = lm.getDefaultLINEMOD(similarity_lut=K.SIMLUT_LINEAR)
+    assert int(dl.getSimilarityLut().sum()) == 528 and not dl.getSimilarityLut()[16:32].any()
     assert np.array_equal(d.getNormalLut(), synth.default_normal_lut())
     with pytest.raises(lm.LinemodError):
         d.setNormalLut(np.full(8000, 3, np.uint8))       # not one-hot
     with pytest.raises(lm.LinemodError):
         d.setSimilarityLut(np.full(256, 5, np.uint8))    # 63 * 5 would overflow a byte
     from oracle import oracle as O
-    d.setSimilarityLut(O.similarity_lut(1))
     assert np.array_equal(d.getSimilarityLut(), O.similarity_lut(1))
+    d.setSimilarityLut(O.similarity_lut(0))
+    assert np.array_equal(d.getSimilarityLut(), O.similarity_lut(0))
+
+
+def test_normal_lut_provenance_and_loader(tmp_path):
+    """The stand-in NORMAL_LUT is never silent: the handle says so, and upstream's normal_lut.i (C initialiser text) or a
+    raw 8000-byte file replaces it."""
+    d = lm.getDefaultLINEMOD()
+    assert d.normalLutIsStandin()
+    rng = np.random.default_rng(0)
+    lut = (1 << rng.integers(0, 8, 8000)).astype(np.uint8)
+    lut[::97] = 0
+    rows = lut.reshape(20, 20, 20)
+    txt = "// generated\n#define GRANULARITY 20\nstatic unsigned char NORMAL_LUT[20][20][20] = {\n"
+    txt += ",\n".join("{" + ", ".join("{" + ", ".join(str(int(v)) for v in r) + "}" for r in plane) + "}" for plane in rows) + "};\n"
+    p = tmp_path / "normal_lut.i"
+    p.write_text(txt)
+    d.loadNormalLut(p)
+    assert not d.normalLutIsStandin() and np.array_equal(d.getNormalLut(), lut)
+    d2 = lm.getDefaultLINEMOD()
+    (tmp_path / "lut.bin").write_bytes(lut.tobytes())
+    d2.loadNormalLut(tmp_path / "lut.bin")
+    assert np.array_equal(d2.getNormalLut(), lut)
+    (tmp_path / "bad.i").write_text("static unsigned char NORMAL_LUT[2] = {1, 2};")
+    with pytest.raises(lm.LinemodError) as e:
+        lm.getDefaultLINEMOD().loadNormalLut(tmp_path / "bad.i")
+    assert e.value.code == K.E_IO
+    d3 = lm.getDefaultLINEMOD()
+    d3.setNormalLut(synth.default_normal_lut())
+    assert not d3.normalLutIsStandin()
+    assert lm.getDefaultLINE().warnings() == ""
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")

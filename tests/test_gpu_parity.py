@@ -43,15 +43,16 @@ def test_frame_side_fixture_golden(fixture_frame, golden):
     q1 = det.debugFetch(K.DBG_QUANTIZED, 0, 2)
     assert sha(q0) == golden["G2G3_L0_T5"]["quantized_sha1"] == "f45507458cb4ef60bbf11099074023f5ddf0bc5d"
     assert sha(q1) == golden["G4_L1_T8"]["quantized_sha1"]
-    assert sha(det.debugFetch(K.DBG_LINMEM, 0, 0)) == golden["G2G3_L0_T5"]["lut0"]["linmem_sha1"]
-    assert sha(det.debugFetch(K.DBG_LINMEM, 0, 2)) == golden["G4_L1_T8"]["lut0"]["linmem_sha1"]
+    # default table = the circular SIMILARITY_LUT: the survey's G3/G4 linear-memory hashes
+    assert sha(det.debugFetch(K.DBG_LINMEM, 0, 0)) == golden["G2G3_L0_T5"]["lut1"]["linmem_sha1"] == "89d3edac27207763163c79a2eb205f6f0750ca75"
+    assert sha(det.debugFetch(K.DBG_LINMEM, 0, 2)) == golden["G4_L1_T8"]["lut1"]["linmem_sha1"] == "b3fd1e4644625c962aa0d22da8a22f751270e4f6"
     assert sha(det.debugFetch(K.DBG_MAGNITUDE, 0, 0)) == golden["G2G3_L0_T5"]["magnitude_sha1"]
     assert sha(det.debugFetch(K.DBG_DN_INDICES, 0, 1)) == golden["G5_dn_indices"]["sha1"]
-    # the survey hashed linear memories under the circular LUT: reproduce those too
-    det2, ora2 = make_pair(sim_lut=O.similarity_lut(1))
+    # the linear variant (lmb200_config.similarity_lut = LMB200_SIMLUT_LINEAR) stays selectable
+    det2, ora2 = make_pair(sim_lut=O.similarity_lut(0))
     det2.match([bgr, depth], 80.0)
-    assert sha(det2.debugFetch(K.DBG_LINMEM, 0, 0)) == "89d3edac27207763163c79a2eb205f6f0750ca75"
-    assert sha(det2.debugFetch(K.DBG_LINMEM, 0, 2)) == "b3fd1e4644625c962aa0d22da8a22f751270e4f6"
+    assert sha(det2.debugFetch(K.DBG_LINMEM, 0, 0)) == golden["G2G3_L0_T5"]["lut0"]["linmem_sha1"]
+    assert sha(det2.debugFetch(K.DBG_LINMEM, 0, 2)) == golden["G4_L1_T8"]["lut0"]["linmem_sha1"]
 
 
 @pytest.mark.parametrize("idx", [0, 1, 2])
@@ -495,3 +496,101 @@ def test_non_default_modality_parameters():
         got, ref = _check_frame_side(det, ora, [bgr, depth], thr, n_maps=4)
         assert_same_matches(got, ref.matches(0), "non-default parameters thr=%g" % thr)
     assert len(got) > 0
+
+
+def _check_similarity_maps(det, ora, ref, picks, what):
+    """SURVEY 8d parity gate: full u16 coarse similarity map (similarity() per modality + addSimilarities()) of sampled
+    templates — production kernel with the early exit disabled vs the oracle."""
+    for cid, tid in picks:
+        got = det.similarityMap(cid, tid)
+        want = ora.similarity_map(ref, cid, tid)
+        assert got.shape == want.shape, "%s: map shape %r vs %r" % (what, got.shape, want.shape)
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, "%s: similarity map of %s/%d differs at %d positions, first %d (%d vs %d)" % (
+            what, cid, tid, bad.size, bad[0], got[bad[0]], want[bad[0]])
+
+
+def _sample_templates(det, n, seed):
+    rng = np.random.default_rng(seed)
+    allt = [(cid, t) for cid in det.classIds() for t in range(det.numTemplates(cid))]
+    idx = rng.choice(len(allt), size=min(n, len(allt)), replace=False)
+    return [allt[i] for i in sorted(idx)]
+
+
+def test_similarity_maps_config2(cfg2_small):
+    det, ora, bgr, depth = cfg2_small
+    det.match([bgr, depth], 80.0)
+    ref = ora.match([bgr, depth], 80.0, threads=8, debug=True)
+    picks = [("planted", t) for t in range(min(8, det.numTemplates("planted")))] + _sample_templates(det, 32, 1)
+    _check_similarity_maps(det, ora, ref, picks, "config 2")
+    # the planted templates must peak at 4 * nf (a perfect match on their own frame)
+    m = det.similarityMap("planted", 0)
+    assert int(m.max()) == 4 * sum(len(t["features"]) for t in det.getTemplates("planted", 0)[2:4])
+
+
+def test_similarity_maps_config1(fixture_frame):
+    import os
+    bgr, depth = fixture_frame
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagergehaeuse_templates.yml.gz")
+    det = lm.Detector.read(path)
+    ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
+    for t in range(1950):
+        ora.add_synthetic(det.getTemplates("lagergehaeuse.ply", t), "lagergehaeuse.ply")
+    det.match([bgr, depth], 80.0)
+    ref = ora.match([bgr, depth], 80.0, threads=16, debug=True)
+    _check_similarity_maps(det, ora, ref, _sample_templates(det, 32, 2), "config 1")
+
+
+def test_similarity_maps_cg_only_and_wide_sums():
+    """{CG} T={2,8} (the shipped yml default) and a single-level pyramid whose sums need u16 (WIDE instantiation)."""
+    bgr, depth = synth.make_frame(2)
+    det, ora = make_pair(modalities=("cg",), T=(2, 8))
+    add_planted_from_oracle(det, ora, [bgr], synth.object_masks(2))
+    add_random(det, ora, 60, n_modalities=1)
+    det.match([bgr], 70.0)
+    ref = ora.match([bgr], 70.0, debug=True)
+    _check_similarity_maps(det, ora, ref, _sample_templates(det, 32, 3), "{CG} T={2,8}")
+    det, ora = make_pair(T=(8,))
+    add_random(det, ora, 40, levels=1)
+    det.match([bgr, depth], 60.0)
+    ref = ora.match([bgr, depth], 60.0, debug=True)
+    _check_similarity_maps(det, ora, ref, _sample_templates(det, 32, 4), "single level, u16 sums")
+
+
+def test_config5_full_10000_templates():
+    """BASELINE config 5 at its full size: 1920x1088, T={4,8,16}, 10 000 templates; final lists + sampled similarity maps."""
+    rows, cols = 1088, 1920
+    bgr, depth = synth.make_frame(7, 1080, cols, n_shapes=60)
+    bgr = np.concatenate([bgr, np.zeros((8, cols, 3), np.uint8)], 0)
+    depth = np.concatenate([depth, np.zeros((8, cols), np.uint16)], 0)
+    det, ora = make_pair(T=(4, 8, 16), max_batch=2)
+    masks = [np.concatenate([m, np.zeros((8, cols), np.uint8)], 0) for m in synth.object_masks(7, 1080, cols, n_shapes=60, min_px=4000)]
+    n = add_planted_from_oracle(det, ora, [bgr, depth], masks[:12])
+    add_random(det, ora, 10000 - n, levels=3, wh_range=(80, 300))
+    assert det.numTemplates() == 10000
+    got = det.match([bgr, depth], 80.0)
+    ref = ora.match([bgr, depth], 80.0, threads=16, debug=True)
+    assert_same_matches(got, ref.matches(0), "config 5, 10 000 templates")
+    assert len(got) > 0
+    _check_similarity_maps(det, ora, ref, _sample_templates(det, 32, 5), "config 5")
+
+
+def test_resident_ranges_survive_store_growth():
+    """several lmb200_match_resident ranges in flight; the first fetch overflows the candidate store and grows
+    it — the other ranges (computed into the old stores) must be re-matched at their own thresholds, not read stale."""
+    det, ora = make_pair(candidate_capacity=64, max_batch=8)
+    bgr, depth = synth.make_frame(0)
+    add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(0))
+    add_random(det, ora, 100)
+    frames = [list(synth.make_frame(i)) for i in range(6)]
+    det.uploadFrames(frames, 0)
+    det.matchResident(0, 2, 20.0)     # overflows 64 candidates
+    det.matchResident(2, 2, 85.0)     # fits
+    det.matchResident(4, 2, 25.0)     # overflows
+    r0 = det.fetchResident(0, 2, cap=400000)     # grows the stores under ranges 2..5
+    r1 = det.fetchResident(2, 2, cap=400000)
+    r2 = det.fetchResident(4, 2, cap=400000)
+    for res, first, thr in ((r0, 0, 20.0), (r1, 2, 85.0), (r2, 4, 25.0)):
+        for i in range(2):
+            want = ora.match(frames[first + i], thr, threads=8).matches(0)
+            assert_same_matches(res[i], want, "resident range at slot %d thr=%g" % (first + i, thr))

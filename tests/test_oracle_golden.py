@@ -49,7 +49,7 @@ def test_G2_G3_level0(fixture_frame, golden):
     assert sha(resp) == SURVEY["G3_resp"]
     lm = np.stack([O.linearize(resp[o], 5) for o in range(8)])
     assert lm.shape == (8, 25, 12288) and sha(lm) == SURVEY["G3_lm"]
-    # default (upstream-as-shipped, non-circular) table, pinned by make_golden.py's numpy restatement
+    # the linear (non-circular) variant, pinned by make_golden.py's numpy restatement
     resp0 = O.response(sp, O.similarity_lut(0))
     assert sha(resp0) == golden["G2G3_L0_T5"]["lut0"]["response_sha1"]
     lm0 = np.stack([O.linearize(resp0[o], 5) for o in range(8)])
@@ -81,6 +81,11 @@ def test_G6_similarity_lut(golden):
     circ, lin = O.similarity_lut(1), O.similarity_lut(0)
     assert sha(circ) == SURVEY["G6"] and int(circ.sum()) == 628
     assert sha(lin) == golden["G6_similarity_lut"]["linear_sha1"]
-    # the table upstream ships (recalled): orientation 0 has an all-zero high-nibble half
+    # the linear variant: orientation 0 has an all-zero high-nibble half
     assert lin[:16].tolist() == [0, 4, 3, 4, 2, 4, 3, 4, 1, 4, 3, 4, 2, 4, 3, 4] and not lin[16:32].any()
     assert lin[32:64].tolist() == [0, 3, 4, 4, 3, 3, 4, 4, 2, 3, 4, 4, 3, 3, 4, 4] + [0, 1] * 8
+    # upstream's literal table as recalled in round 2 == the circular table == the oracle's default
+    import json, os
+    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "similarity_lut_recalled.json")))["table"]
+    assert len(rec) == 256 and rec == circ.tolist()
+    assert O.Detector([dict(type=O.CG)], [5, 8]).similarity_lut().tolist() == rec

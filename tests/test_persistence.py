@@ -292,3 +292,72 @@ def test_corrupted_files_fail_cleanly(tmp_path):
     for ci in (0, 1):
         with pytest.raises(lm.LinemodError):
             lm.read_pose_sidecar(side, ci)
+
+
+def test_class_id_with_bracket_round_trips(tmp_path):
+    """a quoted class_id containing '[' must not be mistaken for a wrapped flow sequence."""
+    d = lm.getDefaultLINEMOD()
+    for i, tp in enumerate(synth.random_templates(4, seed=8)):
+        d.addSyntheticTemplate(tp, "a[b" if i % 2 else "c]d [e")
+    path = str(tmp_path / "brackets.yml.gz")
+    d.write(path)
+    _same(d, lm.Detector.read(path))
+    cv2 = pytest.importorskip("cv2")
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+    ids = sorted(fs.getNode("classes").at(i).getNode("class_id").string() for i in range(2))
+    assert ids == ["a[b", "c]d [e"]
+
+
+def test_bare_class_file_with_modalities_before_class_id(tmp_path):
+    """key order inside a map is free: `modalities` listed before `class_id` is one class, not two."""
+    d = lm.getDefaultLINEMOD()
+    tps = synth.random_templates(2, seed=9)
+    for tp in tps:
+        d.addSyntheticTemplate(tp, "obj")
+    p = str(tmp_path / "templates_obj.yml")
+    d.writeClass("obj", p)
+    lines = open(p).read().split("\n")
+    ci = next(i for i, l in enumerate(lines) if l.startswith("class_id"))
+    mi = next(i for i, l in enumerate(lines) if l.startswith("modalities"))
+    assert ci < mi
+    lines[ci], lines[mi] = lines[mi], lines[ci]
+    q = str(tmp_path / "swapped.yml")
+    open(q, "w").write("\n".join(lines))
+    e = lm.getDefaultLINEMOD()
+    e.readClass(q)
+    _same(d, e)
+
+
+def test_loaded_templates_are_validated(tmp_path):
+    """> 63 features or a label outside 0..7 is refused at READ time with upstream's error class, not at the
+    next match."""
+    d = lm.getDefaultLINEMOD()
+    d.addSyntheticTemplate(synth.random_templates(1, seed=10)[0], "obj")
+    p = str(tmp_path / "t.yml")
+    d.write(p)
+    txt = open(p).read()
+    first = txt.index("- [")
+    line = txt[first:txt.index("\n", first)]
+    bad_label = txt.replace(line, "- [ 3, 4, 9 ]", 1)
+    open(str(tmp_path / "label.yml"), "w").write(bad_label)
+    with pytest.raises(lm.LinemodError) as e:
+        lm.Detector.read(str(tmp_path / "label.yml"))
+    assert e.value.code == K.E_IO
+    many = txt.replace(line, "\n".join([line] * 70), 1)
+    open(str(tmp_path / "many.yml"), "w").write(many)
+    with pytest.raises(lm.LinemodError) as e:
+        lm.Detector.read(str(tmp_path / "many.yml"))
+    assert e.value.code == K.E_FEATURES
+
+
+def test_write_errors_are_reported(tmp_path):
+    """a failing write is an error, not a silently truncated template file (/dev/full: every write fails)."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    d = lm.getDefaultLINEMOD()
+    _fill(d, 40)
+    with pytest.raises(lm.LinemodError) as e:
+        d.write("/dev/full")
+    assert e.value.code == K.E_IO
+    with pytest.raises(lm.LinemodError):
+        d.writeCache("/dev/full")
