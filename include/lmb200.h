@@ -258,6 +258,15 @@ int lmb200_comm_destroy(lmb200_handle h);
  * Template-sharded mode: all ranks hold the same frames. */
 int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, int count,
                                     lmb200_match_rec* out, size_t cap, size_t* offsets);
+/* The same template-sharded step with the expensive half of the frame side sharded as well: rank r quantises only the
+ * frame block [first + r*n, first + (r+1)*n) (n = count / world) — so only those frames have to be uploaded on rank r —
+ * the quantized maps are all-gathered in place over NVLink (one NCCL group), and every rank spreads all frames and
+ * scores its template shard.  Needs lmb200_comm_init + lmb200_set_template_shard with the same rank/world; count not a
+ * multiple of world falls back to lmb200_match_resident (replicated frame side).  Follow with
+ * lmb200_fetch_resident_allgather, which also distributes the host epilogue (rank r sorts/uniques its frame block, a
+ * second small all-gather shares the finished lists). */
+int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, float threshold,
+                                  const char* const* class_ids, int n_class_ids);
 /* Pure host helper (no GPU): merge per-rank, generation-ordered partial lists exactly as above.
  * parts[r] has counts[r] records.  Used by the gloo CPU tests and by callers with their own transport. */
 int lmb200_merge_matches(const lmb200_match_rec* const* parts, const size_t* counts, int world,
@@ -278,9 +287,25 @@ typedef struct {
   long long bytes_local;              /* algorithmic bytes gathered by similarityLocal (sum nf*256) */
   long long frames;
   long long candidates, matches;
+  long long chunks_coarse;            /* 16-byte chunk loads the coarse kernel actually issued (after its early exit) */
 } lmb200_profile;
+/* Measurement knobs.  "early_exit" (default 1): 0 switches off the coarse kernel's exact early exit (results are
+ * identical either way; the bench reports both so the workload dependence of the exit is visible).
+ * "upload_async" (default 0): 1 makes lmb200_upload_frames return without synchronising (pinned host frames that stay
+ * valid until the results of the next match on those slots have been fetched). */
+int lmb200_set_option(lmb200_handle h, const char* name, int value);
 int lmb200_set_profiling(lmb200_handle h, int enabled);        /* CUDA events around every launch */
 int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset);
+
+/* Measured roofs of the device the library runs on (csrc/microbench.cu): achieved GB/s of
+ *   L2_READ : 128-bit loads streaming an L2-resident buffer with L1 bypassed (the similarity kernels' L2 roof),
+ *   L1_READ : 128-bit loads re-reading an L1-resident window per CTA (their L1 data-pipe roof),
+ *   HBM_READ: the same stream over 2 GiB,
+ *   H2D     : cudaMemcpyAsync from pinned host memory (roof of the streamed end-to-end path; call it on every rank
+ *             at once to get the shared-host figure).
+ * bytes = 0 picks the default size of each kind; the result is the best of `iters` timed launches (H2D: their mean). */
+enum { LMB200_MB_L2_READ = 0, LMB200_MB_L1_READ = 1, LMB200_MB_HBM_READ = 2, LMB200_MB_H2D = 3 };
+int lmb200_microbench(int kind, size_t bytes, int iters, double* gbps);
 
 enum { LMB200_DBG_QUANTIZED = 0, LMB200_DBG_LINMEM = 1, LMB200_DBG_COARSE = 2, LMB200_DBG_UNSORTED = 3,
        LMB200_DBG_MAGNITUDE = 4, LMB200_DBG_DN_INDICES = 5, LMB200_DBG_SIMILARITY = 6 };

@@ -9,6 +9,7 @@ MAX_MOD, MAX_LEVELS = 4, 8
 T_8UC1, T_16UC1, T_8UC3 = 0, 2, 16
 COLOR_GRADIENT, DEPTH_NORMAL = 0, 1
 SIMLUT_CIRCULAR, SIMLUT_LINEAR = 0, 1
+MB_L2_READ, MB_L1_READ, MB_HBM_READ, MB_H2D = range(4)
 OK, E_INVALID, E_SOURCES, E_SIZE, E_FEATURES, E_CLASS, E_IO, E_CUDA, E_TRUNCATED, E_COMM, E_NODEVICE = range(0, -11, -1)
 K_NAMES = ["upload", "pyrdown", "cg_quantize", "dn_quantize", "median", "decimate", "linearize",
            "sim_coarse", "sim_local", "pack"]
@@ -48,7 +49,7 @@ class MatchRec(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * 10), ("launches", C.c_longlong * 10), ("bytes_coarse", C.c_longlong),
                 ("bytes_local", C.c_longlong), ("frames", C.c_longlong), ("candidates", C.c_longlong),
-                ("matches", C.c_longlong)]
+                ("matches", C.c_longlong), ("chunks_coarse", C.c_longlong)]
 
 
 class Mesh(C.Structure):
@@ -108,6 +109,7 @@ SIGNATURES = {
     "lmb200_match_batch_collect": (C.c_int, [_H, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_upload_frames": (C.c_int, [_H, _P(Image), C.c_int, C.c_int, C.c_int]),
     "lmb200_match_resident": (C.c_int, [_H, C.c_int, C.c_int, C.c_float, _P(C.c_char_p), C.c_int]),
+    "lmb200_match_resident_sharded": (C.c_int, [_H, C.c_int, C.c_int, C.c_float, _P(C.c_char_p), C.c_int]),
     "lmb200_fetch_resident": (C.c_int, [_H, C.c_int, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_synchronize": (C.c_int, [_H]),
     "lmb200_stream": (C.c_void_p, [_H]),
@@ -129,8 +131,10 @@ SIGNATURES = {
     "lmb200_fetch_resident_allgather": (C.c_int, [_H, C.c_int, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_merge_matches": (C.c_int, [_P(_P(MatchRec)), _P(C.c_size_t), C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_shard_plan": (C.c_int, [_P(C.c_double), C.c_int, C.c_int, _P(C.c_int)]),
+    "lmb200_set_option": (C.c_int, [_H, C.c_char_p, C.c_int]),
     "lmb200_set_profiling": (C.c_int, [_H, C.c_int]),
     "lmb200_get_profile": (C.c_int, [_H, _P(Profile), C.c_int]),
+    "lmb200_microbench": (C.c_int, [C.c_int, C.c_size_t, C.c_int, _P(C.c_double)]),
     "lmb200_debug_fetch": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_size_t)]),
 }
 

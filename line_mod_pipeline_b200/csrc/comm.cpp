@@ -22,11 +22,13 @@ typedef int (*fn_init_rank)(void**, int, ncclUniqueId_t, int);
 typedef int (*fn_destroy)(void*);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
+typedef int (*fn_group)(void);
 
 struct Nccl {
   void* lib = nullptr;
   fn_get_uid get_uid = nullptr; fn_init_rank init_rank = nullptr; fn_destroy destroy = nullptr;
   fn_allgather allgather = nullptr; fn_errstr errstr = nullptr;
+  fn_group group_start = nullptr, group_end = nullptr;
   std::string err;
 };
 Nccl g_nccl;
@@ -43,6 +45,8 @@ void load_nccl() {
   g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.allgather = (fn_allgather)dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allgather) g_nccl.err = "libnccl lacks a required symbol";
 }
 bool nccl_ok(std::string& err) {
@@ -89,6 +93,16 @@ int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t byte
   if (!h->nccl_comm) return set_error(h, LMB200_E_COMM, "communicator not initialised (lmb200_comm_init)");
   int rc = g_nccl.allgather(send, recv, bytes, /*ncclInt8*/ 0, h->nccl_comm, st);
   if (rc) return set_error(h, LMB200_E_COMM, nccl_msg("ncclAllGather", rc));
+  return LMB200_OK;
+}
+
+// several collectives fused into one NCCL launch (optional: absent symbols make these no-ops)
+int comm_group_begin(lmb200_detector* h) {
+  if (g_nccl.group_start) { int rc = g_nccl.group_start(); if (rc) return set_error(h, LMB200_E_COMM, nccl_msg("ncclGroupStart", rc)); }
+  return LMB200_OK;
+}
+int comm_group_end(lmb200_detector* h) {
+  if (g_nccl.group_end) { int rc = g_nccl.group_end(); if (rc) return set_error(h, LMB200_E_COMM, nccl_msg("ncclGroupEnd", rc)); }
   return LMB200_OK;
 }
 

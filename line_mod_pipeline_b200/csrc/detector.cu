@@ -250,6 +250,11 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
   rc = rebuild_templates(h);
   if (rc) return rc;
   const int S = h->cfg.max_batch > 0 ? h->cfg.max_batch : 64;
+  {
+    const char* e = std::getenv("LMB200_GENERIC_FRAME");
+    const bool gen = e && *e && *e != '0';
+    if (gen != h->generic_frame_side) { h->generic_frame_side = gen; h->rows = 0; }  // re-plan
+  }
   bool geom_changed = rows != h->rows || cols != h->cols || S != h->slots || (int)h->levels.size() != L;
   if (geom_changed) {
     // validate like upstream's CV_Asserts (linearize: rows%T, cols%T; computeResponseMaps: (rows*cols)%16)
@@ -286,6 +291,9 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
       lb.g.strips = l == L - 1 ? 0 : (lb.g.W + 15) / 16;
       lb.g.plane = lb.g.strips ? (u32)lb.g.strips * lb.g.H * 16u : (u32)lb.g.W * lb.g.H;
       lb.g.per_label = (u32)T * T * lb.g.plane;
+      lb.fast_spread = spread_fast_covers(lb.g) && !h->generic_frame_side;
+      // DepthNormalPyramid::pyrDown is resize(INTER_NEAREST) to (cols/2, rows/2): src[2y][2x] exactly while the sizes stay even
+      lb.dn_inplace = l == 0 ? true : (h->levels[l - 1].dn_inplace && h->levels[l - 1].g.rows % 2 == 0 && h->levels[l - 1].g.cols % 2 == 0);
       lb.q_stride = up256((size_t)r * c);
       lb.lm_stride = up256((size_t)8 * lb.g.per_label + LM_PAD + (lb.g.strips ? (size_t)lb.g.H * 16 : 0));  // + one strip column: the
                                                                  // second chunk of a patch row in the last strip is loaded, never used
@@ -306,6 +314,8 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
       }
       r /= 2; c /= 2;
     }
+    h->dn_materialize = false;
+    for (int l = 1; l < L; ++l) h->dn_materialize |= !(h->levels[l].fast_spread && h->levels[l].dn_inplace);
     h->depth_stride = h->frame_bytes / 2;   // u16 elements between the depth images of consecutive slots
     for (int m = 0; m < M; ++m)
       if (h->cfg.modalities[m].type == LMB200_DEPTH_NORMAL) {
@@ -463,27 +473,46 @@ static bool chunk_is_contiguous(lmb200_detector* h, const lmb200_image* frames, 
 
 // Frame side for slots [first, first+count): quantise every modality at every level, then
 // spread + response + linearize.  (Detector::match, first half.)
-static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st) {
+// phase: FS_ALL, or one half of it — FS_QUANTIZE (pyrDown + the quantizers: everything that writes quantized maps) /
+// FS_SPREAD (spread + response + linearize).  The template-sharded multi-GPU step quantises only the rank's own frame
+// block, all-gathers the quantized maps over NCCL and then spreads every frame (lmb200_match_resident_sharded).
+enum { FS_ALL = 0, FS_QUANTIZE = 1, FS_SPREAD = 2 };
+static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st, int phase = FS_ALL) {
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
-  CU(cudaMemsetAsync(h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD, 0, (size_t)count * MAX_MOD * sizeof(u32), st));
+  if (phase != FS_QUANTIZE)
+    CU(cudaMemsetAsync(h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD, 0, (size_t)count * MAX_MOD * sizeof(u32), st));
   for (int l = 0; l < L; ++l) {
     LevelBuffers& lb = h->levels[l];
     for (int m = 0; m < M; ++m) {
       const lmb200_modality& mod = h->cfg.modalities[m];
       u8* q = lb.q[m].as<u8>() + (size_t)first * lb.q_stride;
-      if (mod.type == LMB200_COLOR_GRADIENT) {
+      if (phase == FS_SPREAD) {
+      } else if (mod.type == LMB200_COLOR_GRADIENT) {
         u8* bgr = lb.bgr[m].as<u8>() + (size_t)first * lb.bgr_stride;
+        const bool gen = h->generic_frame_side;   // round 1's kernels keep the coarser levels interleaved, round 2's as byte planes
         if (l > 0) {
           LevelBuffers& pb = h->levels[l - 1];
           ProfScope ps(h, LMB200_K_PYRDOWN, st);
-          launch_pyrdown_bgr(pb.bgr[m].as<u8>() + (size_t)first * pb.bgr_stride, pb.bgr_stride, bgr, lb.bgr_stride,
-                             pb.g.rows, pb.g.cols, count, st);
+          if (gen)
+            launch_pyrdown_bgr(pb.bgr[m].as<u8>() + (size_t)first * pb.bgr_stride, pb.bgr_stride, bgr, lb.bgr_stride,
+                               pb.g.rows, pb.g.cols, count, st);
+          else
+            launch_pyrdown_planar(pb.bgr[m].as<u8>() + (size_t)first * pb.bgr_stride, pb.bgr_stride, l - 1 > 0, bgr, lb.bgr_stride,
+                                  pb.g.rows, pb.g.cols, count, st);
         }
         ProfScope ps(h, LMB200_K_CG_QUANTIZE, st);
-        launch_cg_quantize(bgr, lb.bgr_stride, q, lb.q_stride, nullptr, 0, lb.g.rows, lb.g.cols,
-                           mod.weak_threshold * mod.weak_threshold, count, st);
+        if (gen)
+          launch_cg_quantize(bgr, lb.bgr_stride, q, lb.q_stride, nullptr, 0, lb.g.rows, lb.g.cols,
+                             mod.weak_threshold * mod.weak_threshold, count, st);
+        else
+          launch_cg_quantize2(bgr, lb.bgr_stride, l > 0, q, lb.q_stride, nullptr, 0, lb.g.rows, lb.g.cols,
+                              mod.weak_threshold * mod.weak_threshold, count, st);
       } else {
-        if (l == 0) {
+        if (l == 0 && !h->generic_frame_side) {
+          ProfScope ps(h, LMB200_K_DN_QUANTIZE, st);
+          launch_dn_median(h->d_depth[m].as<u16>() + (size_t)first * h->depth_stride, h->depth_stride, q, lb.q_stride,
+                           lb.g.rows, lb.g.cols, mod.distance_threshold, mod.difference_threshold, h->d_normal_lut.as<u8>(), count, st);
+        } else if (l == 0) {
           u8* raw = h->d_dnraw[m].as<u8>() + (size_t)first * lb.q_stride;
           {
             ProfScope ps(h, LMB200_K_DN_QUANTIZE, st);
@@ -493,16 +522,32 @@ static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t
           }
           ProfScope ps(h, LMB200_K_MEDIAN, st);
           launch_median5(raw, lb.q_stride, q, lb.q_stride, lb.g.rows, lb.g.cols, count, st);
-        } else {
+        } else if (h->dn_materialize) {  // some level needs the decimated maps in memory: write the whole chain
           LevelBuffers& pb = h->levels[l - 1];
           ProfScope ps(h, LMB200_K_DECIMATE, st);
           launch_resize_nn(pb.q[m].as<u8>() + (size_t)first * pb.q_stride, pb.q_stride, pb.g.rows, pb.g.cols, q,
                            lb.q_stride, lb.g.rows, lb.g.cols, count, st);
         }
       }
+      if (phase == FS_QUANTIZE) continue;
       const u8* mask = nullptr;
       if (h->masks_in_use && lb.mask[m].p) mask = lb.mask[m].as<u8>() + (size_t)first * lb.q_stride;
       ProfScope ps(h, LMB200_K_LINEARIZE, st);
+      if (lb.fast_spread) {
+        SpreadArgs a;
+        a.q = q; a.q_stride = lb.q_stride; a.q_pitch = lb.g.cols; a.q_step = 1;
+        if (mod.type == LMB200_DEPTH_NORMAL && l > 0 && !h->dn_materialize) {  // read the level-0 map with stride 2^l
+          LevelBuffers& l0 = h->levels[0];
+          a.q = l0.q[m].as<u8>() + (size_t)first * l0.q_stride; a.q_stride = l0.q_stride; a.q_pitch = l0.g.cols; a.q_step = 1 << l;
+        }
+        a.mask = mask; a.mask_stride = lb.q_stride;
+        a.lm = lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride; a.lm_stride = lb.lm_stride;
+        a.lmn = l == L - 1 ? lb.lmn[m].as<u8>() + (size_t)first * lb.lmn_stride : nullptr; a.lmn_stride = lb.lmn_stride;
+        a.resp_sum = h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD + m; a.resp_stride = MAX_MOD;
+        a.g = lb.g; a.table = h->d_table.as<uint2>();
+        if (!launch_spread_fast(a, count, st)) return set_error(h, LMB200_E_INVALID, "internal: fast spread kernel does not cover this level");
+        continue;
+      }
       launch_spread_linearize(q, lb.q_stride, mask, lb.q_stride, lb.lm[m].as<u8>() + (size_t)first * lb.lm_stride,
                               lb.lm_stride, lb.g, h->d_table.as<uint2>(), count, st);
       if (l == L - 1) h->prof.launches[LMB200_K_LINEARIZE]++;  // the nibble packer is a launch of its own
@@ -516,6 +561,24 @@ static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t
   return LMB200_OK;
 }
 
+// The fast spread kernels read DepthNormal's coarser levels out of the level-0 map in place; callers that want those
+// quantized maps themselves (quantized_images of match(), lmb200_debug_fetch) get them materialised here.
+static int materialize_dn_levels(lmb200_detector* h, int first, int count, cudaStream_t st) {
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  for (int m = 0; m < M; ++m) {
+    if (h->cfg.modalities[m].type != LMB200_DEPTH_NORMAL) continue;
+    for (int l = 1; l < L; ++l) {
+      LevelBuffers& lb = h->levels[l];
+      LevelBuffers& pb = h->levels[l - 1];
+      if (h->dn_materialize) continue;  // run_frame_side wrote the chain already
+      launch_resize_nn(pb.q[m].as<u8>() + (size_t)first * pb.q_stride, pb.q_stride, pb.g.rows, pb.g.cols,
+                       lb.q[m].as<u8>() + (size_t)first * lb.q_stride, lb.q_stride, lb.g.rows, lb.g.cols, count, st);
+    }
+  }
+  CU(cudaGetLastError());
+  return LMB200_OK;
+}
+
 static MatchParams make_match_params(lmb200_detector* h, int first, int count, float threshold) {
   MatchParams mp;
   mp.M = h->cfg.num_modalities;
@@ -523,6 +586,7 @@ static MatchParams make_match_params(lmb200_detector* h, int first, int count, f
   mp.frames = count;
   mp.sel = h->d_sel.as<int>();
   mp.threshold = threshold;
+  mp.early_exit = h->early_exit ? 1 : 0;
   mp.cand = h->d_cand.as<Cand>() + (size_t)first * h->cand_cap;
   mp.cand_cap = h->cand_cap;
   mp.ctr = h->d_ctr.as<SlotCtr>() + first;
@@ -618,6 +682,7 @@ static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, 
     const Cand* src = h->h_out + (size_t)(first + i) * h->out_cap;
     out[i].assign(src, src + n);
     h->prof.bytes_local += (long long)h->h_ctr[first + i].local_bytes;
+    h->prof.chunks_coarse += (long long)h->h_ctr[first + i].coarse_chunks;
   }
   if (h->profiling) collect_profile(h);
   return LMB200_OK;
@@ -732,7 +797,7 @@ int lmb200_upload_frames(lmb200_handle h, const lmb200_image* frames, int n_fram
     rc = upload_one(h, frames + (size_t)f * n_sources, first_slot + f, st);
     if (rc) return rc;
   }
-  CU(cudaStreamSynchronize(st));
+  if (!h->upload_async) CU(cudaStreamSynchronize(st));  // "upload_async": pinned frames that stay valid until the next fetch
   return LMB200_OK;
 }
 
@@ -753,6 +818,58 @@ int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float thre
   if (rc) return rc;
   // completion event of this slot range: the fetch calls wait on it from the copy stream, so a fetch of step k does
   // not queue behind the kernels of step k+1 that were already enqueued on the compute stream
+  ResidentMark& mk = h->resident_marks[h->resident_next++ & 3];
+  if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
+  mk.first = first_slot; mk.count = count;
+  CU(cudaEventRecord(mk.ev, st));
+  return LMB200_OK;
+}
+
+// Template-sharded step with the frame side sharded too (one process per GPU, after lmb200_set_template_shard +
+// lmb200_comm_init; every rank holds the same frames in slots [first, first+count) — or at least its own block of them):
+// rank r quantises frames [first + r*n, first + (r+1)*n), n = count / world; the quantized maps (1 B per pixel, level and
+// modality: 0.7 MB per cfg-A frame) are all-gathered in place over NVLink in one NCCL group; every rank then spreads all
+// frames and scores its template shard.  The expensive half of the frame side (pyrDown + quantisers) is thereby divided
+// by the number of GPUs instead of replicated — it was what capped round 1's template-sharded scaling at ~29 %.
+// Falls back to the replicated frame side when count is not a multiple of the world size.
+int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, float threshold,
+                                  const char* const* class_ids, int n_class_ids) {
+  if (!h || !h->device_ready || h->rows == 0) return set_error(h, LMB200_E_INVALID, "no frames uploaded");
+  if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
+  if (!h->nccl_comm || h->comm_world != h->shard_world || h->comm_rank != h->shard_rank)
+    return set_error(h, LMB200_E_COMM, "lmb200_match_resident_sharded needs lmb200_comm_init and lmb200_set_template_shard with the same rank/world");
+  const int world = h->comm_world;
+  if (world == 1 || count % world != 0) return lmb200_match_resident(h, first_slot, count, threshold, class_ids, n_class_ids);
+  cudaSetDevice(h->device);
+  drain_tickets(h);
+  int rc = ensure_plan(h, h->rows, h->cols);
+  if (rc) return rc;
+  rc = ensure_selection(h, class_ids, n_class_ids);
+  if (rc) return rc;
+  h->masks_in_use = false;
+  const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+  const int n = count / world, own = first_slot + h->comm_rank * n;
+  cudaStream_t st = h->lanes[0].stream;
+  rc = run_frame_side(h, own, n, st, FS_QUANTIZE);
+  if (rc) return rc;
+  rc = comm_group_begin(h);
+  if (rc) return rc;
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      // maps the quantise phase writes: ColorGradient at every level; DepthNormal at level 0 (+ the decimation chain when materialised)
+      const bool written = h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT || l == 0 || h->dn_materialize;
+      if (!written) continue;
+      LevelBuffers& lb = h->levels[l];
+      u8* base = lb.q[m].as<u8>() + (size_t)first_slot * lb.q_stride;
+      rc = comm_allgather(h, base + (size_t)h->comm_rank * n * lb.q_stride, base, (size_t)n * lb.q_stride, st);
+      if (rc) { comm_group_end(h); return rc; }
+    }
+  rc = comm_group_end(h);
+  if (rc) return rc;
+  rc = run_frame_side(h, first_slot, count, st, FS_SPREAD);
+  if (rc) return rc;
+  rc = run_matching(h, first_slot, count, threshold, st);
+  if (rc) return rc;
   ResidentMark& mk = h->resident_marks[h->resident_next++ & 3];
   if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
   mk.first = first_slot; mk.count = count;
@@ -880,6 +997,9 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
   if (rc) return rc;
   if (quantized_out) {
     const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
+    rc = materialize_dn_levels(h, 0, 1, st);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
     for (int l = 0; l < L; ++l)
       for (int m = 0; m < M; ++m) {
         lmb200_image& qi = quantized_out[l * M + m];
@@ -1032,6 +1152,7 @@ static int batch_finalize(lmb200_detector* h, BatchTicket& tk, lmb200_match_rec*
       if (tk.b_ctr[f].overflow || n > h->out_cap || n > tk.head_used) return 1;
       raw.assign(tk.b_out + (size_t)f * tk.head_used, tk.b_out + (size_t)f * tk.head_used + n);
       h->prof.bytes_local += (long long)tk.b_ctr[f].local_bytes;
+      h->prof.chunks_coarse += (long long)tk.b_ctr[f].coarse_chunks;
       to_matches(h, raw, m);
       h->prof.candidates += (long long)raw.size();
       finalize_matches(m);
@@ -1124,6 +1245,13 @@ int lmb200_host_alloc(size_t bytes, void** out) {
 }
 int lmb200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LMB200_OK : LMB200_E_CUDA; }
 
+int lmb200_set_option(lmb200_handle h, const char* name, int value) {
+  if (!h || !name) return LMB200_E_INVALID;
+  if (std::strcmp(name, "early_exit") == 0) { h->early_exit = value != 0; return LMB200_OK; }
+  if (std::strcmp(name, "upload_async") == 0) { h->upload_async = value != 0; return LMB200_OK; }
+  return set_error(h, LMB200_E_INVALID, std::string("unknown option ") + name);
+}
+
 int lmb200_set_profiling(lmb200_handle h, int enabled) {
   if (!h) return LMB200_E_INVALID;
   h->profiling = enabled != 0;
@@ -1158,7 +1286,22 @@ int lmb200_debug_fetch(lmb200_handle h, int kind, int slot, int index, void* dst
     if (index < 0 || index >= L * M) return set_error(h, LMB200_E_INVALID, "bad map index");
     LevelBuffers& lb = h->levels[index / M];
     int m = index % M;
-    if (kind == LMB200_DBG_QUANTIZED) return give(lb.q[m].as<u8>() + (size_t)slot * lb.q_stride, (size_t)lb.g.rows * lb.g.cols);
+    if (kind == LMB200_DBG_QUANTIZED) {
+      int rc = materialize_dn_levels(h, slot, 1, st);
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(st));
+      return give(lb.q[m].as<u8>() + (size_t)slot * lb.q_stride, (size_t)lb.g.rows * lb.g.cols);
+    }
+    if (!lb.g.strips && lb.fast_spread) {  // coarsest level, fast path: only the nibble-packed memory exists; unpack it
+      const size_t flat = (size_t)8 * lb.g.rows * lb.g.cols, capb = *n_bytes;
+      *n_bytes = flat;
+      if (!dst || capb < flat) return LMB200_E_TRUNCATED;
+      std::vector<u8> tmp(flat / 2);
+      CU(cudaMemcpy(tmp.data(), lb.lmn[m].as<u8>() + (size_t)slot * lb.lmn_stride, tmp.size(), cudaMemcpyDeviceToHost));
+      u8* o = (u8*)dst;
+      for (size_t i = 0; i < tmp.size(); ++i) { o[2 * i] = tmp[i] & 15; o[2 * i + 1] = tmp[i] >> 4; }
+      return LMB200_OK;
+    }
     if (!lb.g.strips) return give(lb.lm[m].as<u8>() + (size_t)slot * lb.lm_stride, (size_t)8 * lb.g.rows * lb.g.cols);
     // strip layout -> upstream's flat layout
     const size_t flat = (size_t)8 * lb.g.rows * lb.g.cols, capb = *n_bytes;
@@ -1537,7 +1680,7 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->lanes[0].stream));
   }
-  for (int i = 0; i < count; ++i) h->prof.bytes_local += (long long)h->h_ctr[first_slot + i].local_bytes;
+  for (int i = 0; i < count; ++i) { h->prof.bytes_local += (long long)h->h_ctr[first_slot + i].local_bytes; h->prof.chunks_coarse += (long long)h->h_ctr[first_slot + i].coarse_chunks; }
   tt[1] = now();
   // 2. fixed-capacity send buffer per frame: record 0 = {count,..}, then up to gather_cap records.
   //    Every rank sees every count after the gather, so all ranks take the same grow decision.
@@ -1572,14 +1715,19 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   tt[2] = now();
   // 3. restore reference generation order (rank-ordered concatenation for contiguous shards; ordered by selection
   //    position for interleaved shards: every template lives on exactly one rank and its records are already in
-  //    raster order), then the same epilogue as the 1-GPU path
+  //    raster order), then the same epilogue as the 1-GPU path.  With enough frames the host work is DISTRIBUTED: rank r
+  //    finalises the frame block [r*per, (r+1)*per) and a second all-gather shares the finished lists (round 1 had every
+  //    rank sort every frame: ~3.6 ms of redundant host work per 96-frame step, the limiter of that mode).
   size_t base = 0;
   int status = LMB200_OK;
-  std::vector<std::vector<Cand>> alls(count);
+  const bool distribute = world > 1 && count >= 2 * world;
+  const int per = distribute ? (count + world - 1) / world : count;
+  const int lo = distribute ? std::min(count, h->comm_rank * per) : 0, hi = distribute ? std::min(count, lo + per) : count;
+  std::vector<std::vector<Cand>> alls(hi - lo);
   {
-    auto gather_frames = [&](int lo, int hi) {
-      for (int i = lo; i < hi; ++i) {
-        std::vector<Cand>& all = alls[i];
+    auto gather_frames = [&](int a, int b) {
+      for (int i = a; i < b; ++i) {
+        std::vector<Cand>& all = alls[i - lo];
         for (int r = 0; r < world; ++r) {
           const Cand* rec = h->h_gather + ((size_t)r * count + i) * (1 + h->gather_cap);
           all.insert(all.end(), rec + 1, rec + 1 + rec[0].tsel);
@@ -1588,11 +1736,11 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
           std::stable_sort(all.begin(), all.end(), [h](const Cand& a, const Cand& b) { return h->pos_of_g[a.tsel] < h->pos_of_g[b.tsel]; });
       }
     };
-    const int nt = count >= 16 ? 4 : 1;
-    if (nt == 1) gather_frames(0, count);
+    const int nf = hi - lo, nt = nf >= 16 ? 4 : 1;
+    if (nt == 1) gather_frames(lo, hi);
     else {
       std::vector<std::thread> pool;
-      for (int t = 0; t < nt; ++t) pool.emplace_back(gather_frames, count * t / nt, count * (t + 1) / nt);
+      for (int t = 0; t < nt; ++t) pool.emplace_back(gather_frames, lo + nf * t / nt, lo + nf * (t + 1) / nt);
       for (auto& th : pool) th.join();
     }
   }
@@ -1600,17 +1748,63 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   std::vector<std::vector<Match>> ms;
   finalize_frames(h, alls, ms);
   tt[4] = now();
-  if (trace && h->comm_rank == 0)
-    std::fprintf(stderr, "[lmb200 trace] allgather fetch: wait compute %.3f ms, gather+D2H %.3f ms, reorder %.3f ms, sort/unique %.3f ms\n",
-                 tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3]);
-  for (int i = 0; i < count; ++i) {
-    h->prof.candidates += (long long)alls[i].size();
-    h->prof.matches += (long long)ms[i].size();
-    size_t n = 0;
-    if (offsets) offsets[i] = base;
-    if (emit(h, ms[i], out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
-    base += n;
+  if (!distribute) {
+    for (int i = 0; i < count; ++i) {
+      h->prof.candidates += (long long)alls[i].size();
+      h->prof.matches += (long long)ms[i].size();
+      size_t n = 0;
+      if (offsets) offsets[i] = base;
+      if (emit(h, ms[i], out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
+      base += n;
+    }
+    if (offsets) offsets[count] = base;
+  } else {
+    // capacity every rank derives identically from the gathered counts (unique can only shrink a list)
+    int fin_cap = 0;
+    for (int i = 0; i < count; ++i) {
+      int tot = 0;
+      for (int r = 0; r < world; ++r) tot += h->h_gather[((size_t)r * count + i) * (1 + h->gather_cap)].tsel;
+      fin_cap = std::max(fin_cap, tot);
+    }
+    const size_t pitch2 = (size_t)(1 + fin_cap), bytes2 = (size_t)per * pitch2 * sizeof(lmb200_match_rec);
+    ALLOC(h->d_fin_send, bytes2);
+    ALLOC(h->d_fin_recv, bytes2 * world);
+    if (h->h_fin_bytes < bytes2 * world) {
+      if (h->h_fin) { cudaFreeHost(h->h_fin); h->h_fin = nullptr; }
+      CU(cudaHostAlloc((void**)&h->h_fin, bytes2 * world, cudaHostAllocDefault));
+      h->h_fin_bytes = bytes2 * world;
+    }
+    lmb200_match_rec* mine = h->h_fin + (size_t)h->comm_rank * per * pitch2;  // staged in place in the pinned receive mirror
+    for (int j = 0; j < per; ++j) {
+      lmb200_match_rec* rec = mine + (size_t)j * pitch2;
+      const int i = lo + j;
+      const int n = i < hi ? (int)ms[j].size() : 0;
+      rec[0].x = n; rec[0].y = 0; rec[0].similarity = 0.f; rec[0].class_index = 0; rec[0].template_id = 0;
+      for (int k = 0; k < n; ++k) {
+        const Match& mt = ms[j][k];
+        rec[1 + k].x = mt.x; rec[1 + k].y = mt.y; rec[1 + k].similarity = mt.similarity;
+        rec[1 + k].class_index = mt.class_index; rec[1 + k].template_id = mt.template_id;
+      }
+      if (i < hi) { h->prof.candidates += (long long)alls[j].size(); h->prof.matches += (long long)n; }
+    }
+    CU(cudaMemcpyAsync(h->d_fin_send.p, mine, bytes2, cudaMemcpyHostToDevice, st));
+    int rc = comm_allgather(h, h->d_fin_send.p, h->d_fin_recv.p, bytes2, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_fin, h->d_fin_recv.p, bytes2 * world, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < count; ++i) {
+      const lmb200_match_rec* rec = h->h_fin + ((size_t)(i / per) * per + (size_t)(i % per)) * pitch2;
+      const size_t n = (size_t)rec[0].x;
+      if (offsets) offsets[i] = base;
+      const size_t room = cap > base ? cap - base : 0, w = std::min(n, room);
+      if (w) std::memcpy(out + base, rec + 1, w * sizeof(lmb200_match_rec));
+      if (w < n) status = LMB200_E_TRUNCATED;
+      base += n;
+    }
+    if (offsets) offsets[count] = base;
   }
-  if (offsets) offsets[count] = base;
+  if (trace && h->comm_rank == 0)
+    std::fprintf(stderr, "[lmb200 trace] allgather fetch: wait compute %.3f ms, gather+D2H %.3f ms, reorder %.3f ms, sort/unique %.3f ms, share %.3f ms\n",
+                 tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], now() - tt[4]);
   return status;
 }

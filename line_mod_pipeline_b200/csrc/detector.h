@@ -58,6 +58,8 @@ struct ScopedDevBuf : DevBuf {
 struct LevelBuffers {
   lmk::LevelGeom g;
   size_t q_stride = 0, lm_stride = 0, bgr_stride = 0, lmn_stride = 0;
+  bool fast_spread = false;            // round-2 spread kernels cover this geometry (kernels.cuh: spread_fast_covers)
+  bool dn_inplace = false;             // DepthNormal at this level = exact 2^l decimation of the level-0 map, read in place
   DevBuf bgr[LMB200_MAX_MODALITIES];   // CG source at this level (level 0 = uploaded frame)
   DevBuf q[LMB200_MAX_MODALITIES];     // quantized map
   DevBuf mask[LMB200_MAX_MODALITIES];  // optional mask pyramid
@@ -131,6 +133,9 @@ struct lmb200_detector {
   int rows = 0, cols = 0, slots = 0;
   int cand_cap = 0, out_cap = 0;
   bool masks_in_use = false;
+  bool dn_materialize = false;          // some DepthNormal level needs its decimated map in memory (generic spread path or odd sizes):
+                                        // then every level's map is written (resize chain); else coarser levels are read in place
+  bool generic_frame_side = false;      // LMB200_GENERIC_FRAME=1: round 1's generic frame-side kernels (A/B runs, fallback tests)
   std::vector<lmh::LevelBuffers> levels;
   lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
   size_t depth_stride = 0;
@@ -152,6 +157,8 @@ struct lmb200_detector {
 
   // profiling
   bool profiling = false;
+  bool upload_async = false;             // lmb200_set_option("upload_async"): lmb200_upload_frames returns without synchronising
+  bool early_exit = true;                // lmb200_set_option("early_exit"): measurement runs switch the coarse kernel's exact exit off
   std::vector<lmh::ProfRec> prof_pending;
   std::vector<cudaEvent_t> event_pool;
   lmb200_profile prof;
@@ -161,6 +168,8 @@ struct lmb200_detector {
   void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
   lmh::DevBuf d_gather_send, d_gather_recv; int gather_cap = 0;
   lmk::Cand* h_gather = nullptr; size_t h_gather_bytes = 0;
+  lmh::DevBuf d_fin_send, d_fin_recv;          // finished (sorted + unique) per-frame lists, second all-gather
+  lmb200_match_rec* h_fin = nullptr; size_t h_fin_bytes = 0;
 
   // scratch for lmb200_get_template
   std::vector<lmb200_feature> tmp_features;
@@ -196,6 +205,8 @@ int comm_unique_id(uint8_t* id128, std::string& err);
 int comm_init(lmb200_detector* h, const uint8_t* id128, int rank, int world);
 int comm_destroy(lmb200_detector* h);
 int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st);
+int comm_group_begin(lmb200_detector* h);
+int comm_group_end(lmb200_detector* h);
 void default_normal_lut(uint8_t* out8000);
 void default_similarity_lut(uint8_t* out256);
 }  // namespace lmh

@@ -73,6 +73,8 @@ struct SlotCtr {
   int out_count;                      // surviving matches written by pack_kernel
   int pad;
   unsigned long long local_bytes;     // algorithmic bytes gathered by similarityLocal (sum nf*256)
+  unsigned long long coarse_chunks;   // 16-byte chunk loads the coarse kernel issued (plan rows executed x active lanes x 2):
+                                      // the bytes it actually REQUESTED, after the early exit (bench roofline)
 };
 
 // Linear-memory layouts.  Coarsest level (strips == 0): upstream's flat rows, LM[label][phase][y/T * W + x/T], which the
@@ -106,6 +108,37 @@ void launch_spread_linearize(const u8* q, size_t q_stride, const u8* mask, size_
                              u8* lm, size_t lm_stride, LevelGeom g, const uint2* table,
                              int frames, cudaStream_t st);
 
+// Round-2 frame-side kernels (kernels_color.cu, kernels_depth.cu).  pyrDown writes byte PLANES ([3][rows][cols]); the
+// quantiser reads either the interleaved BGR frame (level 0) or planes (levels >= 1).
+void launch_pyrdown_planar(const u8* src, size_t src_stride, bool src_planar, u8* dst, size_t dst_stride, int rows, int cols,
+                           int frames, cudaStream_t st);
+void launch_cg_quantize2(const u8* src, size_t src_stride, bool src_planar, u8* q, size_t q_stride, float* mag /*nullable*/,
+                         size_t mag_stride, int rows, int cols, float weak_sq, int frames, cudaStream_t st);
+// quantizedNormals + medianBlur(5) in one kernel
+void launch_dn_median(const u16* depth, size_t depth_stride /*elements*/, u8* out, size_t out_stride, int rows, int cols,
+                      int dist_thr, int diff_thr, const u8* lut_dev, int frames, cudaStream_t st);
+
+// Round-2 fused spread + response + linearize (kernels_spread.cu).  Finer levels (g.strips > 0) write the strip layout
+// into `lm`; the coarsest level writes the nibble-packed flat layout straight into `lmn` (+ resp_sum).  q_step > 1 reads
+// the quantized map of a finer level in place: pixel (y, x) of this level = q[y*q_step][x*q_step] (DepthNormal pyrDown).
+struct SpreadArgs {
+  const u8* q; size_t q_stride;       // quantized map and its per-frame stride
+  int q_pitch, q_step;                // bytes per row of the map `q` points to; sampling step (1 = this level's own map)
+  const u8* mask; size_t mask_stride; // optional mask at THIS level's resolution (pitch = g.cols), nullable
+  u8* lm; size_t lm_stride;           // strip-layout output (finer levels)
+  u8* lmn; size_t lmn_stride;         // nibble-packed flat output (coarsest level)
+  u32* resp_sum; int resp_stride;     // += sampled response sum per frame (coarsest level), nullable
+  LevelGeom g;
+  const uint2* table;                 // 256 x uint2: the 8 orientation responses of one spread byte
+};
+// false: geometry not covered by the fast kernels (T not in {2,4,5,8,16}, or a coarsest level with W % 8 != 0) -> the
+// caller runs launch_spread_linearize (+ launch_pack_nibbles) instead.
+bool launch_spread_fast(const SpreadArgs& a, int frames, cudaStream_t st);
+inline bool spread_fast_covers(const LevelGeom& g) {
+  const bool t_ok = g.T == 2 || g.T == 4 || g.T == 5 || g.T == 8 || g.T == 16;
+  return t_ok && (g.strips ? true : (g.W & 7) == 0);
+}
+
 // ------------------------------------------------------------------ template side
 // Plan: flat linear-memory offsets of every feature for one level's geometry + safe flags.
 // coarsest = true: nibble-space buckets ((off>>3)&3), COARSE_SLOTS per modality, every bucket padded to a multiple of 3
@@ -120,6 +153,7 @@ void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_str
 
 struct MatchParams {
   int M, nsel, frames;
+  int early_exit;                     // 1 (default): the coarse kernel's exact early exit is on; 0: measurement runs without it
   const int* sel;                     // selection list: global template indices, generation order
   float threshold;
   // candidate store, per frame

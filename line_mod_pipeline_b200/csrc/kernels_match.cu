@@ -243,6 +243,8 @@ struct CoarseCtx {
   u32 per_label;
   const int* Pm;                     // plan: upstream's template_positions per modality
   const int* ord;                    // this frame's modality order (shared memory)
+  int early_exit;
+  mutable u32 chunks;                // 16 B chunk loads issued for this template (lane-uniform)
   u16* dump;                         // DUMP instantiation: the template's full u16 similarity map [H*W] (pre-zeroed)
   __device__ __forceinline__ int P(int m) const { return __ldg(Pm + m); }
 };
@@ -295,6 +297,7 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       const u32 bk = cx.hdr.bkt(m);
       const int n0 = bk & 255, n1 = (bk >> 8) & 255, n2 = (bk >> 16) & 255, n3 = bk >> 24;
       const uint2* lst = cx.lst + m * COARSE_SLOTS;
+      cx.chunks += 2u * (u32)(n0 + n1 + n2 + n3) * (u32)__popc(__ballot_sync(0xffffffffu, rem > 0));
       if (rem > 0) {  // lanes past template_positions sit the modality out (one branch, not one per group)
         accum_bucket<0, SAFE>(lmb, lst, 0, n0, pos0, P, cx.per_label, acc);
         accum_bucket<1, SAFE>(lmb, lst, n0, n1, pos0, P, cx.per_label, acc);
@@ -317,7 +320,7 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       int later = 0;  // features of the modalities still to come
       for (int k = mi + 1; k < cx.M; ++k) later += cx.hdr.nf(cx.ord[k]);
       const int bound = cx.raw_thr - 4 * later;
-      if (!DUMP && mi + 1 < cx.M && bound >= 0) {  // warp-uniform
+      if (!DUMP && cx.early_exit && mi + 1 < cx.M && bound >= 0) {  // warp-uniform
         const u32 Kb = (u32)(0x7FFF - bound) * 0x00010001u;
         u32 alive = 0;
         if (WIDE) {
@@ -405,6 +408,7 @@ __device__ __forceinline__ void coarse_template(const MatchParams& mp, const Coa
     mp.tpl_start[(size_t)frame * mp.nsel_stride + isel] = base;
     mp.tpl_cnt[(size_t)frame * mp.nsel_stride + isel] = run;
     mp.tpl_alive[(size_t)frame * mp.nsel_stride + isel] = run;
+    atomicAdd(&mp.ctr[frame].coarse_chunks, (unsigned long long)cx.chunks);
   }
   base = __shfl_sync(0xffffffffu, base, 0);
   run = __shfl_sync(0xffffffffu, run, 0);
@@ -468,6 +472,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) similarity_coarse_kern
     cx.Pm = lp.hdr[g].P;
     cx.ord = s_ord;
     cx.dump = dump;
+    cx.early_exit = mp.early_exit;
+    cx.chunks = 0u;
     __syncwarp();  // the previous template's reads of s_off / s_queue are done
     for (int s = lane; s < cx.M * COARSE_SLOTS; s += 32)
       s_off[warp][s] = __ldg(reinterpret_cast<const uint2*>(lp.offs) + (size_t)g * cx.M * COARSE_SLOTS + s);

@@ -340,6 +340,11 @@ class Detector:
         ids, nids = _cstr_array(class_ids)
         self._check(self._L.lmb200_match_resident(self._h, first_slot, count, C.c_float(threshold), ids, nids))
 
+    def matchResidentSharded(self, first_slot, count, threshold, class_ids=()):
+        """Template-sharded step with the quantisers sharded by frame block + NCCL all-gather of the quantized maps."""
+        ids, nids = _cstr_array(class_ids)
+        self._check(self._L.lmb200_match_resident_sharded(self._h, first_slot, count, C.c_float(threshold), ids, nids))
+
     def fetchResident(self, first_slot, count, allgather=False, cap=None):
         cap = cap or 1024 * count
         fn = self._L.lmb200_fetch_resident_allgather if allgather else self._L.lmb200_fetch_resident
@@ -403,8 +408,11 @@ class Detector:
         self._check(self._L.lmb200_get_profile(self._h, C.byref(p), int(reset)))
         d = dict(ms={K.K_NAMES[i]: p.ms[i] for i in range(10)}, launches={K.K_NAMES[i]: p.launches[i] for i in range(10)},
                  bytes_coarse=p.bytes_coarse, bytes_local=p.bytes_local, frames=p.frames, candidates=p.candidates,
-                 matches=p.matches)
+                 matches=p.matches, chunks_coarse=p.chunks_coarse)
         return d
+
+    def setOption(self, name, value):
+        self._check(self._L.lmb200_set_option(self._h, name.encode(), int(value)))
 
     def debugFetch(self, kind, slot=0, index=0):
         n = C.c_size_t(0)

@@ -594,3 +594,22 @@ def test_resident_ranges_survive_store_growth():
         for i in range(2):
             want = ora.match(frames[first + i], thr, threads=8).matches(0)
             assert_same_matches(res[i], want, "resident range at slot %d thr=%g" % (first + i, thr))
+
+
+def test_generic_frame_side_fallback_still_exact(monkeypatch):
+    """Round 1's generic frame-side kernels stay in the library as the fallback for geometries the round-2 kernels do
+    not cover (T outside {2,4,5,8,16}, coarsest W % 8 != 0); LMB200_GENERIC_FRAME=1 forces them everywhere."""
+    monkeypatch.setenv("LMB200_GENERIC_FRAME", "1")
+    bgr, depth = synth.make_frame(1)
+    det, ora = make_pair()
+    _check_frame_side(det, ora, [bgr, depth])
+    monkeypatch.delenv("LMB200_GENERIC_FRAME")
+    det2, ora2 = make_pair()
+    _check_frame_side(det2, ora2, [bgr, depth])
+
+
+@pytest.mark.parametrize("T,rows,cols", [((3, 6), 480, 672), ((7,), 448, 672), ((5, 10), 480, 640)])
+def test_frame_side_uncovered_T_uses_fallback(T, rows, cols):
+    bgr, depth = synth.make_frame(2, rows, cols, n_shapes=20)
+    det, ora = make_pair(T=T)
+    _check_frame_side(det, ora, [bgr, depth], n_maps=2 * len(T))

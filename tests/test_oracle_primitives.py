@@ -48,3 +48,22 @@ def test_median_erode_dist_resize():
     mm = RNG.integers(0, 255, (61, 83), dtype=np.uint8)
     assert np.array_equal(O.resize_nn(mm, 30, 41), cv2.resize(mm, (41, 30), interpolation=cv2.INTER_NEAREST))
     assert np.array_equal(O.resize_nn(mm[:60, :82], 30, 41), mm[:60:2, :82:2])
+
+
+def test_integer_label_rule():
+    """The integer-compare orientation rule of csrc/kernels_color.cu (label_from_gradient) against the oracle's
+    quantize(fastAtan2) & 7 table over ALL 2041^2 Sobel pairs (SURVEY golden G1 pins that table's sha1)."""
+    import hashlib
+    tab = np.empty((2041, 2041), np.uint8)
+    O.lib().lmo_label_table(tab.ctypes.data_as(O.C.c_void_p), 1)
+    assert hashlib.sha1(tab.tobytes()).hexdigest() == "521625b4366ecc3f18d4997fe506a3eb147af327"
+    d = np.arange(-1020, 1021, dtype=np.int64)
+    DY, DX = np.meshgrid(d, d, indexing="ij")
+    ax, ay = np.abs(DX), np.abs(DY)
+    mn, mx = np.minimum(ax, ay), np.maximum(ax, ay)
+    N1, N2 = 208571, 700819
+    assert int((mn << 20).max()) < 2 ** 31 and int((mx * N2).max()) < 2 ** 31      # the kernel's 32-bit products never overflow
+    k = ((mn << 20) > mx * N1).astype(np.int64) + ((mn << 20) > mx * N2)
+    t = np.where(ay > ax, 4 - k, k)
+    lab = np.where((DX ^ DY) < 0, (8 - t) & 7, t)
+    assert np.array_equal(lab.astype(np.uint8), tab)
