@@ -51,13 +51,14 @@ def parse():
     ap.add_argument("--templates", type=int, default=3000)
     ap.add_argument("--threshold", type=float, default=80.0)
     ap.add_argument("--ts-templates", type=int, default=20000, help="template_sharded leg: templates (configs[3]: 20 000)")
-    ap.add_argument("--ts-frames", type=int, default=64, help="template_sharded leg: frames per step (all ranks together)")
+    ap.add_argument("--ts-frames", type=int, default=128, help="template_sharded leg: frames per step (all ranks together)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--template-cache", default="", help="YAML(.gz) written/read through the product's persistence; skips addTemplate when present")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ts", action="store_true", help="skip the template_sharded leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the no_early_exit and config1 legs")
+    ap.add_argument("--only-ts", action="store_true", help="run only the template_sharded leg (diagnosis)")
     return ap.parse_args()
 
 
@@ -269,7 +270,8 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
     """BASELINE configs[3] / north_star's multi-GPU split.  Returns the dict for the JSON line (rank 0) or None."""
     Bt = args.ts_frames - args.ts_frames % max(1, world)
     thr = args.threshold
-    det = lm.getDefaultLINEMOD(device=local, max_batch=2 * Bt)
+    G = 3                                                 # slot groups: two steps in flight on the GPU while the host fetches a third
+    det = lm.getDefaultLINEMOD(device=local, max_batch=G * Bt)
     bgr0, depth0 = synth.make_frame(0)
     planted = build_templates_sharded_set(det, args.ts_templates, bgr0, depth0)
     L = lm.capi.lib()
@@ -291,16 +293,26 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         torch.cuda.synchronize()
         det.synchronize()
 
-    # ---- full set on ONE GPU (every rank measures it on its own device; rank 0's figure is reported)
-    det.uploadFrames(frames, 0)
-    for _ in range(2):
-        det.matchResident(0, Bt, thr); det.fetchResident(0, Bt, cap=4096 * Bt)
-    barrier()
+    # ---- full set on ONE GPU (every rank measures it on its own device; rank 0's figure is reported).  Pipelined like the
+    #      sharded step: step k is enqueued on one slot half, then step k-1 is fetched (D2H + host sort/unique) from the other.
+    for g in range(G):
+        det.uploadFrames(frames, g * Bt)
     k1 = max(3, K // 2)
+
+    def one_gpu_steps(n):
+        res = None
+        for k in range(n):
+            det.matchResident((k % G) * Bt, Bt, thr)
+            if k >= G - 1:
+                res = det.fetchResident(((k - (G - 1)) % G) * Bt, Bt, cap=4096 * Bt)
+        for k in range(max(0, n - (G - 1)), n):
+            res = det.fetchResident((k % G) * Bt, Bt, cap=4096 * Bt)
+        return res
+
+    one_gpu_steps(G)
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(k1):
-        det.matchResident(0, Bt, thr)
-        res1 = det.fetchResident(0, Bt, cap=4096 * Bt)
+    res1 = one_gpu_steps(k1)
     det.synchronize()
     dt1 = time.perf_counter() - t0
     single = {"value": Bt * k1 / dt1, "ms_per_step": 1e3 * dt1 / k1}
@@ -335,26 +347,25 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         uid = uid.cuda()
         dist.broadcast(uid, 0)
         det.commInit(uid.cpu().numpy(), rank, world)
-        det.uploadFrames(frames, Bt)                      # second slot half: step k+1 is computed while step k is gathered
-        state = {"half": 0, "pending": None, "last": None}
+        state = {"k": 0, "pending": [], "last": None}
 
         def step(upload):
-            h = state["half"]
+            g = state["k"] % G
+            state["k"] += 1
             if upload:                                    # e2e: only the rank's own frame block crosses PCIe
                 n = Bt // world
-                det.uploadFrames(frames[rank * n:(rank + 1) * n], h * Bt + rank * n)
-            det.matchResidentSharded(h * Bt, Bt, thr)
-            if state["pending"] is not None:
-                state["last"] = det.fetchResident(state["pending"] * Bt, Bt, allgather=True, cap=4096 * Bt)
-            state["pending"], state["half"] = h, h ^ 1
+                det.uploadFrames(frames[rank * n:(rank + 1) * n], g * Bt + rank * n)
+            det.matchResidentSharded(g * Bt, Bt, thr)
+            state["pending"].append(g)
+            if len(state["pending"]) >= G:                # keep G-1 steps in flight behind the one being fetched
+                state["last"] = det.fetchResident(state["pending"].pop(0) * Bt, Bt, allgather=True, cap=4096 * Bt)
 
         def drain():
-            if state["pending"] is not None:
-                state["last"] = det.fetchResident(state["pending"] * Bt, Bt, allgather=True, cap=4096 * Bt)
-                state["pending"] = None
+            while state["pending"]:
+                state["last"] = det.fetchResident(state["pending"].pop(0) * Bt, Bt, allgather=True, cap=4096 * Bt)
 
         def timed(upload):
-            for _ in range(max(2, W)):
+            for _ in range(max(4, W)):
                 step(upload)
             drain()
             barrier()
@@ -465,6 +476,13 @@ def main():
     B, K, W = args.frames, args.steps, max(args.warmup, 3)
     n_tpl = args.templates
     L = lm.capi.lib()
+    if args.only_ts:
+        ts = template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
+        if rank == 0:
+            print(json.dumps({"template_sharded": ts}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- measured roofs of this device (and of the shared host path: every rank copies at once)
     roofs = {"l2_read_GBps": microbench(L, K_.MB_L2_READ), "l1_read_GBps": microbench(L, K_.MB_L1_READ),
@@ -605,15 +623,25 @@ def main():
                "mode": "lmb200_match_batch_submit/_collect, step k+1 submitted before step k is collected",
                "h2d_GBps_all_gpus": h2d_GBps, "frac_of_h2d_roof": h2d_GBps / roofs["h2d_GBps_all_gpus"] if roofs["h2d_GBps_all_gpus"] else None,
                "blocking_call": {"value": B * K * world / dt_sync, "ms_per_step": 1e3 * dt_sync / K}}
-        # single-frame latency of the reference-facing call (configs[1] literally: one frame, host buffers in, matches out)
+        # single-frame latency of the reference-facing call (configs[1] literally: one frame, host buffers in, sorted matches
+        # out): lmb200_match, whose kernel sequence is replayed as a CUDA graph; the blocking batch call with one frame beside it
+        def latency(fn):
+            lat = []
+            for i in range(80):
+                t0 = time.perf_counter()
+                fn()
+                lat.append(time.perf_counter() - t0)
+            lat = sorted(lat[20:])
+            return {"median_ms": 1e3 * lat[len(lat) // 2], "p90_ms": 1e3 * lat[int(len(lat) * 0.9)], "frames_per_s": 1.0 / lat[len(lat) // 2]}
+        prep_s = det.prepareSingle(frames[0], cap=8192)
         prep1 = det.prepareBatch(frames[:1], cap=8192)
-        lat = []
-        for i in range(60):
-            t0 = time.perf_counter()
-            det.matchPrepared(prep1, args.threshold)
-            lat.append(time.perf_counter() - t0)
-        lat = sorted(lat[10:])
-        single = {"median_ms": 1e3 * lat[len(lat) // 2], "p90_ms": 1e3 * lat[int(len(lat) * 0.9)], "frames_per_s": 1.0 / lat[len(lat) // 2]}
+        single = latency(lambda: det.matchPreparedSingle(prep_s, args.threshold))
+        single["call"] = "lmb200_match (CUDA graph replay of the frame's kernel sequence), pinned host frame in, sorted match list out"
+        det.setOption("cuda_graph", 0)
+        single["without_cuda_graph"] = latency(lambda: det.matchPreparedSingle(prep_s, args.threshold))
+        det.setOption("cuda_graph", 1)
+        single["lmb200_match_batch_of_1"] = latency(lambda: det.matchPrepared(prep1, args.threshold))
+        assert det.matchPreparedSingle(prep_s, args.threshold) == len(res[0]), "single-frame call and resident path disagree"
 
     # ---- other legs
     cfg1 = config1_leg(args, lm, torch, local, max(3, K // 2)) if (world == 1 and not args.no_extra) else None
@@ -621,7 +649,7 @@ def main():
     if not args.no_ts:
         if dist is not None:
             dist.barrier()
-        ts = template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, max(3, K // 2), W)
+        ts = template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
 
     if rank != 0:
         if dist is not None:

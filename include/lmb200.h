@@ -223,6 +223,21 @@ int lmb200_timer_elapsed_ms(lmb200_handle h, float* ms);        /* synchronises 
 int lmb200_host_alloc(size_t bytes, void** out);                /* cudaHostAlloc (pinned) */
 int lmb200_host_free(void* p);
 
+/* ---- post-match checks (the per-match image operations right behind Detector::match) ------------------
+ * Colour check of HighLevelLineMOD::detectTemplate / templateMask / colorCheck (src/HighLevelLinemod.cpp:159-161, :113-135,
+ * :424-434) on the GPU, for the frame resident in `slot` (lmb200_match leaves its frame in slot 0): cvtColor(BGR2HSV) +
+ * inRange(lower, upper) once per call, then per match the convex hull of the level-0 features of every modality shifted
+ * to the match, filled like cv::fillPoly:  total[i] = countNonZero(mask), inside[i] = countNonZero(hue & mask).
+ * colorCheck is then `(float)(inside * 100 / total) > percentToPassCheck` (integer division).  A match whose hull leaves
+ * the image (cv::fillPoly would clip it) or whose template is unknown gets inside = total = -1. */
+int lmb200_postmatch_color(lmb200_handle h, int slot, const uint8_t* lower_hsv, const uint8_t* upper_hsv,
+                           const lmb200_match_rec* matches, size_t n, int* inside, int* total);
+/* groupSimilarMatches + discardSmallMatchGroups (src/HighLevelLinemod.cpp:206-253), host code: group_of_match[i] = index
+ * of the surviving group the match belongs to (groups in order of their first member) or -1 when its group was discarded
+ * (size * 100 / biggest <= discard_group_ratio). */
+int lmb200_group_matches(const lmb200_match_rec* matches, size_t n, float radius_threshold, float discard_group_ratio,
+                         int* group_of_match, int* n_groups);
+
 /* ---- tables --------------------------------------------------------------------------- */
 /* 256-byte SIMILARITY_LUT (layout of upstream's table: [32*ori + 16*half + nibble]); entries <= 4.
  * Default = lmb200_config.similarity_lut (circular distance, see LMB200_SIMLUT_*). */
@@ -292,7 +307,9 @@ typedef struct {
 /* Measurement knobs.  "early_exit" (default 1): 0 switches off the coarse kernel's exact early exit (results are
  * identical either way; the bench reports both so the workload dependence of the exit is visible).
  * "upload_async" (default 0): 1 makes lmb200_upload_frames return without synchronising (pinned host frames that stay
- * valid until the results of the next match on those slots have been fetched). */
+ * valid until the results of the next match on those slots have been fetched).
+ * "cuda_graph" (default 1; environment LMB200_NO_GRAPH=1 starts with 0): lmb200_match replays the kernel sequence of one
+ * frame as a CUDA graph (re-captured when plan, templates, selection, stores or threshold change). */
 int lmb200_set_option(lmb200_handle h, const char* name, int value);
 int lmb200_set_profiling(lmb200_handle h, int enabled);        /* CUDA events around every launch */
 int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset);
@@ -345,6 +362,17 @@ int lmb200_render_lookat(const lmb200_mesh* mesh, const lmb200_camera* cam, cons
  * (glm is column-major: R[3*i+j] = in_rotMat[j][i]) and t = (tx, -ty, -tz). */
 int lmb200_render_pose(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* rotations,
                        const double* translations, int n_views, uint16_t* depth_out, uint8_t* colour_out, int threads);
+/* Benchmark::calculateErrorHodan (src/Benchmark.cpp:18-38 with calculateVisibilityMasks :133-154): the visibility-masked
+ * depth-difference error of an estimated pose, from the input depth image and the model rendered at the ground-truth and
+ * at the estimated pose (u16 millimetres, 0 = background).  The reference's defaults: visibility_threshold 15,
+ * error_threshold 20 (include/Benchmark.h:92,:98); a pose counts as correct when error < 0.3 (Benchmark.cpp:33).
+ * n_ok / n_comb (nullable) return the two pixel counts of the ratio. */
+int lmb200_hodan_error(const uint16_t* input_depth, const uint16_t* gt_render, const uint16_t* est_render, int rows, int cols,
+                       int visibility_threshold, int error_threshold, float* error, long long* n_ok, long long* n_comb);
+/* The same including the two renders (lmb200_render_pose conventions): rotations[2][9], translations[2][3] =
+ * ground truth, estimate. */
+int lmb200_hodan_error_poses(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* rotations, const double* translations,
+                             const uint16_t* input_depth, int visibility_threshold, int error_threshold, float* error);
 /* ASCII PLY loader (the .ply models of the reference; polygons become triangle fans).  Free both arrays with lmb200_free. */
 int lmb200_load_ply(const char* path, double** vertices, int* n_vertices, int** triangles, int* n_triangles);
 void lmb200_free(void* p);

@@ -6,10 +6,10 @@ package holds its sources (csrc/), the build script and a thin ctypes mirror of 
 Detector interface.  There is no CPU fallback.
 """
 from .detector import (Detector, ColorGradient, DepthNormal, getDefaultLINE, getDefaultLINEMOD, LinemodError,
-                       MATCH_DTYPE, merge_matches, shard_plan, comm_unique_id, read_pose_sidecar, write_pose_sidecar, POSE_DTYPE)
+                       MATCH_DTYPE, merge_matches, shard_plan, comm_unique_id, read_pose_sidecar, write_pose_sidecar, POSE_DTYPE, group_matches)
 from . import _capi as capi
 from . import render
 
 __all__ = ["Detector", "ColorGradient", "DepthNormal", "getDefaultLINE", "getDefaultLINEMOD", "LinemodError",
            "MATCH_DTYPE", "merge_matches", "shard_plan", "comm_unique_id", "read_pose_sidecar", "write_pose_sidecar",
-           "POSE_DTYPE", "capi", "render"]
+           "POSE_DTYPE", "group_matches", "capi", "render"]

@@ -68,6 +68,9 @@ _P = C.POINTER
 SIGNATURES = {
     "lmb200_render_lookat": (C.c_int, [_P(Mesh), _P(Camera), _P(C.c_double), C.c_int, _P(C.c_uint16), _P(C.c_uint8), C.c_int]),
     "lmb200_render_pose": (C.c_int, [_P(Mesh), _P(Camera), _P(C.c_double), _P(C.c_double), C.c_int, _P(C.c_uint16), _P(C.c_uint8), C.c_int]),
+    "lmb200_hodan_error": (C.c_int, [_P(C.c_uint16), _P(C.c_uint16), _P(C.c_uint16), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_float),
+                                     _P(C.c_longlong), _P(C.c_longlong)]),
+    "lmb200_hodan_error_poses": (C.c_int, [_P(Mesh), _P(Camera), _P(C.c_double), _P(C.c_double), _P(C.c_uint16), C.c_int, C.c_int, _P(C.c_float)]),
     "lmb200_load_ply": (C.c_int, [C.c_char_p, _P(_P(C.c_double)), _P(C.c_int), _P(_P(C.c_int)), _P(C.c_int)]),
     "lmb200_free": (None, [C.c_void_p]),
     "lmb200_default_modality": (None, [C.c_int, _P(Modality)]),
@@ -131,6 +134,8 @@ SIGNATURES = {
     "lmb200_fetch_resident_allgather": (C.c_int, [_H, C.c_int, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_merge_matches": (C.c_int, [_P(_P(MatchRec)), _P(C.c_size_t), C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_shard_plan": (C.c_int, [_P(C.c_double), C.c_int, C.c_int, _P(C.c_int)]),
+    "lmb200_postmatch_color": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, _P(MatchRec), C.c_size_t, _P(C.c_int), _P(C.c_int)]),
+    "lmb200_group_matches": (C.c_int, [_P(MatchRec), C.c_size_t, C.c_float, C.c_float, _P(C.c_int), _P(C.c_int)]),
     "lmb200_set_option": (C.c_int, [_H, C.c_char_p, C.c_int]),
     "lmb200_set_profiling": (C.c_int, [_H, C.c_int]),
     "lmb200_get_profile": (C.c_int, [_H, _P(Profile), C.c_int]),

@@ -102,6 +102,7 @@ int lmb200_create(const lmb200_config* cfg, lmb200_handle* out) {
   similarity_lut_variant(cfg->similarity_lut == LMB200_SIMLUT_LINEAR, h->sim_lut);
   default_normal_lut(h->normal_lut);
   h->normal_lut_standin = true;
+  { const char* e = std::getenv("LMB200_NO_GRAPH"); h->use_graph = !(e && *e && *e != '0'); }
   *out = h;
   return LMB200_OK;
 }
@@ -117,7 +118,7 @@ void lmb200_destroy(lmb200_handle h) {
     for (int m = 0; m < LMB200_MAX_MODALITIES; ++m) { h->d_depth[m].release(); h->d_dnraw[m].release(); }
     for (int l = 0; l < LMB200_MAX_LEVELS; ++l) { h->d_hdr[l].release(); h->d_feat[l].release(); h->d_offs[l].release(); }
     lmh::DevBuf* bufs[] = {&h->d_frames, &h->d_table, &h->d_normal_lut, &h->d_sel, &h->d_mag, &h->d_dnidx, &h->d_cand, &h->d_ctr,
-                           &h->d_tpl_start, &h->d_tpl_cnt, &h->d_tpl_alive, &h->d_out, &h->d_gather_send, &h->d_gather_recv, &h->d_resp_sum, &h->d_fin_send, &h->d_fin_recv};
+                           &h->d_tpl_start, &h->d_tpl_cnt, &h->d_tpl_alive, &h->d_out, &h->d_gather_send, &h->d_gather_recv, &h->d_resp_sum, &h->d_fin_send, &h->d_fin_recv, &h->d_hue_bits};
     for (auto* b : bufs) b->release();
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -130,6 +131,8 @@ void lmb200_destroy(lmb200_handle h) {
     }
     for (auto e : h->group_done) cudaEventDestroy(e);
     for (auto& mk : h->resident_marks) if (mk.ev) cudaEventDestroy(mk.ev);
+    if (h->upload_ev) cudaEventDestroy(h->upload_ev);
+    if (h->match_graph) cudaGraphExecDestroy(h->match_graph);
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < LMB200_LANES; ++i) {

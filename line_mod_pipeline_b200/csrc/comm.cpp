@@ -23,12 +23,14 @@ typedef int (*fn_destroy)(void*);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 typedef int (*fn_group)(void);
+typedef int (*fn_split)(void*, int, int, void**, void*);
 
 struct Nccl {
   void* lib = nullptr;
   fn_get_uid get_uid = nullptr; fn_init_rank init_rank = nullptr; fn_destroy destroy = nullptr;
   fn_allgather allgather = nullptr; fn_errstr errstr = nullptr;
   fn_group group_start = nullptr, group_end = nullptr;
+  fn_split split = nullptr;
   std::string err;
 };
 Nccl g_nccl;
@@ -47,6 +49,7 @@ void load_nccl() {
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
   g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
   g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
+  g_nccl.split = (fn_split)dlsym(g_nccl.lib, "ncclCommSplit");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allgather) g_nccl.err = "libnccl lacks a required symbol";
 }
 bool nccl_ok(std::string& err) {
@@ -80,18 +83,29 @@ int comm_init(lmb200_detector* h, const uint8_t* id128, int rank, int world) {
   rc = g_nccl.init_rank(&comm, world, id, rank);
   if (rc) return set_error(h, LMB200_E_COMM, nccl_msg("ncclCommInitRank", rc));
   h->nccl_comm = comm; h->comm_rank = rank; h->comm_world = world;
+  // A second communicator over the same ranks for the result-fetch collectives (copy lane): NCCL serialises the
+  // operations of ONE communicator in issue order, which would make the match gather of step k-1 wait for the quantized-map
+  // all-gather of step k+1 that the compute lane has already queued.  Optional: older NCCL without ncclCommSplit shares one.
+  h->nccl_comm_fetch = nullptr;
+  if (g_nccl.split && world > 1) {
+    void* c2 = nullptr;
+    if (g_nccl.split(comm, 0, rank, &c2, nullptr) == 0 && c2) h->nccl_comm_fetch = c2;
+  }
   return LMB200_OK;
 }
 
 int comm_destroy(lmb200_detector* h) {
+  if (h->nccl_comm_fetch && g_nccl.destroy) g_nccl.destroy(h->nccl_comm_fetch);
+  h->nccl_comm_fetch = nullptr;
   if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
   h->nccl_comm = nullptr; h->comm_world = 1; h->comm_rank = 0;
   return LMB200_OK;
 }
 
-int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st) {
+int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st, bool fetch_path) {
   if (!h->nccl_comm) return set_error(h, LMB200_E_COMM, "communicator not initialised (lmb200_comm_init)");
-  int rc = g_nccl.allgather(send, recv, bytes, /*ncclInt8*/ 0, h->nccl_comm, st);
+  void* comm = (fetch_path && h->nccl_comm_fetch) ? h->nccl_comm_fetch : h->nccl_comm;
+  int rc = g_nccl.allgather(send, recv, bytes, /*ncclInt8*/ 0, comm, st);
   if (rc) return set_error(h, LMB200_E_COMM, nccl_msg("ncclAllGather", rc));
   return LMB200_OK;
 }

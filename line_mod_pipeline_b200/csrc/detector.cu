@@ -76,8 +76,12 @@ int ensure_device(lmb200_detector* h) {
   if (dev >= n) return set_error(h, LMB200_E_INVALID, "device ordinal out of range");
   CU(cudaSetDevice(dev));
   h->device = dev;
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < LMB200_LANES; ++i) {
-    CU(cudaStreamCreateWithFlags(&h->lanes[i].stream, cudaStreamNonBlocking));
+    // lane 1 (copies, NCCL, result fetches) runs at the highest priority: its small kernels and collectives must not queue
+    // behind the compute lanes' grids of the next step
+    CU(cudaStreamCreateWithPriority(&h->lanes[i].stream, cudaStreamNonBlocking, i == 1 ? prio_hi : prio_lo));
   }
   h->device_ready = true;
   return LMB200_OK;
@@ -154,6 +158,7 @@ static int upload_luts(lmb200_detector* h) {
   CU(cudaMemcpy(h->d_table.p, table, sizeof(table), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_normal_lut.p, h->normal_lut, 8000, cudaMemcpyHostToDevice));
   h->luts_dirty = false;
+  h->plan_epoch++;
   return LMB200_OK;
 }
 
@@ -213,6 +218,7 @@ static void free_host_mirrors(lmb200_detector* h) {
 }
 
 static int alloc_match_buffers(lmb200_detector* h) {
+  h->plan_epoch++;
   const int S = h->slots;
   h->nsel_stride = std::max(1, h->ntpl);
   ALLOC(h->d_cand, (size_t)S * h->cand_cap * sizeof(Cand));
@@ -323,6 +329,7 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
         ALLOC(h->d_dnraw[m], h->levels[0].q_stride * S);
       }
     h->rows = rows; h->cols = cols; h->slots = S;
+    h->plan_epoch++;
     if (h->cand_cap <= 0) h->cand_cap = h->cfg.candidate_capacity > 0 ? h->cfg.candidate_capacity : 16384;
     if (h->out_cap <= 0) h->out_cap = h->cand_cap;
     h->nsel_stride = 0;
@@ -357,6 +364,7 @@ static int ensure_plan(lmb200_detector* h, int rows, int cols) {
         h->tpl_cost[gi++] = cost;
       }
     h->plan_dirty = false;
+    h->plan_epoch++;
     h->sel_key.clear();
   }
   return LMB200_OK;
@@ -420,6 +428,7 @@ static int ensure_selection(lmb200_detector* h, const char* const* class_ids, in
   ALLOC(h->d_sel, std::max<size_t>(1, sel.size()) * sizeof(int));
   if (!sel.empty()) CU(cudaMemcpy(h->d_sel.p, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice));
   h->sel_key = key;
+  h->plan_epoch++;
   return LMB200_OK;
 }
 
@@ -657,11 +666,20 @@ static int grow_capacity(lmb200_detector* h) {
 // D2H of counts + list heads, then per-frame record vectors in generation order (global template
 // index in .tsel).  Returns +1 (nothing consumed) when a device-side store overflowed: the caller
 // grows the stores (grow_capacity) and redoes the template side — linear memories stay resident.
-static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out) {
+// D2H of the counters and list heads of slots [first, first+count) (also captured into the single-frame CUDA graph)
+static int enqueue_result_copies(lmb200_detector* h, int first, int count, cudaStream_t st) {
   CU(cudaMemcpyAsync(h->h_ctr + first, h->d_ctr.as<SlotCtr>() + first, sizeof(SlotCtr) * count, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpy2DAsync(h->h_out + (size_t)first * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
                        h->d_out.as<Cand>() + (size_t)first * h->out_cap, (size_t)h->out_cap * sizeof(Cand),
                        (size_t)h->h_head * sizeof(Cand), count, cudaMemcpyDeviceToHost, st));
+  return LMB200_OK;
+}
+
+static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out, bool copies_enqueued = false) {
+  if (!copies_enqueued) {
+    int rc = enqueue_result_copies(h, first, count, st);
+    if (rc) return rc;
+  }
   CU(cudaStreamSynchronize(st));
   for (int i = 0; i < count; ++i)
     if (h->h_ctr[first + i].overflow != 0 || h->h_ctr[first + i].out_count > h->out_cap) return 1;
@@ -704,13 +722,14 @@ static int revalidate_slots(lmb200_detector* h, int first, int count) {
   return LMB200_OK;
 }
 
-static int fetch_grow(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out) {
+static int fetch_grow(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out, bool copies_enqueued = false) {
   {
     int rc = revalidate_slots(h, first, count);
     if (rc) return rc;
   }
   for (;;) {
-    int rc = fetch_raw(h, first, count, st, out);
+    int rc = fetch_raw(h, first, count, st, out, copies_enqueued);
+    copies_enqueued = false;
     if (rc <= 0) return rc;
     float thr = h->slot_threshold[first];
     rc = grow_capacity(h);
@@ -791,13 +810,33 @@ int lmb200_upload_frames(lmb200_handle h, const lmb200_image* frames, int n_fram
   int rc = prepare(h, frames, n_frames, n_sources, nullptr, 0);
   if (rc) return rc;
   if (first_slot < 0 || first_slot + n_frames > h->slots) return set_error(h, LMB200_E_INVALID, "slot range exceeds max_batch");
-  cudaStream_t st = h->lanes[0].stream;
+  // "upload_async": the copies run on a lane of their own, behind the last match that read these slots, and the next
+  // match on the compute lane waits for them — H2D of step k+1 overlaps the kernels of step k
+  cudaStream_t st = h->upload_async ? h->lanes[2].stream : h->lanes[0].stream;
+  if (h->upload_async)
+    for (auto& mk : h->resident_marks)
+      if (mk.ev && mk.first < first_slot + n_frames && first_slot < mk.first + mk.count) CU(cudaStreamWaitEvent(st, mk.ev, 0));
   for (int f = 0; f < n_frames; ++f) {
     ProfScope ps(h, LMB200_K_UPLOAD, st);
     rc = upload_one(h, frames + (size_t)f * n_sources, first_slot + f, st);
     if (rc) return rc;
   }
-  if (!h->upload_async) CU(cudaStreamSynchronize(st));  // "upload_async": pinned frames that stay valid until the next fetch
+  if (h->upload_async) {
+    if (!h->upload_ev) CU(cudaEventCreateWithFlags(&h->upload_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->upload_ev, st));
+    h->upload_pending = true;
+  } else {
+    CU(cudaStreamSynchronize(st));
+  }
+  return LMB200_OK;
+}
+
+// the compute lane picks up frames uploaded asynchronously
+static int wait_async_upload(lmb200_detector* h) {
+  if (h->upload_pending) {
+    CU(cudaStreamWaitEvent(h->lanes[0].stream, h->upload_ev, 0));
+    h->upload_pending = false;
+  }
   return LMB200_OK;
 }
 
@@ -812,6 +851,8 @@ int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float thre
   rc = ensure_selection(h, class_ids, n_class_ids);
   if (rc) return rc;
   cudaStream_t st = h->lanes[0].stream;
+  rc = wait_async_upload(h);
+  if (rc) return rc;
   rc = run_frame_side(h, first_slot, count, st);
   if (rc) return rc;
   rc = run_matching(h, first_slot, count, threshold, st);
@@ -850,6 +891,8 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
   const int n = count / world, own = first_slot + h->comm_rank * n;
   cudaStream_t st = h->lanes[0].stream;
+  rc = wait_async_upload(h);
+  if (rc) return rc;
   rc = run_frame_side(h, own, n, st, FS_QUANTIZE);
   if (rc) return rc;
   rc = comm_group_begin(h);
@@ -987,12 +1030,42 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
   } else {
     h->masks_in_use = false;
   }
-  rc = run_frame_side(h, 0, 1, st);
-  if (rc) return rc;
-  rc = run_matching(h, 0, 1, threshold, st);
-  if (rc) return rc;
+  // Single-frame latency path (BASELINE configs[1] literally): the ~15 launches + memsets + result copies of one frame are
+  // captured once into a CUDA graph and replayed with one launch; any change of plan, template set, selection, stores or
+  // threshold re-captures (plan_epoch).  Masks, profiling and LMB200_NO_GRAPH=1 take the plain stream path.
+  bool graphed = false;
+  if (!masks && !h->profiling && h->use_graph) {
+    u32 thr_bits; std::memcpy(&thr_bits, &threshold, 4);
+    if (!h->match_graph || h->graph_epoch != h->plan_epoch || h->graph_thr_bits != thr_bits || h->graph_early_exit != h->early_exit) {
+      if (h->match_graph) { cudaGraphExecDestroy(h->match_graph); h->match_graph = nullptr; }
+      lmb200_profile before = h->prof;
+      cudaGraph_t g = nullptr;
+      CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int r1 = run_frame_side(h, 0, 1, st);
+      int r2 = r1 ? r1 : run_matching(h, 0, 1, threshold, st);
+      int r3 = r2 ? r2 : enqueue_result_copies(h, 0, 1, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (r3 || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return r3 ? r3 : cuda_fail(h, ce, "cudaStreamEndCapture"); }
+      ce = cudaGraphInstantiate(&h->match_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { h->match_graph = nullptr; return cuda_fail(h, ce, "cudaGraphInstantiate"); }
+      for (int k = 0; k < LMB200_K_COUNT; ++k) h->graph_launches[k] = h->prof.launches[k] - before.launches[k];
+      h->prof = before;   // the capture itself launched nothing
+      h->graph_epoch = h->plan_epoch; h->graph_thr_bits = thr_bits; h->graph_early_exit = h->early_exit;
+    }
+    CU(cudaGraphLaunch(h->match_graph, st));
+    for (int k = 0; k < LMB200_K_COUNT; ++k) h->prof.launches[k] += h->graph_launches[k];
+    h->prof.frames += 1; h->prof.bytes_coarse += h->sel_bytes_coarse;
+    h->slot_threshold[0] = threshold; h->slot_gen[0] = h->buffer_generation;
+    graphed = true;
+  } else {
+    rc = run_frame_side(h, 0, 1, st);
+    if (rc) return rc;
+    rc = run_matching(h, 0, 1, threshold, st);
+    if (rc) return rc;
+  }
   std::vector<std::vector<Cand>> raw;
-  rc = fetch_grow(h, 0, 1, st, raw);
+  rc = fetch_grow(h, 0, 1, st, raw, graphed);
   h->masks_in_use = false;
   if (rc) return rc;
   if (quantized_out) {
@@ -1060,13 +1133,25 @@ static int batch_enqueue(lmb200_detector* h, BatchTicket& tk) {
     h->group_used.assign(G, 0);
     h->b_groups = G;
   }
-  // chunk schedule: ramp up (chunk/3, 2*chunk/3, chunk, chunk, ...) so compute starts after a short first copy
+  // chunk schedule.  Blocking call: ramp up (chunk/3, 2*chunk/3, chunk, ...) so compute starts after a short first copy.
+  // Streaming (submit/collect): the previous batch is still computing when this one starts copying, so there is nothing to
+  // hide — equal chunks, as large as the slot groups allow (kernels are more efficient on larger launches).  The tail is
+  // balanced instead of leaving a runt chunk.
   tk.cf0.clear(); tk.ccnt.clear();
-  for (int f = 0, k = 0; f < n_frames; ++k) {
-    int want = k == 0 ? std::max(1, chunk / 3) : (k == 1 ? std::max(1, 2 * chunk / 3) : chunk);
-    int cnt = std::min(want, n_frames - f);
-    tk.cf0.push_back(f); tk.ccnt.push_back(cnt);
-    f += cnt;
+  {
+    int f = 0;
+    if (!tk.streaming)
+      for (int k = 0; k < 2 && f < n_frames; ++k) {
+        int cnt = std::min(std::max(1, (k + 1) * chunk / 3), n_frames - f);
+        tk.cf0.push_back(f); tk.ccnt.push_back(cnt);
+        f += cnt;
+      }
+    const int rest = n_frames - f, nc = (rest + chunk - 1) / chunk;
+    for (int k = 0; k < nc; ++k) {
+      int cnt = rest / nc + (k < rest % nc ? 1 : 0);
+      tk.cf0.push_back(f); tk.ccnt.push_back(cnt);
+      f += cnt;
+    }
   }
   const int nchunks = (int)tk.cf0.size();
   // per-frame pinned staging for the results of this batch
@@ -1217,7 +1302,7 @@ int lmb200_match_batch_collect(lmb200_handle h, int ticket, lmb200_match_rec* ou
       bool store = false;
       for (int f = 0; f < tk.n_frames; ++f) store |= tk.b_ctr[f].overflow != 0 || tk.b_ctr[f].out_count > h->out_cap;
       if (store) { rc = grow_capacity(h); if (rc) { tk.active = false; return rc; } }
-      else { h->h_head = std::min(h->out_cap, h->h_head * 4); h->buffer_generation++; }
+      else { h->h_head = std::min(h->out_cap, h->h_head * 4); h->buffer_generation++; h->plan_epoch++; }
     }
     std::vector<const char*> ids;
     for (auto& s : tk.class_ids) ids.push_back(s.c_str());
@@ -1245,10 +1330,81 @@ int lmb200_host_alloc(size_t bytes, void** out) {
 }
 int lmb200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LMB200_OK : LMB200_E_CUDA; }
 
+// ---------------------------------------------------------------- post-match colour check
+int lmb200_postmatch_color(lmb200_handle h, int slot, const uint8_t* lower_hsv, const uint8_t* upper_hsv,
+                           const lmb200_match_rec* matches, size_t n, int* inside, int* total) {
+  if (!h || !lower_hsv || !upper_hsv || (n && (!matches || !inside || !total))) return set_error(h, LMB200_E_INVALID, "bad arguments");
+  if (!h->device_ready || h->rows == 0 || slot < 0 || slot >= h->slots) return set_error(h, LMB200_E_INVALID, "no frame resident in that slot (call lmb200_match / lmb200_upload_frames first)");
+  cudaSetDevice(h->device);
+  int rc = ensure_plan(h, h->rows, h->cols);
+  if (rc) return rc;
+  const int M = h->cfg.num_modalities;
+  int mc = -1;
+  for (int m = 0; m < M && mc < 0; ++m) if (h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT) mc = m;
+  if (mc < 0) return set_error(h, LMB200_E_INVALID, "the colour check needs a ColorGradient modality (its BGR source image)");
+  if (n == 0) return LMB200_OK;
+  cudaStream_t st = h->lanes[0].stream;
+  const int wpr = (h->cols + 31) / 32;
+  ALLOC(h->d_hue_bits, (size_t)h->rows * wpr * sizeof(u32));
+  LevelBuffers& l0 = h->levels[0];
+  launch_hsv_inrange_bits(l0.bgr[mc].as<u8>() + (size_t)slot * l0.bgr_stride, h->rows, h->cols, lower_hsv, upper_hsv, h->d_hue_bits.as<u32>(), st);
+  // (class_index, template_id) -> global template index
+  std::vector<int> first(h->class_list.size() + 1, 0);
+  for (int i = 0; i < h->ntpl; ++i) first[h->g_class[i] + 1] = i + 1;
+  for (size_t c = 1; c < first.size(); ++c) first[c] = std::max(first[c], first[c - 1]);
+  std::vector<int2> xy(n);
+  std::vector<int> gi(n);
+  for (size_t i = 0; i < n; ++i) {
+    xy[i] = make_int2(matches[i].x, matches[i].y);
+    const int c = matches[i].class_index, t = matches[i].template_id;
+    gi[i] = (c >= 0 && c < (int)h->class_list.size() && t >= 0 && first[c] + t < first[c + 1]) ? first[c] + t : -1;
+  }
+  ScopedDevBuf d_xy, d_g, d_res;
+  ALLOC(d_xy, n * sizeof(int2)); ALLOC(d_g, n * sizeof(int)); ALLOC(d_res, n * sizeof(int2));
+  CU(cudaMemcpyAsync(d_xy.p, xy.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_g.p, gi.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+  launch_template_mask_count(d_xy.as<int2>(), (int)n, d_g.as<int>(), h->d_hdr[0].as<TplHdr>(), h->d_feat[0].as<u32>(), M, h->rows, h->cols,
+                             h->d_hue_bits.as<u32>(), d_res.as<int2>(), st);
+  CU(cudaGetLastError());
+  std::vector<int2> res(n);
+  CU(cudaMemcpyAsync(res.data(), d_res.p, n * sizeof(int2), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < n; ++i) { inside[i] = res[i].x; total[i] = res[i].y; }
+  return LMB200_OK;
+}
+
+// HighLevelLineMOD::groupSimilarMatches + discardSmallMatchGroups (src/HighLevelLinemod.cpp:206-253), host code: the greedy
+// grouping depends on the order of `matches` (the first member anchors its group), so it is restated sequentially.
+int lmb200_group_matches(const lmb200_match_rec* matches, size_t n, float radius_threshold, float discard_group_ratio,
+                         int* group_of_match, int* n_groups) {
+  if ((n && (!matches || !group_of_match)) || !n_groups) return LMB200_E_INVALID;
+  struct G { int x, y; std::vector<size_t> idx; };
+  std::vector<G> groups;
+  for (size_t i = 0; i < n; ++i) {
+    bool found = false;
+    for (size_t q = 0; q < groups.size() && !found; ++q) {
+      const double dx = (double)matches[i].x - groups[q].x, dy = (double)matches[i].y - groups[q].y;
+      if (std::sqrt(dx * dx + dy * dy) < radius_threshold) { groups[q].idx.push_back(i); found = true; }  // cv::norm(Point) < float
+    }
+    if (!found) { G g; g.x = matches[i].x; g.y = matches[i].y; g.idx.push_back(i); groups.push_back(g); }
+  }
+  size_t biggest = 0;
+  for (auto& g : groups) biggest = std::max(biggest, g.idx.size());
+  for (size_t i = 0; i < n; ++i) group_of_match[i] = -1;
+  int kept = 0;
+  for (auto& g : groups) {
+    const float ratio = (float)(g.idx.size() * 100 / biggest);   // integer division first, like the reference
+    if (ratio > discard_group_ratio) { for (size_t i : g.idx) group_of_match[i] = kept; ++kept; }
+  }
+  *n_groups = kept;
+  return LMB200_OK;
+}
+
 int lmb200_set_option(lmb200_handle h, const char* name, int value) {
   if (!h || !name) return LMB200_E_INVALID;
   if (std::strcmp(name, "early_exit") == 0) { h->early_exit = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "upload_async") == 0) { h->upload_async = value != 0; return LMB200_OK; }
+  if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return LMB200_OK; }
   return set_error(h, LMB200_E_INVALID, std::string("unknown option ") + name);
 }
 
@@ -1662,31 +1818,18 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   const bool trace = std::getenv("LMB200_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double tt[5] = {now(), 0, 0, 0, 0};
-  // 1. local overflow check (a rank that overflowed redoes its own template side; no collective involved)
+  // 1+2. One round trip: a kernel packs {count, overflow flag, counters, first gather_cap matches} of every frame, the
+  //      buffers are all-gathered and copied to pinned host memory.  Every rank sees every flag and count, so all ranks
+  //      take the same decisions: a rank that overflowed its candidate store grows it and redoes its template side, a list
+  //      longer than gather_cap doubles the capacity, and the gather is repeated.
   {
     int rc = revalidate_slots(h, first_slot, count);
     if (rc) return rc;
   }
+  constexpr int HDR = 2;
+  if (h->gather_cap <= 0) h->gather_cap = 254;  // 4 KB per frame and rank; doubles when a list is longer
   for (;;) {
-    CU(cudaMemcpyAsync(h->h_ctr + first_slot, h->d_ctr.as<SlotCtr>() + first_slot, sizeof(SlotCtr) * count, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    bool over = false;
-    for (int i = 0; i < count; ++i) over |= h->h_ctr[first_slot + i].overflow != 0 || h->h_ctr[first_slot + i].out_count > h->out_cap;
-    if (!over) break;
-    float thr = h->slot_threshold[first_slot];
-    int rc = grow_capacity(h);
-    if (rc) return rc;
-    rc = run_matching(h, first_slot, count, thr, h->lanes[0].stream);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(h->lanes[0].stream));
-  }
-  for (int i = 0; i < count; ++i) { h->prof.bytes_local += (long long)h->h_ctr[first_slot + i].local_bytes; h->prof.chunks_coarse += (long long)h->h_ctr[first_slot + i].coarse_chunks; }
-  tt[1] = now();
-  // 2. fixed-capacity send buffer per frame: record 0 = {count,..}, then up to gather_cap records.
-  //    Every rank sees every count after the gather, so all ranks take the same grow decision.
-  if (h->gather_cap <= 0) h->gather_cap = 255;  // 4 KB per frame and rank; doubles when a list is longer
-  for (;;) {
-    const size_t pitch = (size_t)(1 + h->gather_cap) * sizeof(Cand);
+    const size_t pitch = (size_t)(HDR + h->gather_cap) * sizeof(Cand);
     const size_t bytes = pitch * count;
     ALLOC(h->d_gather_send, bytes);
     ALLOC(h->d_gather_recv, bytes * world);
@@ -1695,22 +1838,38 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       CU(cudaHostAlloc((void**)&h->h_gather, bytes * world, cudaHostAllocDefault));
       h->h_gather_bytes = bytes * world;
     }
-    CU(cudaMemsetAsync(h->d_gather_send.p, 0, bytes, st));
-    CU(cudaMemcpy2DAsync(h->d_gather_send.p, pitch, &h->d_ctr.as<SlotCtr>()[first_slot].out_count, sizeof(SlotCtr), sizeof(int), count,
-                         cudaMemcpyDeviceToDevice, st));
-    size_t w = (size_t)std::min(h->gather_cap, h->out_cap) * sizeof(Cand);
-    CU(cudaMemcpy2DAsync((char*)h->d_gather_send.p + sizeof(Cand), pitch, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap,
-                         (size_t)h->out_cap * sizeof(Cand), w, count, cudaMemcpyDeviceToDevice, st));
-    int rc = comm_allgather(h, h->d_gather_send.p, h->d_gather_recv.p, bytes, st);
+    launch_gather_pack(h->d_ctr.as<SlotCtr>() + first_slot, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap, h->out_cap,
+                       h->d_gather_send.as<Cand>(), h->gather_cap, count, st);
+    int rc = comm_allgather(h, h->d_gather_send.p, h->d_gather_recv.p, bytes, st, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_gather, h->d_gather_recv.p, bytes * world, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     int maxc = 0;
+    bool any_over = false, my_over = false;
     for (int r = 0; r < world; ++r)
-      for (int i = 0; i < count; ++i) maxc = std::max(maxc, h->h_gather[((size_t)r * count + i) * (1 + h->gather_cap)].tsel);
+      for (int i = 0; i < count; ++i) {
+        const Cand& hd = h->h_gather[((size_t)r * count + i) * (HDR + h->gather_cap)];
+        maxc = std::max(maxc, hd.tsel);
+        if (hd.x) { any_over = true; if (r == h->comm_rank) my_over = true; }
+      }
+    if (my_over) {
+      float thr = h->slot_threshold[first_slot];
+      rc = grow_capacity(h);
+      if (rc) return rc;
+      rc = run_matching(h, first_slot, count, thr, h->lanes[0].stream);
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(h->lanes[0].stream));
+    }
+    if (any_over) continue;
     if (maxc <= h->gather_cap) break;
     while (h->gather_cap < maxc) h->gather_cap *= 2;
   }
+  for (int i = 0; i < count; ++i) {
+    const Cand& st1 = h->h_gather[((size_t)h->comm_rank * count + i) * (HDR + h->gather_cap) + 1];
+    h->prof.bytes_local += (long long)(((unsigned long long)(u32)st1.x << 32) | (u32)st1.tsel);
+    h->prof.chunks_coarse += (long long)(((unsigned long long)(u32)__builtin_bit_cast(int, st1.sim) << 32) | (u32)st1.y);
+  }
+  tt[1] = now();
   if (h->profiling) collect_profile(h);
   tt[2] = now();
   // 3. restore reference generation order (rank-ordered concatenation for contiguous shards; ordered by selection
@@ -1729,8 +1888,8 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       for (int i = a; i < b; ++i) {
         std::vector<Cand>& all = alls[i - lo];
         for (int r = 0; r < world; ++r) {
-          const Cand* rec = h->h_gather + ((size_t)r * count + i) * (1 + h->gather_cap);
-          all.insert(all.end(), rec + 1, rec + 1 + rec[0].tsel);
+          const Cand* rec = h->h_gather + ((size_t)r * count + i) * (HDR + h->gather_cap);
+          all.insert(all.end(), rec + HDR, rec + HDR + rec[0].tsel);
         }
         if (h->shard_interleaved)
           std::stable_sort(all.begin(), all.end(), [h](const Cand& a, const Cand& b) { return h->pos_of_g[a.tsel] < h->pos_of_g[b.tsel]; });
@@ -1763,7 +1922,7 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     int fin_cap = 0;
     for (int i = 0; i < count; ++i) {
       int tot = 0;
-      for (int r = 0; r < world; ++r) tot += h->h_gather[((size_t)r * count + i) * (1 + h->gather_cap)].tsel;
+      for (int r = 0; r < world; ++r) tot += h->h_gather[((size_t)r * count + i) * (HDR + h->gather_cap)].tsel;
       fin_cap = std::max(fin_cap, tot);
     }
     const size_t pitch2 = (size_t)(1 + fin_cap), bytes2 = (size_t)per * pitch2 * sizeof(lmb200_match_rec);
@@ -1788,7 +1947,7 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       if (i < hi) { h->prof.candidates += (long long)alls[j].size(); h->prof.matches += (long long)n; }
     }
     CU(cudaMemcpyAsync(h->d_fin_send.p, mine, bytes2, cudaMemcpyHostToDevice, st));
-    int rc = comm_allgather(h, h->d_fin_send.p, h->d_fin_recv.p, bytes2, st);
+    int rc = comm_allgather(h, h->d_fin_send.p, h->d_fin_recv.p, bytes2, st, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_fin, h->d_fin_recv.p, bytes2 * world, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -140,6 +140,7 @@ struct lmb200_detector {
   lmh::DevBuf d_depth[LMB200_MAX_MODALITIES], d_dnraw[LMB200_MAX_MODALITIES], d_mag, d_dnidx;
   size_t depth_stride = 0;
   lmh::DevBuf d_frames; size_t frame_bytes = 0, src_off[LMB200_MAX_MODALITIES] = {0, 0, 0, 0};  // [slots][sources back to back]
+  lmh::DevBuf d_hue_bits;                           // post-match colour check: bit mask of the in-range pixels of one frame
   lmh::DevBuf d_resp_sum;                           // [slots][MAX_MOD] response sums of the coarsest linear memories
   lmh::DevBuf d_cand, d_ctr, d_tpl_start, d_tpl_cnt, d_tpl_alive, d_out;
   int nsel_stride = 0;
@@ -157,6 +158,10 @@ struct lmb200_detector {
 
   // profiling
   bool profiling = false;
+  cudaEvent_t upload_ev = nullptr; bool upload_pending = false;
+  // single-frame CUDA graph (lmb200_match)
+  cudaGraphExec_t match_graph = nullptr; long long plan_epoch = 0, graph_epoch = -1; uint32_t graph_thr_bits = 0; bool graph_early_exit = true;
+  long long graph_launches[LMB200_K_COUNT] = {0}; bool use_graph = true;
   bool upload_async = false;             // lmb200_set_option("upload_async"): lmb200_upload_frames returns without synchronising
   bool early_exit = true;                // lmb200_set_option("early_exit"): measurement runs switch the coarse kernel's exact exit off
   std::vector<lmh::ProfRec> prof_pending;
@@ -166,6 +171,7 @@ struct lmb200_detector {
 
   // comm
   void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+  void* nccl_comm_fetch = nullptr;          // second communicator (ncclCommSplit) for the result-fetch collectives
   lmh::DevBuf d_gather_send, d_gather_recv; int gather_cap = 0;
   lmk::Cand* h_gather = nullptr; size_t h_gather_bytes = 0;
   lmh::DevBuf d_fin_send, d_fin_recv;          // finished (sorted + unique) per-frame lists, second all-gather
@@ -204,7 +210,7 @@ void set_create_error(const std::string& msg);
 int comm_unique_id(uint8_t* id128, std::string& err);
 int comm_init(lmb200_detector* h, const uint8_t* id128, int rank, int world);
 int comm_destroy(lmb200_detector* h);
-int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st);
+int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st, bool fetch_path = false);
 int comm_group_begin(lmb200_detector* h);
 int comm_group_end(lmb200_detector* h);
 void default_normal_lut(uint8_t* out8000);

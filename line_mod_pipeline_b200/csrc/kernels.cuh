@@ -177,5 +177,14 @@ void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaS
 void launch_similarity_map(const MatchParams& mp, const LevelParams& lp, bool wide, u16* map, cudaStream_t st);
 // Ordered compaction: out[frame][0..n) in generation order, count[frame] = n (may exceed cap -> overflow).
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st);
+// multi-GPU: per-frame send buffer {2 header records, first min(out_count, gather_cap) matches} for the match all-gather
+void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int gather_cap, int frames, cudaStream_t st);
+
+// ------------------------------------------------------------------ post-match colour check (kernels_postmatch.cu)
+// bits: [rows][(cols+31)/32] u32, bit x%32 of word x/32 = pixel (y, x) lies in the HSV range (cvtColor BGR2HSV + inRange)
+void launch_hsv_inrange_bits(const u8* bgr, int rows, int cols, const u8 lower[3], const u8 upper[3], u32* bits, cudaStream_t st);
+// per match: result = {countNonZero(hue & templateMask), countNonZero(templateMask)}; (-1,-1) when the hull leaves the image
+void launch_template_mask_count(const int2* xy, int n, const int* g_of_match, const TplHdr* hdr0, const u32* feat0, int M, int rows,
+                                int cols, const u32* hue_bits, int2* result, cudaStream_t st);
 
 }  // namespace lmk

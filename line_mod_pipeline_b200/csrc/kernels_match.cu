@@ -771,6 +771,31 @@ __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __rest
   }
 }
 
+// Send buffer of the template-sharded match gather, one block per frame: two header records
+//   {out_count, overflow flag, 0, 0}   {local_bytes lo, hi, coarse_chunks lo, hi}
+// followed by the first min(out_count, gather_cap) packed matches (one launch instead of a memset and two 2-D copies).
+__global__ void __launch_bounds__(256) gather_pack_kernel(const SlotCtr* __restrict__ ctr, const Cand* __restrict__ out, int out_cap,
+                                                          Cand* __restrict__ send, int gather_cap) {
+  const int f = blockIdx.x;
+  const SlotCtr c = ctr[f];
+  Cand* dst = send + (size_t)f * (2 + gather_cap);
+  if (threadIdx.x == 0) {
+    Cand h0, h1;
+    h0.tsel = c.out_count; h0.x = (c.overflow != 0 || c.out_count > out_cap) ? 1 : 0; h0.y = 0; h0.sim = 0.f;
+    h1.tsel = (int)(u32)c.local_bytes; h1.x = (int)(u32)(c.local_bytes >> 32);
+    h1.y = (int)(u32)c.coarse_chunks; h1.sim = __int_as_float((int)(u32)(c.coarse_chunks >> 32));
+    dst[0] = h0; dst[1] = h1;
+  }
+  const int n = min(min(c.out_count, out_cap), gather_cap);
+  const uint4* src = reinterpret_cast<const uint4*>(out + (size_t)f * out_cap);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + 2);
+  for (int i = threadIdx.x; i < n; i += 256) d4[i] = src[i];
+}
+
+void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int gather_cap, int frames, cudaStream_t st) {
+  if (frames > 0) gather_pack_kernel<<<frames, 256, 0, st>>>(ctr, out, out_cap, send, gather_cap);
+}
+
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st) {
   if (mp.frames <= 0) return;
   pack_kernel<<<mp.frames, 1024, 0, st>>>(mp, out, out_cap);

@@ -204,4 +204,50 @@ int lmb200_load_ply(const char* path, double** vertices, int* n_vertices, int** 
 
 void lmb200_free(void* p) { std::free(p); }
 
+// Benchmark::calculateErrorHodan (src/Benchmark.cpp:18-38) with calculateVisibilityMasks (:133-154), restated per pixel.
+// The reference works on CV_16U images: Mat subtraction saturates at 0, cv::threshold(..., 65536, ...) yields 65535, and the
+// masks are combined with bitwise and/or of those 16-bit words, which is what the nested conditions below spell out:
+//   gtVis  = gt > 1 and not (gt - in > visThr)                      (:138-142)
+//   estVis = (est > 1 and not (est - in > visThr)) | (gtVis & est)  (:144-150; the `&` is bitwise on the depth VALUE)
+//   inter  = gtVis & estVis, comb = gtVis | estVis                  (:152-153)
+//   ok     = inter & (|gt - est| <= errThr)                         (:28-30)
+//   error  = 1 - countNonZero(ok) / countNonZero(comb)              (:31-32; 0/0 -> NaN like the reference's float division)
+int lmb200_hodan_error(const uint16_t* input_depth, const uint16_t* gt_render, const uint16_t* est_render, int rows, int cols,
+                       int visibility_threshold, int error_threshold, float* error, long long* n_ok, long long* n_comb) {
+  if (!input_depth || !gt_render || !est_render || !error || rows <= 0 || cols <= 0) return LMB200_E_INVALID;
+  long long ok = 0, comb = 0;
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = 0; i < n; ++i) {
+    const int in = input_depth[i], gt = gt_render[i], est = est_render[i];
+    const unsigned gt_occl = (gt > in && gt - in > visibility_threshold) ? 65535u : 0u;    // saturating gt - in, then THRESH_BINARY
+    const unsigned est_occl = (est > in && est - in > visibility_threshold) ? 65535u : 0u;
+    const unsigned gt_bin = gt > 1 ? 65535u : 0u, est_bin = est > 1 ? 65535u : 0u;
+    const unsigned gt_vis = gt_bin > gt_occl ? gt_bin - gt_occl : 0u;                        // saturating subtraction
+    unsigned est_vis = est_bin > est_occl ? est_bin - est_occl : 0u;
+    est_vis |= (gt_vis & (unsigned)est);
+    const unsigned inter = gt_vis & est_vis, cmb = gt_vis | est_vis;
+    const int ad = gt > est ? gt - est : est - gt;
+    const unsigned close = ad > error_threshold ? 0u : 65535u;                               // THRESH_BINARY_INV
+    if (inter & close) ++ok;
+    if (cmb) ++comb;
+  }
+  *error = 1.0f - (float)ok / (float)comb;
+  if (n_ok) *n_ok = ok;
+  if (n_comb) *n_comb = comb;
+  return LMB200_OK;
+}
+
+// The whole call of PoseDetection.cpp:99: render the model at the ground-truth and at the estimated pose (Benchmark::renderPose
+// -> OpenGLRender::renderDepthToFrontBuff, here the headless rasteriser) and score them against the input depth image.
+// rotations: two 3x3 row-major model-view rotations (ground truth, estimate), translations: two xyz (see lmb200_render_pose).
+int lmb200_hodan_error_poses(const lmb200_mesh* mesh, const lmb200_camera* cam, const double* rotations, const double* translations,
+                             const uint16_t* input_depth, int visibility_threshold, int error_threshold, float* error) {
+  if (!mesh || !cam || !rotations || !translations || !input_depth || !error) return LMB200_E_INVALID;
+  std::vector<uint16_t> depth((size_t)2 * cam->width * cam->height);
+  int rc = lmb200_render_pose(mesh, cam, rotations, translations, 2, depth.data(), nullptr, 2);
+  if (rc) return rc;
+  return lmb200_hodan_error(input_depth, depth.data(), depth.data() + (size_t)cam->width * cam->height, cam->height, cam->width,
+                            visibility_threshold, error_threshold, error, nullptr, nullptr);
+}
+
 }  // extern "C"

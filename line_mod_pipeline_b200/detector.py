@@ -301,6 +301,19 @@ class Detector:
             self._out_cache = buf
         return buf
 
+    def prepareSingle(self, sources, cap=8192):
+        """Marshals ONE frame once so matchPreparedSingle() costs exactly one lmb200_match C-ABI call (what the reference's
+        detector->match(...) costs a C++ caller)."""
+        imgs = [_image(s) for s in sources]
+        arr = (K.Image * len(imgs))(*[i[0] for i in imgs])
+        return dict(arr=arr, keep=imgs, n=len(imgs), cap=cap, out=np.empty(cap, MATCH_DTYPE), count=C.c_size_t(0))
+
+    def matchPreparedSingle(self, prep, threshold, class_ids=()):
+        ids, nids = _cstr_array(class_ids)
+        self._check(self._L.lmb200_match(self._h, prep["arr"], prep["n"], C.c_float(threshold), ids, nids,
+                                         prep["out"].ctypes.data_as(C.POINTER(K.MatchRec)), prep["cap"], C.byref(prep["count"]), None, None))
+        return int(prep["count"].value)
+
     def prepareBatch(self, frames, cap=None):
         """Marshals a frame list once (ctypes image array + result buffers) so repeated matchPrepared() calls
         cost exactly one lmb200_match_batch C-ABI call — what a C/C++ caller pays."""
@@ -410,6 +423,16 @@ class Detector:
                  bytes_coarse=p.bytes_coarse, bytes_local=p.bytes_local, frames=p.frames, candidates=p.candidates,
                  matches=p.matches, chunks_coarse=p.chunks_coarse)
         return d
+
+    def postmatchColor(self, matches, lower_hsv, upper_hsv, slot=0):
+        """GPU colour check of the reference (HighLevelLinemod.cpp:159-161, :113-135, :424-434) for `matches` (a match record
+        array of this detector) on the frame resident in `slot` -> (inside, total) int32 arrays; -1 = hull leaves the image."""
+        m = np.ascontiguousarray(matches, MATCH_DTYPE)
+        lo = np.ascontiguousarray(lower_hsv, np.uint8); hi = np.ascontiguousarray(upper_hsv, np.uint8)
+        inside = np.zeros(len(m), np.int32); total = np.zeros(len(m), np.int32)
+        self._check(self._L.lmb200_postmatch_color(self._h, slot, lo.ctypes.data, hi.ctypes.data, m.ctypes.data_as(C.POINTER(K.MatchRec)), len(m),
+                                                   inside.ctypes.data_as(C.POINTER(C.c_int)), total.ctypes.data_as(C.POINTER(C.c_int))))
+        return inside, total
 
     def setOption(self, name, value):
         self._check(self._L.lmb200_set_option(self._h, name.encode(), int(value)))
@@ -526,3 +549,14 @@ def shard_plan(costs, world):
     if rc:
         raise LinemodError(rc, "shard_plan failed")
     return list(begin)
+
+
+def group_matches(matches, radius_threshold, discard_group_ratio):
+    """groupSimilarMatches + discardSmallMatchGroups (reference: HighLevelLinemod.cpp:206-253) -> (group index per match or -1, n_groups)."""
+    m = np.ascontiguousarray(matches, MATCH_DTYPE)
+    out = np.zeros(len(m), np.int32); ng = C.c_int(0)
+    rc = K.lib().lmb200_group_matches(m.ctypes.data_as(C.POINTER(K.MatchRec)), len(m), C.c_float(radius_threshold), C.c_float(discard_group_ratio),
+                                      out.ctypes.data_as(C.POINTER(C.c_int)), C.byref(ng))
+    if rc:
+        raise LinemodError(rc, "lmb200_group_matches")
+    return out, ng.value

@@ -84,3 +84,33 @@ def render_pose(vertices, triangles, rotations, translations, camera=None, depth
     if rc:
         raise RenderError(rc, "lmb200_render_pose")
     return d, c
+
+
+def hodan_error(input_depth, gt_render, est_render, visibility_threshold=15, error_threshold=20):
+    """Benchmark::calculateErrorHodan (src/Benchmark.cpp:18-38, :133-154) on three u16 depth images (mm).
+    -> (error, n_ok, n_comb); the reference counts a pose as correct when error < 0.3."""
+    a = [np.ascontiguousarray(x, np.uint16) for x in (input_depth, gt_render, est_render)]
+    if not (a[0].shape == a[1].shape == a[2].shape and a[0].ndim == 2):
+        raise ValueError("three u16 images of one size expected")
+    err = C.c_float(); ok = C.c_longlong(); comb = C.c_longlong()
+    P = C.POINTER(C.c_uint16)
+    rc = K.lib().lmb200_hodan_error(a[0].ctypes.data_as(P), a[1].ctypes.data_as(P), a[2].ctypes.data_as(P), a[0].shape[0], a[0].shape[1],
+                                    visibility_threshold, error_threshold, C.byref(err), C.byref(ok), C.byref(comb))
+    if rc:
+        raise RenderError(rc, "lmb200_hodan_error")
+    return err.value, ok.value, comb.value
+
+
+def hodan_error_poses(vertices, triangles, R_gt, t_gt, R_est, t_est, input_depth, camera=None, visibility_threshold=15, error_threshold=20):
+    """The whole call of PoseDetection.cpp:99: both renders (headless rasteriser) + the error."""
+    cam = camera or Camera()
+    m, keep = _mesh(vertices, triangles)
+    R = np.ascontiguousarray(np.stack([np.asarray(R_gt, np.float64).reshape(9), np.asarray(R_est, np.float64).reshape(9)]))
+    t = np.ascontiguousarray(np.stack([np.asarray(t_gt, np.float64).reshape(3), np.asarray(t_est, np.float64).reshape(3)]))
+    d = np.ascontiguousarray(input_depth, np.uint16)
+    err = C.c_float()
+    rc = K.lib().lmb200_hodan_error_poses(C.byref(m), C.byref(cam.c), R.ctypes.data_as(C.POINTER(C.c_double)), t.ctypes.data_as(C.POINTER(C.c_double)),
+                                          d.ctypes.data_as(C.POINTER(C.c_uint16)), visibility_threshold, error_threshold, C.byref(err))
+    if rc:
+        raise RenderError(rc, "lmb200_hodan_error_poses")
+    return err.value

@@ -154,6 +154,31 @@ def test_cpp_surface_header_compiles_and_runs(tmp_path):
     assert r.returncode == 0 and "CPP_SURFACE_OK" in r.stdout, r.stdout + r.stderr
 
 
+def _build_dropin(tmp_path):
+    exe = str(tmp_path / "cpp_dropin_check")
+    so_dir = os.path.dirname(K.SO_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "tests", "cv_stub"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp_dropin_check.cpp"), "-o", exe, "-L", so_dir, "-llmb200", "-Wl,-rpath," + so_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_dropin_header_compiles_reference_call_sites_verbatim(tmp_path):
+    """include/lmb200_opencv.hpp declares namespace cv::linemod: the reference's call expressions (HighLevelLinemod.cpp:26-43,
+    :50-65, :92-101, :115-126, :142-156, :258-270, :292-300), copied verbatim into tests/cpp_dropin_check.cpp, compile and run
+    through the C ABI (FileStorage / FileNode persistence round trip included).  The YAML it writes is read by real cv2."""
+    exe = _build_dropin(tmp_path)
+    env = dict(os.environ, LMB200_QUIET="1")
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "DROPIN_OK" in r.stdout, r.stdout + r.stderr
+    cv2 = pytest.importorskip("cv2")
+    fs = cv2.FileStorage(str(tmp_path / "linemod_templates.yml.gz"), cv2.FILE_STORAGE_READ)
+    assert fs.isOpened() and int(fs.getNode("pyramid_levels").real()) == 2 and fs.getNode("classes").size() == 2
+    tp = fs.getNode("classes").at(0).getNode("template_pyramids").at(1).getNode("templates").at(0)
+    assert int(tp.getNode("width").real()) == 120 and tp.getNode("features").size() == 63
+
+
 def test_header_is_plain_c(tmp_path):
     """include/lmb200.h is the drop-in boundary: it must compile as C99 (cgo / JNI / FFI generators read it) and link."""
     src = tmp_path / "cabi.c"
@@ -186,3 +211,33 @@ def test_c_example_builds_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 0 and "matches" in r.stdout
     else:
         assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_group_matches_equals_the_reference_loop():
+    """lmb200_group_matches = groupSimilarMatches + discardSmallMatchGroups (src/HighLevelLinemod.cpp:206-253)."""
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n = int(rng.integers(1, 300))
+        centres = rng.integers(0, 600, (int(rng.integers(1, 6)), 2))
+        m = np.zeros(n, lm.MATCH_DTYPE)
+        c = centres[rng.integers(0, len(centres), n)] + rng.integers(-30, 31, (n, 2))
+        m["x"], m["y"] = c[:, 0], c[:, 1]
+        radius, ratio = float(rng.choice([10.0, 35.5, 80.0])), float(rng.choice([0.0, 20.0, 50.0, 99.0]))
+        # the reference, restated literally
+        groups = []
+        for i in range(n):
+            for g in groups:
+                if np.sqrt(float(m["x"][i] - g[0][0]) ** 2 + float(m["y"][i] - g[0][1]) ** 2) < np.float32(radius):
+                    g[1].append(i)
+                    break
+            else:
+                groups.append(((int(m["x"][i]), int(m["y"][i])), [i]))
+        biggest = max(len(g[1]) for g in groups)
+        want = np.full(n, -1, np.int32)
+        kept = 0
+        for g in groups:
+            if np.float32(len(g[1]) * 100 // biggest) > np.float32(ratio):
+                want[g[1]] = kept
+                kept += 1
+        got, ng = lm.group_matches(m, radius, ratio)
+        assert ng == kept and np.array_equal(got, want), trial

@@ -613,3 +613,59 @@ def test_frame_side_uncovered_T_uses_fallback(T, rows, cols):
     bgr, depth = synth.make_frame(2, rows, cols, n_shapes=20)
     det, ora = make_pair(T=T)
     _check_frame_side(det, ora, [bgr, depth], n_maps=2 * len(T))
+
+
+def test_dropin_header_runs_reference_call_sites_on_gpu(tmp_path):
+    """The verbatim reference call sites (tests/cpp_dropin_check.cpp over include/lmb200_opencv.hpp) with a device present:
+    addTemplate on a synthetic view, match finds it again at similarity 100, getTemplates feeds the hull points."""
+    import subprocess, os
+    from test_capi_host import _build_dropin
+    exe = _build_dropin(tmp_path)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=dict(os.environ, LMB200_QUIET="1"))
+    assert r.returncode == 0 and "DROPIN_OK" in r.stdout, r.stdout + r.stderr
+    assert r.stdout.count("GPU: wiring") == 2 and "no GPU" not in r.stdout, r.stdout
+
+
+def test_postmatch_color_check_equals_oracle_and_cv2(fixture_frame):
+    """lmb200_postmatch_color (HSV inRange bit mask + per-match hull / fillPoly mask counts on the GPU) against
+    oracle/postmatch.py (pinned to cv2 by tests/test_oracle_postmatch.py) and against cv2 itself, on synthetic matches and
+    on the reference's own frame with the lagergehaeuse templates."""
+    import os
+    from oracle import postmatch as PM
+    cv2 = pytest.importorskip("cv2")
+    cases = []
+    bgr, depth = synth.make_frame(4)
+    det, ora = make_pair()
+    add_planted_from_oracle(det, ora, [bgr, depth], synth.object_masks(4)[:10], class_id="obj")
+    add_random(det, ora, 30)
+    cases.append((det, bgr, depth, 70.0, (0, 0, 90), (180, 255, 255)))
+    fb, fd = fixture_frame
+    det1 = lm.Detector.read(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagergehaeuse_templates.yml.gz"))
+    cases.append((det1, fb, fd, 88.0, (0, 30, 40), (40, 255, 255)))       # HSV range of the reference's model file shape
+    for d, b, dp, thr, lower, upper in cases:
+        res = d.match([b, dp], thr)
+        assert len(res) >= 5
+        res = res[:200]
+        inside, total = d.postmatchColor(res, lower, upper)
+        hue_ref = cv2.inRange(cv2.cvtColor(b, cv2.COLOR_BGR2HSV), lower, upper)
+        ids = d.classIds()
+        checked = 0
+        for i in range(len(res)):
+            tp = d.getTemplates(ids[int(res.class_index[i])], int(res.template_id[i]))
+            M = len(d.getModalities())
+            x, y = int(res.x[i]), int(res.y[i])
+            pts = np.array([(fx + x, fy + y) for m in range(M) for fx, fy, _ in tp[m]["features"]], np.int64)
+            if pts[:, 0].min() < 0 or pts[:, 1].min() < 0 or pts[:, 0].max() >= b.shape[1] or pts[:, 1].max() >= b.shape[0]:
+                assert inside[i] == -1 and total[i] == -1
+                continue
+            mask = PM.template_mask(tp, M, x, y, b.shape[0], b.shape[1])
+            assert total[i] == int(np.count_nonzero(mask)), "match %d: mask area %d vs oracle %d" % (i, total[i], np.count_nonzero(mask))
+            assert inside[i] == int(np.count_nonzero(hue_ref & mask)), "match %d" % i
+            if i < 20:   # and the reference's own formulation with real cv2
+                ref_mask = np.zeros(b.shape[:2], np.uint8)
+                cv2.fillPoly(ref_mask, [cv2.convexHull(pts.astype(np.int32))[:, 0, :]], 255)
+                assert total[i] == cv2.countNonZero(ref_mask) and inside[i] == cv2.countNonZero(cv2.bitwise_and(hue_ref, ref_mask))
+            checked += 1
+        assert checked >= 5
+    with pytest.raises(lm.LinemodError):
+        lm.getDefaultLINEMOD().postmatchColor(res[:1], (0, 0, 0), (1, 1, 1))   # no frame resident

@@ -124,3 +124,56 @@ def test_argument_errors(tmp_path):
     # a model entirely behind the near plane renders nothing
     d, _ = R.render_lookat(v, t, [(0.0, 0.0, 90.0)], camera=R.Camera(near_mm=100.0), colour=False)
     assert d.max() == 0 or d[d > 0].min() >= 100
+
+
+def _hodan_cv2(inp, gt, est, vis_thr=15, err_thr=20):
+    """Benchmark::calculateErrorHodan + calculateVisibilityMasks written with the SAME cv2 calls as the reference
+    (src/Benchmark.cpp:27-32, :133-154), on CV_16U images."""
+    cv2 = pytest.importorskip("cv2")
+    gtv = cv2.subtract(gt, inp)
+    _, gtv = cv2.threshold(gtv, vis_thr, 65536, cv2.THRESH_BINARY)
+    _, bgt = cv2.threshold(gt, 1, 65536, cv2.THRESH_BINARY)
+    gtv = cv2.subtract(bgt, gtv)
+    ev = cv2.subtract(est, inp)
+    _, ev = cv2.threshold(ev, vis_thr, 65536, cv2.THRESH_BINARY)
+    _, best = cv2.threshold(est, 1, 65536, cv2.THRESH_BINARY)
+    ev = cv2.subtract(best, ev)
+    best = cv2.bitwise_and(gtv, est)
+    ev = cv2.bitwise_or(ev, best)
+    inter = cv2.bitwise_and(gtv, ev)
+    comb = cv2.bitwise_or(gtv, ev)
+    ad = cv2.absdiff(gt, est)
+    _, ad = cv2.threshold(ad, err_thr, 65536, cv2.THRESH_BINARY_INV)
+    applied = cv2.bitwise_and(inter, ad)
+    return np.float32(1) - np.float32(cv2.countNonZero(applied)) / np.float32(cv2.countNonZero(comb)), cv2.countNonZero(applied), cv2.countNonZero(comb)
+
+
+def test_hodan_error_equals_the_references_cv2_calls():
+    """the benchmark's error render path (Benchmark.cpp:18-38) on the headless rasteriser."""
+    rng = np.random.default_rng(3)
+    verts, faces = torus_mesh()
+    tris = [[q[0], q[k], q[k + 1]] for q in faces for k in range(1, len(q) - 1)]
+    cam = R.Camera()
+    c, s = np.cos(0.3), np.sin(0.3)
+    Rg = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    c2, s2 = np.cos(0.36), np.sin(0.36)
+    Re = np.array([[c2, 0, s2], [0, 1, 0], [-s2, 0, c2]])
+    tg, te = np.array([10.0, -5.0, -700.0]), np.array([14.0, -3.0, -708.0])
+    d, _ = R.render_pose(verts, tris, [Rg, Re], [tg, te], cam, colour=False)
+    gt, est = d[0], d[1]
+    assert gt.max() > 0 and est.max() > 0
+    # input depth: the ground-truth render + sensor noise, an occluder in front of part of it, holes
+    inp = gt.copy().astype(np.int32)
+    inp[gt > 0] += rng.integers(-6, 7, int((gt > 0).sum()))
+    inp[gt == 0] = 1200
+    inp[200:260, 300:360] = 450
+    inp[rng.random(inp.shape) < 0.03] = 0
+    inp = np.clip(inp, 0, 65535).astype(np.uint16)
+    for vt, et in ((15, 20), (5, 3), (40, 60)):
+        want = _hodan_cv2(inp, gt, est, vt, et)
+        got = R.hodan_error(inp, gt, est, vt, et)
+        assert (got[1], got[2]) == (want[1], want[2]) and got[0] == want[0], (got, want)
+    err_same = R.hodan_error(inp, gt, gt)[0]
+    assert err_same < R.hodan_error(inp, gt, est)[0] < 1.0
+    e2 = R.hodan_error_poses(verts, tris, Rg, tg, Re, te, inp, cam)
+    assert e2 == R.hodan_error(inp, gt, est)[0]
