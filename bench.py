@@ -381,6 +381,15 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
 
         dt = timed(False)
         last = state["last"]
+        # where the step goes on the device (CUDA events of rank 0, a few extra steps outside the timed region)
+        det.setProfiling(True); det.getProfile(reset=True)
+        for _ in range(4):
+            step(False)
+        drain()
+        pr = det.getProfile(reset=True)
+        det.setProfiling(False)
+        out["device_ms_per_step"] = {k: round(v / 4, 4) for k, v in pr["ms"].items() if v > 0}
+        out["device_ms_per_step"]["sum"] = round(sum(pr["ms"].values()) / 4, 4)
         det.setOption("upload_async", 1)
         dte = timed(True)
         det.setOption("upload_async", 0)

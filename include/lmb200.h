@@ -293,6 +293,7 @@ int lmb200_shard_plan(const double* costs, int n, int world, int* begin);
 enum {
   LMB200_K_UPLOAD = 0, LMB200_K_PYRDOWN, LMB200_K_CG_QUANTIZE, LMB200_K_DN_QUANTIZE, LMB200_K_MEDIAN,
   LMB200_K_DECIMATE, LMB200_K_LINEARIZE, LMB200_K_SIM_COARSE, LMB200_K_SIM_LOCAL, LMB200_K_PACK,
+  LMB200_K_COMM,           /* NCCL collectives issued on the compute lane (all-gather of the quantized maps) */
   LMB200_K_COUNT
 };
 typedef struct {

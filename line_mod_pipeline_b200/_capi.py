@@ -12,7 +12,7 @@ SIMLUT_CIRCULAR, SIMLUT_LINEAR = 0, 1
 MB_L2_READ, MB_L1_READ, MB_HBM_READ, MB_H2D = range(4)
 OK, E_INVALID, E_SOURCES, E_SIZE, E_FEATURES, E_CLASS, E_IO, E_CUDA, E_TRUNCATED, E_COMM, E_NODEVICE = range(0, -11, -1)
 K_NAMES = ["upload", "pyrdown", "cg_quantize", "dn_quantize", "median", "decimate", "linearize",
-           "sim_coarse", "sim_local", "pack"]
+           "sim_coarse", "sim_local", "pack", "comm"]
 DBG_QUANTIZED, DBG_LINMEM, DBG_COARSE, DBG_UNSORTED, DBG_MAGNITUDE, DBG_DN_INDICES, DBG_SIMILARITY = range(7)
 
 
@@ -47,7 +47,7 @@ class MatchRec(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 10), ("launches", C.c_longlong * 10), ("bytes_coarse", C.c_longlong),
+    _fields_ = [("ms", C.c_double * 11), ("launches", C.c_longlong * 11), ("bytes_coarse", C.c_longlong),
                 ("bytes_local", C.c_longlong), ("frames", C.c_longlong), ("candidates", C.c_longlong),
                 ("matches", C.c_longlong), ("chunks_coarse", C.c_longlong)]
 

@@ -124,6 +124,7 @@ void lmb200_destroy(lmb200_handle h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_gather) cudaFreeHost(h->h_gather);
     if (h->h_fin) cudaFreeHost(h->h_fin);
+    for (auto& g : h->gsets) { g.send.release(); g.recv.release(); if (g.host) cudaFreeHost(g.host); if (g.ev) cudaEventDestroy(g.ev); }
     for (auto& tk : h->tickets) {
       if (tk.b_ctr) cudaFreeHost(tk.b_ctr);
       if (tk.b_out) cudaFreeHost(tk.b_out);

@@ -15,9 +15,17 @@
 #include <cstring>
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 using namespace lmk;
 
 namespace lmh {
+
+// NVTX range per stage of the path (Nsight Systems / ncu --nvtx): frame side, template side, fetch + epilogue, gather
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 void finalize_matches(std::vector<Match>& m) {
   std::sort(m.begin(), m.end());
@@ -102,11 +110,13 @@ struct ProfScope {
     a = take(); b = take();
     cudaEventRecord(a, st);
   }
-  ~ProfScope() {
+  void finish() {
     if (!a) return;
     cudaEventRecord(b, st);
     h->prof_pending.push_back(ProfRec{family, a, b});
+    a = nullptr;
   }
+  ~ProfScope() { finish(); }
 };
 
 static void collect_profile(lmb200_detector* h) {
@@ -487,6 +497,7 @@ static bool chunk_is_contiguous(lmb200_detector* h, const lmb200_image* frames, 
 // block, all-gathers the quantized maps over NCCL and then spreads every frame (lmb200_match_resident_sharded).
 enum { FS_ALL = 0, FS_QUANTIZE = 1, FS_SPREAD = 2 };
 static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st, int phase = FS_ALL) {
+  NvtxRange nvtx(phase == FS_QUANTIZE ? "lmb200:quantize" : phase == FS_SPREAD ? "lmb200:spread_linearize" : "lmb200:frame_side");
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
   if (phase != FS_QUANTIZE)
     CU(cudaMemsetAsync(h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD, 0, (size_t)count * MAX_MOD * sizeof(u32), st));
@@ -632,6 +643,7 @@ static LevelParams make_level_params(lmb200_detector* h, int l, int first, bool 
 // ordered compaction.  (Detector::matchClass.)  stop_after_coarse: debug path.
 static int run_matching(lmb200_detector* h, int first, int count, float threshold, cudaStream_t st,
                         bool stop_after_coarse = false) {
+  NvtxRange nvtx("lmb200:matchClass(similarity, similarityLocal, pack)");
   const int L = h->cfg.pyramid_levels;
   MatchParams mp = make_match_params(h, first, count, threshold);
   CU(cudaMemsetAsync(mp.ctr, 0, sizeof(SlotCtr) * count, st));
@@ -676,6 +688,7 @@ static int enqueue_result_copies(lmb200_detector* h, int first, int count, cudaS
 }
 
 static int fetch_raw(lmb200_detector* h, int first, int count, cudaStream_t st, std::vector<std::vector<Cand>>& out, bool copies_enqueued = false) {
+  NvtxRange nvtx("lmb200:fetch(D2H match lists)");
   if (!copies_enqueued) {
     int rc = enqueue_result_copies(h, first, count, st);
     if (rc) return rc;
@@ -771,6 +784,7 @@ static void drain_tickets(lmb200_detector* h) {
 
 // Host epilogue of n independent frames (record -> Match, std::sort, std::unique) on a few threads.
 static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Cand>>& raws, std::vector<std::vector<Match>>& outs) {
+  NvtxRange nvtx("lmb200:epilogue(std::sort, std::unique)");
   const int n = (int)raws.size();
   outs.resize(n);
   auto work = [&](int lo, int hi) {
@@ -895,6 +909,7 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
   if (rc) return rc;
   rc = run_frame_side(h, own, n, st, FS_QUANTIZE);
   if (rc) return rc;
+  ProfScope ps_comm(h, LMB200_K_COMM, st);
   rc = comm_group_begin(h);
   if (rc) return rc;
   for (int l = 0; l < L; ++l)
@@ -909,6 +924,7 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
     }
   rc = comm_group_end(h);
   if (rc) return rc;
+  ps_comm.finish();
   rc = run_frame_side(h, first_slot, count, st, FS_SPREAD);
   if (rc) return rc;
   rc = run_matching(h, first_slot, count, threshold, st);
@@ -917,6 +933,34 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
   if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
   mk.first = first_slot; mk.count = count;
   CU(cudaEventRecord(mk.ev, st));
+  // The match gather rides on the compute lane right behind the kernels — pack, ncclAllGather and the copy to pinned host
+  // memory need no host decision — so lmb200_fetch_resident_allgather finds every rank's lists waiting for it instead of
+  // running a latency-bound collective of its own.  (Overflowing stores / lists longer than the buffer are detected at
+  // fetch time from the gathered headers and take the synchronous path there.)
+  {
+    GatherSet* gs = nullptr;
+    for (auto& g : h->gsets) if (g.first == first_slot && g.count == count) gs = &g;
+    if (!gs) gs = &h->gsets[h->gset_next++ & 3];
+    if (h->gather_cap <= 0) h->gather_cap = 256;   // average records per frame the buffer holds; doubles when a step needs more
+    const int rec_cap = h->gather_cap * count;
+    const size_t bytes = ((size_t)2 * count + rec_cap) * sizeof(Cand);
+    gs->valid = false; gs->first = first_slot; gs->count = count;
+    ALLOC(gs->send, bytes);
+    ALLOC(gs->recv, bytes * world);
+    if (gs->host_bytes < bytes * world) {
+      if (gs->host) { cudaFreeHost(gs->host); gs->host = nullptr; }
+      CU(cudaHostAlloc((void**)&gs->host, bytes * world, cudaHostAllocDefault));
+      gs->host_bytes = bytes * world;
+    }
+    if (!gs->ev) CU(cudaEventCreateWithFlags(&gs->ev, cudaEventDisableTiming));
+    launch_gather_pack(h->d_ctr.as<SlotCtr>() + first_slot, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap, h->out_cap,
+                       gs->send.as<Cand>(), rec_cap, count, st);
+    rc = comm_allgather(h, gs->send.p, gs->recv.p, bytes, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(gs->host, gs->recv.p, bytes * world, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(gs->ev, st));
+    gs->cap = rec_cap; gs->generation = h->buffer_generation; gs->valid = true;
+  }
   return LMB200_OK;
 }
 
@@ -1111,6 +1155,7 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
 // group, so consecutive batches pipeline into each other.
 //   C:  [wait group_done(g)] H2D(k) rec h2d(k)          X:  [wait h2d(k)] kernels(k) D2H(k) rec group_done(g), done(k)
 static int batch_enqueue(lmb200_detector* h, BatchTicket& tk) {
+  NvtxRange nvtx("lmb200:batch_enqueue(H2D chunks + kernels)");
   const int n_frames = tk.n_frames, n_sources = tk.n_sources;
   const lmb200_image* frames = tk.frames.data();
   cudaStream_t Xs[4] = {h->lanes[0].stream, h->lanes[2].stream, h->lanes[3].stream, h->lanes[4].stream}, Cs = h->lanes[1].stream;
@@ -1826,11 +1871,24 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     int rc = revalidate_slots(h, first_slot, count);
     if (rc) return rc;
   }
-  constexpr int HDR = 2;
-  if (h->gather_cap <= 0) h->gather_cap = 254;  // 4 KB per frame and rank; doubles when a list is longer
-  for (;;) {
-    const size_t pitch = (size_t)(HDR + h->gather_cap) * sizeof(Cand);
-    const size_t bytes = pitch * count;
+  if (h->gather_cap <= 0) h->gather_cap = 256;    // average records per frame the buffer holds; doubles when a step needs more
+  const Cand* G = nullptr;   // gathered buffers of all ranks in host memory, per rank: [2*count headers][gcap records]
+  int gcap = 0;
+  auto rank_base = [&](int r) { return G + (size_t)r * ((size_t)2 * count + gcap); };
+  for (auto& g : h->gsets) {  // the sharded step already gathered on the compute lane: wait for its copy only
+    if (!(g.valid && g.first == first_slot && g.count == count && g.generation == h->buffer_generation)) continue;
+    g.valid = false;
+    CU(cudaEventSynchronize(g.ev));
+    bool redo = false;
+    for (int r = 0; r < world && !redo; ++r)
+      for (int i = 0; i < count; ++i)
+        if (g.host[(size_t)r * ((size_t)2 * count + g.cap) + 2 * i].x) { redo = true; break; }
+    if (!redo) { G = g.host; gcap = g.cap; }
+    break;
+  }
+  while (!G) {
+    const int rec_cap = h->gather_cap * count;
+    const size_t bytes = ((size_t)2 * count + rec_cap) * sizeof(Cand);
     ALLOC(h->d_gather_send, bytes);
     ALLOC(h->d_gather_recv, bytes * world);
     if (h->h_gather_bytes < bytes * world) {
@@ -1839,18 +1897,17 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       h->h_gather_bytes = bytes * world;
     }
     launch_gather_pack(h->d_ctr.as<SlotCtr>() + first_slot, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap, h->out_cap,
-                       h->d_gather_send.as<Cand>(), h->gather_cap, count, st);
+                       h->d_gather_send.as<Cand>(), rec_cap, count, st);
     int rc = comm_allgather(h, h->d_gather_send.p, h->d_gather_recv.p, bytes, st, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_gather, h->d_gather_recv.p, bytes * world, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    int maxc = 0;
-    bool any_over = false, my_over = false;
+    bool store_over = false, my_over = false, small = false;
     for (int r = 0; r < world; ++r)
       for (int i = 0; i < count; ++i) {
-        const Cand& hd = h->h_gather[((size_t)r * count + i) * (HDR + h->gather_cap)];
-        maxc = std::max(maxc, hd.tsel);
-        if (hd.x) { any_over = true; if (r == h->comm_rank) my_over = true; }
+        const int fl = h->h_gather[(size_t)r * ((size_t)2 * count + rec_cap) + 2 * i].x;
+        if (fl & 1) { store_over = true; if (r == h->comm_rank) my_over = true; }
+        if (fl & 2) small = true;
       }
     if (my_over) {
       float thr = h->slot_threshold[first_slot];
@@ -1860,12 +1917,12 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       if (rc) return rc;
       CU(cudaStreamSynchronize(h->lanes[0].stream));
     }
-    if (any_over) continue;
-    if (maxc <= h->gather_cap) break;
-    while (h->gather_cap < maxc) h->gather_cap *= 2;
+    if (store_over) continue;
+    if (small) { h->gather_cap *= 2; continue; }   // every rank sees the flag: all double together
+    G = h->h_gather; gcap = rec_cap;
   }
   for (int i = 0; i < count; ++i) {
-    const Cand& st1 = h->h_gather[((size_t)h->comm_rank * count + i) * (HDR + h->gather_cap) + 1];
+    const Cand& st1 = rank_base(h->comm_rank)[2 * i + 1];
     h->prof.bytes_local += (long long)(((unsigned long long)(u32)st1.x << 32) | (u32)st1.tsel);
     h->prof.chunks_coarse += (long long)(((unsigned long long)(u32)__builtin_bit_cast(int, st1.sim) << 32) | (u32)st1.y);
   }
@@ -1888,8 +1945,9 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       for (int i = a; i < b; ++i) {
         std::vector<Cand>& all = alls[i - lo];
         for (int r = 0; r < world; ++r) {
-          const Cand* rec = h->h_gather + ((size_t)r * count + i) * (HDR + h->gather_cap);
-          all.insert(all.end(), rec + HDR, rec + HDR + rec[0].tsel);
+          const Cand* rb = rank_base(r);
+          const Cand* rec = rb + 2 * (size_t)count + rb[2 * i].y;
+          all.insert(all.end(), rec, rec + rb[2 * i].tsel);
         }
         if (h->shard_interleaved)
           std::stable_sort(all.begin(), all.end(), [h](const Cand& a, const Cand& b) { return h->pos_of_g[a.tsel] < h->pos_of_g[b.tsel]; });
@@ -1918,14 +1976,16 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
     }
     if (offsets) offsets[count] = base;
   } else {
-    // capacity every rank derives identically from the gathered counts (unique can only shrink a list)
-    int fin_cap = 0;
-    for (int i = 0; i < count; ++i) {
-      int tot = 0;
-      for (int r = 0; r < world; ++r) tot += h->h_gather[((size_t)r * count + i) * (HDR + h->gather_cap)].tsel;
-      fin_cap = std::max(fin_cap, tot);
+    // Compact per-rank buffer [per header records {count}][records of the block's frames back to back]; its capacity is
+    // derived identically on every rank from the gathered counts (unique can only shrink a list): the largest block total.
+    size_t cap2 = 0;
+    for (int r = 0; r < world; ++r) {
+      size_t tot = 0;
+      for (int i = std::min(count, r * per); i < std::min(count, (r + 1) * per); ++i)
+        for (int q = 0; q < world; ++q) tot += (size_t)rank_base(q)[2 * i].tsel;
+      cap2 = std::max(cap2, tot);
     }
-    const size_t pitch2 = (size_t)(1 + fin_cap), bytes2 = (size_t)per * pitch2 * sizeof(lmb200_match_rec);
+    const size_t pitch2 = (size_t)per + cap2, bytes2 = pitch2 * sizeof(lmb200_match_rec);
     ALLOC(h->d_fin_send, bytes2);
     ALLOC(h->d_fin_recv, bytes2 * world);
     if (h->h_fin_bytes < bytes2 * world) {
@@ -1933,32 +1993,38 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       CU(cudaHostAlloc((void**)&h->h_fin, bytes2 * world, cudaHostAllocDefault));
       h->h_fin_bytes = bytes2 * world;
     }
-    lmb200_match_rec* mine = h->h_fin + (size_t)h->comm_rank * per * pitch2;  // staged in place in the pinned receive mirror
-    for (int j = 0; j < per; ++j) {
-      lmb200_match_rec* rec = mine + (size_t)j * pitch2;
-      const int i = lo + j;
-      const int n = i < hi ? (int)ms[j].size() : 0;
-      rec[0].x = n; rec[0].y = 0; rec[0].similarity = 0.f; rec[0].class_index = 0; rec[0].template_id = 0;
-      for (int k = 0; k < n; ++k) {
-        const Match& mt = ms[j][k];
-        rec[1 + k].x = mt.x; rec[1 + k].y = mt.y; rec[1 + k].similarity = mt.similarity;
-        rec[1 + k].class_index = mt.class_index; rec[1 + k].template_id = mt.template_id;
+    lmb200_match_rec* mine = h->h_fin + (size_t)h->comm_rank * pitch2;  // staged in place in the pinned receive mirror
+    {
+      lmb200_match_rec* rec = mine + per;
+      for (int j = 0; j < per; ++j) {
+        const int i = lo + j;
+        const int n = i < hi ? (int)ms[j].size() : 0;
+        mine[j].x = n; mine[j].y = 0; mine[j].similarity = 0.f; mine[j].class_index = 0; mine[j].template_id = 0;
+        for (int k = 0; k < n; ++k, ++rec) {
+          const Match& mt = ms[j][k];
+          rec->x = mt.x; rec->y = mt.y; rec->similarity = mt.similarity; rec->class_index = mt.class_index; rec->template_id = mt.template_id;
+        }
+        if (i < hi) { h->prof.candidates += (long long)alls[j].size(); h->prof.matches += (long long)n; }
       }
-      if (i < hi) { h->prof.candidates += (long long)alls[j].size(); h->prof.matches += (long long)n; }
     }
     CU(cudaMemcpyAsync(h->d_fin_send.p, mine, bytes2, cudaMemcpyHostToDevice, st));
     int rc = comm_allgather(h, h->d_fin_send.p, h->d_fin_recv.p, bytes2, st, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_fin, h->d_fin_recv.p, bytes2 * world, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < count; ++i) {
-      const lmb200_match_rec* rec = h->h_fin + ((size_t)(i / per) * per + (size_t)(i % per)) * pitch2;
-      const size_t n = (size_t)rec[0].x;
-      if (offsets) offsets[i] = base;
-      const size_t room = cap > base ? cap - base : 0, w = std::min(n, room);
-      if (w) std::memcpy(out + base, rec + 1, w * sizeof(lmb200_match_rec));
-      if (w < n) status = LMB200_E_TRUNCATED;
-      base += n;
+    for (int r = 0; r < world; ++r) {
+      const lmb200_match_rec* hdr = h->h_fin + (size_t)r * pitch2;
+      const lmb200_match_rec* rec = hdr + per;
+      for (int j = 0; j < per; ++j) {
+        const int i = r * per + j;
+        if (i >= count) break;
+        const size_t n = (size_t)hdr[j].x;
+        if (offsets) offsets[i] = base;
+        const size_t room = cap > base ? cap - base : 0, w = std::min(n, room);
+        if (w) std::memcpy(out + base, rec, w * sizeof(lmb200_match_rec));
+        if (w < n) status = LMB200_E_TRUNCATED;
+        base += n; rec += n;
+      }
     }
     if (offsets) offsets[count] = base;
   }

@@ -72,6 +72,16 @@ struct Lane {
 };
 
 struct ProfRec { int family; cudaEvent_t a, b; };
+// Match gather of one sharded step, enqueued on the compute lane right behind the step's kernels
+// (lmb200_match_resident_sharded): the fetch only waits for `ev` and finds every rank's lists in pinned memory.
+struct GatherSet {
+  int first = -1, count = 0, cap = 0;
+  long long generation = -1;
+  bool valid = false;
+  DevBuf send, recv;
+  lmk::Cand* host = nullptr; size_t host_bytes = 0;
+  cudaEvent_t ev = nullptr;
+};
 struct ResidentMark { cudaEvent_t ev = nullptr; int first = 0, count = 0; };  // completion of one lmb200_match_resident call
 
 // One submitted lmb200_match_batch: chunk schedule, completion events and per-frame pinned result staging.
@@ -174,6 +184,7 @@ struct lmb200_detector {
   void* nccl_comm_fetch = nullptr;          // second communicator (ncclCommSplit) for the result-fetch collectives
   lmh::DevBuf d_gather_send, d_gather_recv; int gather_cap = 0;
   lmk::Cand* h_gather = nullptr; size_t h_gather_bytes = 0;
+  lmh::GatherSet gsets[4]; unsigned gset_next = 0;
   lmh::DevBuf d_fin_send, d_fin_recv;          // finished (sorted + unique) per-frame lists, second all-gather
   lmb200_match_rec* h_fin = nullptr; size_t h_fin_bytes = 0;
 

@@ -177,8 +177,8 @@ void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaS
 void launch_similarity_map(const MatchParams& mp, const LevelParams& lp, bool wide, u16* map, cudaStream_t st);
 // Ordered compaction: out[frame][0..n) in generation order, count[frame] = n (may exceed cap -> overflow).
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st);
-// multi-GPU: per-frame send buffer {2 header records, first min(out_count, gather_cap) matches} for the match all-gather
-void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int gather_cap, int frames, cudaStream_t st);
+// multi-GPU: compact send buffer of the match all-gather: [2*frames header records][rec_cap match records, frames back to back]
+void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int rec_cap, int frames, cudaStream_t st);
 
 // ------------------------------------------------------------------ post-match colour check (kernels_postmatch.cu)
 // bits: [rows][(cols+31)/32] u32, bit x%32 of word x/32 = pixel (y, x) lies in the HSV range (cvtColor BGR2HSV + inRange)

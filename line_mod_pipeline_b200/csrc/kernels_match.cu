@@ -553,6 +553,10 @@ void launch_pack_nibbles(const u8* lm, size_t lm_stride, u8* lmn, size_t lmn_str
 // Slow path: upstream's per-feature bounds checks with guarded byte loads (malformed / oversized
 // templates — N4 in SURVEY.md — where upstream itself is undefined; semantics = oracle's).
 // ---------------------------------------------------------------------------------------------
+// WPC = false: one CTA per candidate, its features split over the four warps (shortest dependent chain: single frames, few
+//              candidates).  WPC = true: one WARP per candidate, no block barriers and no shared-memory reduction — four
+//              independent candidates per CTA keep the load pipeline busier when there are thousands of them per launch.
+template <bool WPC>
 __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, LevelParams lp) {
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -572,12 +576,12 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
     s_lm[3] = lp.lm[3] + (size_t)frame * lp.lm_stride[3];
   }
   __shared__ uint4 s_part[4][32];
-  __shared__ uint2 s_ent[4][16];
+  __shared__ uint2 s_ent[4][32];
   __syncthreads();
 
-  for (int c = blockIdx.x; c < n; c += gridDim.x) {
+  for (int c = WPC ? blockIdx.x * 4 + warp : blockIdx.x; c < n; c += WPC ? gridDim.x * 4 : gridDim.x) {
     Cand rec = cands[c];
-    if (rec.sim < 0.f || rec.tsel < 0 || rec.tsel >= mp.nsel) continue;  // CTA-uniform
+    if (rec.sim < 0.f || rec.tsel < 0 || rec.tsel >= mp.nsel) continue;  // CTA-uniform (WPC: warp-uniform)
     const int g = mp.sel[rec.tsel];
     const HdrR hdr = load_hdr(lp.hdr + g);
     int x = rec.x * 2 + 1, y = rec.y * 2 + 1;
@@ -599,9 +603,10 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
         // word select and two funnel shifts realign them; a warp's load touches the 4-6 lines of the patch.
         const u32 yrow = (u32)(cyT + rr) * 16u, xh = (u32)cxT + 8u * (u32)hh;
         const uint2* offp = reinterpret_cast<const uint2*>(lp.offs) + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
-        const int q = (nf + 3) >> 2, kb = warp * q, ke = min(nf, kb + q);  // this warp's quarter of the features (<= 16)
-        const int kn = ke - kb;
-        __syncwarp();  // the previous modality's reads of s_ent are done
+        const int q = WPC ? nf : (nf + 3) >> 2, kb0 = WPC ? 0 : warp * q, ke = min(nf, kb0 + q);  // this warp's share of the features
+        for (int kb = kb0; kb < ke; kb += 32) {
+        const int kn = min(32, ke - kb);
+        __syncwarp();  // the previous reads of s_ent are done
         if (lane < kn) s_ent[warp][lane] = __ldg(offp + kb + lane);
         __syncwarp();
 #pragma unroll 4
@@ -617,7 +622,8 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
           a0 += __funnelshift_r(v0, v1, sh);
           a1 += __funnelshift_r(v1, v2, sh);
         }
-      } else if (warp == 0) {
+        }
+      } else if (WPC || warp == 0) {
         const u32* fp = lp.feat + (size_t)g * M * FEAT_SLOTS + m * FEAT_SLOTS;
         for (int k = 0; k < nf; ++k) {
           u32 f = __ldg(fp + k);
@@ -643,11 +649,15 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       t0 += a0 & 0x00FF00FFu; t1 += (a0 >> 8) & 0x00FF00FFu;
       t2 += a1 & 0x00FF00FFu; t3 += (a1 >> 8) & 0x00FF00FFu;
     }
-    s_part[warp][lane] = make_uint4(t0, t1, t2, t3);
-    __syncthreads();
-    if (warp == 0) {
-      const uint4 p1 = s_part[1][lane], p2 = s_part[2][lane], p3 = s_part[3][lane];
-      t0 += p1.x + p2.x + p3.x; t1 += p1.y + p2.y + p3.y; t2 += p1.z + p2.z + p3.z; t3 += p1.w + p2.w + p3.w;
+    if (!WPC) {
+      s_part[warp][lane] = make_uint4(t0, t1, t2, t3);
+      __syncthreads();
+    }
+    if (WPC || warp == 0) {
+      if (!WPC) {
+        const uint4 p1 = s_part[1][lane], p2 = s_part[2][lane], p3 = s_part[3][lane];
+        t0 += p1.x + p2.x + p3.x; t1 += p1.y + p2.y + p3.y; t2 += p1.z + p2.z + p3.z; t3 += p1.w + p2.w + p3.w;
+      }
     // argmax, strict '>' in raster order from best = 0
     int v[8] = {(int)(t0 & 0xFFFF), (int)(t1 & 0xFFFF), (int)(t0 >> 16), (int)(t1 >> 16),
                 (int)(t2 & 0xFFFF), (int)(t3 & 0xFFFF), (int)(t2 >> 16), (int)(t3 >> 16)};
@@ -670,7 +680,7 @@ __global__ void __launch_bounds__(128) similarity_local_kernel(MatchParams mp, L
       atomicAdd(&mp.ctr[frame].local_bytes, (unsigned long long)nfl * 256ull);
     }
     }
-    __syncthreads();  // s_part is reused by the next candidate
+    if (!WPC) __syncthreads();  // s_part is reused by the next candidate
   }
 }
 
@@ -680,7 +690,8 @@ void launch_similarity_local(const MatchParams& mp, const LevelParams& lp, cudaS
   int bx = 148 * 8;
   if (mp.frames >= 8) bx = 148 * 2;
   dim3 grid(bx, mp.frames);
-  similarity_local_kernel<<<grid, 128, 0, st>>>(mp, lp);
+  if (mp.frames >= 8) similarity_local_kernel<true><<<grid, 128, 0, st>>>(mp, lp);   // batches: a warp per candidate
+  else similarity_local_kernel<false><<<grid, 128, 0, st>>>(mp, lp);                 // latency path: a CTA per candidate
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -771,29 +782,42 @@ __global__ void __launch_bounds__(1024) pack_kernel(MatchParams mp, Cand* __rest
   }
 }
 
-// Send buffer of the template-sharded match gather, one block per frame: two header records
-//   {out_count, overflow flag, 0, 0}   {local_bytes lo, hi, coarse_chunks lo, hi}
-// followed by the first min(out_count, gather_cap) packed matches (one launch instead of a memset and two 2-D copies).
+// Send buffer of the template-sharded match gather: a COMPACT variable-length packing (one frame with thousands of
+// matches must not size every frame's slot), one block per frame:
+//   send[2f]     = {out_count, flags (1: candidate store overflowed, 2: the record area is too small), offset, 0}
+//   send[2f + 1] = {local_bytes lo, hi, coarse_chunks lo, hi}
+//   send[2*frames + offset ...] = the frame's packed matches; offset = sum of the counts of the frames before it.
 __global__ void __launch_bounds__(256) gather_pack_kernel(const SlotCtr* __restrict__ ctr, const Cand* __restrict__ out, int out_cap,
-                                                          Cand* __restrict__ send, int gather_cap) {
+                                                          Cand* __restrict__ send, int frames, int rec_cap) {
+  __shared__ int s_part[8];
   const int f = blockIdx.x;
+  int part = 0;
+  for (int i = threadIdx.x; i < f; i += 256) part += min(ctr[i].out_count, out_cap);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  int offset = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) offset += s_part[w];
   const SlotCtr c = ctr[f];
-  Cand* dst = send + (size_t)f * (2 + gather_cap);
+  const int n = min(c.out_count, out_cap);
+  const bool fits = offset + n <= rec_cap;
   if (threadIdx.x == 0) {
     Cand h0, h1;
-    h0.tsel = c.out_count; h0.x = (c.overflow != 0 || c.out_count > out_cap) ? 1 : 0; h0.y = 0; h0.sim = 0.f;
+    h0.tsel = c.out_count; h0.x = ((c.overflow != 0 || c.out_count > out_cap) ? 1 : 0) | (fits ? 0 : 2); h0.y = offset; h0.sim = 0.f;
     h1.tsel = (int)(u32)c.local_bytes; h1.x = (int)(u32)(c.local_bytes >> 32);
     h1.y = (int)(u32)c.coarse_chunks; h1.sim = __int_as_float((int)(u32)(c.coarse_chunks >> 32));
-    dst[0] = h0; dst[1] = h1;
+    send[2 * f] = h0; send[2 * f + 1] = h1;
   }
-  const int n = min(min(c.out_count, out_cap), gather_cap);
+  if (!fits) return;
   const uint4* src = reinterpret_cast<const uint4*>(out + (size_t)f * out_cap);
-  uint4* d4 = reinterpret_cast<uint4*>(dst + 2);
+  uint4* d4 = reinterpret_cast<uint4*>(send + 2 * (size_t)frames + offset);
   for (int i = threadIdx.x; i < n; i += 256) d4[i] = src[i];
 }
 
-void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int gather_cap, int frames, cudaStream_t st) {
-  if (frames > 0) gather_pack_kernel<<<frames, 256, 0, st>>>(ctr, out, out_cap, send, gather_cap);
+void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int rec_cap, int frames, cudaStream_t st) {
+  if (frames > 0) gather_pack_kernel<<<frames, 256, 0, st>>>(ctr, out, out_cap, send, frames, rec_cap);
 }
 
 void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st) {

@@ -13,21 +13,27 @@
 
 namespace {
 
-// Each thread sums uint4 loads; `stride` walks the CTA over the buffer, `span16` is the buffer size in uint4.
+// Each thread sums uint4 loads.  Four independent loads are in flight per thread and the index arithmetic is 32-bit
+// (per_cta16 is a multiple of 256 * 4), so the loop is bounded by the load path, not by address computation.
 template <int MODE>  // 0: L2 (ld.cg), 1: L1 (ld.nc)
-__global__ void __launch_bounds__(256) read_kernel(const uint4* __restrict__ buf, size_t span16, size_t per_cta16, int reps,
+__global__ void __launch_bounds__(256) read_kernel(const uint4* __restrict__ buf, unsigned span16, unsigned per_cta16, int reps,
                                                    unsigned* __restrict__ sink) {
-  unsigned acc = 0;
-  const size_t base = ((size_t)blockIdx.x * per_cta16) % span16;
+  unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const unsigned base = (unsigned)(((unsigned long long)blockIdx.x * per_cta16) % span16);
   for (int r = 0; r < reps; ++r) {
-#pragma unroll 4
-    for (size_t i = threadIdx.x; i < per_cta16; i += 256) {
-      size_t k = base + i;
-      if (k >= span16) k -= span16;
-      const uint4 v = MODE == 0 ? __ldcg(buf + k) : __ldg(buf + k);
-      acc += v.x ^ v.y ^ v.z ^ v.w;
+    for (unsigned i = threadIdx.x; i < per_cta16; i += 256 * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned idx = base + i + 256u * k;
+        if (idx >= span16) idx -= span16;
+        v[k] = MODE == 0 ? __ldcg(buf + idx) : __ldg(buf + idx);
+      }
+#pragma unroll
+      a0 += v[0].x ^ v[0].w; a1 += v[1].y ^ v[1].z; a2 += v[2].x ^ v[2].y; a3 += v[3].z ^ v[3].w;
     }
   }
+  const unsigned acc = a0 ^ a1 ^ a2 ^ a3;
   if (acc == 0x9E3779B9u) sink[0] = acc;  // never true for the zero-filled buffer: keeps the loads alive
 }
 
@@ -67,7 +73,9 @@ extern "C" int lmb200_microbench(int kind, size_t bytes, int iters, double* gbps
     // L1: the buffer is `bytes` PER CTA window (all CTAs of an SM share windows of the same small buffer set)
     const size_t total = kind == LMB200_MB_L1_READ ? bytes * (size_t)ctas : bytes;
     const size_t span16 = total / 16;
-    const size_t per_cta16 = kind == LMB200_MB_L1_READ ? bytes / 16 : span16 / ctas * (kind == LMB200_MB_L2_READ ? 16 : 1);
+    size_t per_cta16 = kind == LMB200_MB_L1_READ ? bytes / 16 : span16 / ctas * (kind == LMB200_MB_L2_READ ? 16 : 1);
+    per_cta16 = per_cta16 / 1024 * 1024;                      // whole unrolled iterations of the CTA
+    if (per_cta16 == 0 || span16 >= (1ull << 32)) { cudaEventDestroy(a); cudaEventDestroy(b); return LMB200_E_INVALID; }
     const int reps = kind == LMB200_MB_L1_READ ? 256 : 1;
     void* d = nullptr;
     unsigned* sink = nullptr;
@@ -76,8 +84,8 @@ extern "C" int lmb200_microbench(int kind, size_t bytes, int iters, double* gbps
       cudaMemset(d, 0, total);
       for (int it = 0; it < iters + 2; ++it) {  // two warm-up passes bring the buffer into L2
         cudaEventRecord(a);
-        if (kind == LMB200_MB_L1_READ) read_kernel<1><<<ctas, 256>>>((const uint4*)d, span16, per_cta16, reps, sink);
-        else read_kernel<0><<<ctas, 256>>>((const uint4*)d, span16, per_cta16, reps, sink);
+        if (kind == LMB200_MB_L1_READ) read_kernel<1><<<ctas, 256>>>((const uint4*)d, (unsigned)span16, (unsigned)per_cta16, reps, sink);
+        else read_kernel<0><<<ctas, 256>>>((const uint4*)d, (unsigned)span16, (unsigned)per_cta16, reps, sink);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         float ms = 0;

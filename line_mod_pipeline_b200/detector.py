@@ -419,7 +419,7 @@ class Detector:
     def getProfile(self, reset=False):
         p = K.Profile()
         self._check(self._L.lmb200_get_profile(self._h, C.byref(p), int(reset)))
-        d = dict(ms={K.K_NAMES[i]: p.ms[i] for i in range(10)}, launches={K.K_NAMES[i]: p.launches[i] for i in range(10)},
+        d = dict(ms={K.K_NAMES[i]: p.ms[i] for i in range(len(K.K_NAMES))}, launches={K.K_NAMES[i]: p.launches[i] for i in range(len(K.K_NAMES))},
                  bytes_coarse=p.bytes_coarse, bytes_local=p.bytes_local, frames=p.frames, candidates=p.candidates,
                  matches=p.matches, chunks_coarse=p.chunks_coarse)
         return d
