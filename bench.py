@@ -299,15 +299,16 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         det.uploadFrames(frames, g * Bt)
     k1 = max(3, K // 2)
 
+    fprep = det.prepareFetch(Bt, cap=4096 * Bt)        # result buffers marshalled once: a fetch is one C-ABI call
+
     def one_gpu_steps(n):
-        res = None
         for k in range(n):
             det.matchResident((k % G) * Bt, Bt, thr)
             if k >= G - 1:
-                res = det.fetchResident(((k - (G - 1)) % G) * Bt, Bt, cap=4096 * Bt)
+                det.fetchResidentPrepared(fprep, ((k - (G - 1)) % G) * Bt)
         for k in range(max(0, n - (G - 1)), n):
-            res = det.fetchResident((k % G) * Bt, Bt, cap=4096 * Bt)
-        return res
+            det.fetchResidentPrepared(fprep, (k % G) * Bt)
+        return det.lists(fprep)
 
     one_gpu_steps(G)
     barrier()
@@ -347,25 +348,26 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         uid = uid.cuda()
         dist.broadcast(uid, 0)
         det.commInit(uid.cpu().numpy(), rank, world)
-        state = {"k": 0, "pending": [], "last": None}
+        state = {"k": 0, "pending": []}
+        nown = Bt // world
+        uprep = det.prepareUpload(frames[rank * nown:(rank + 1) * nown])   # e2e: only the rank's own frame block crosses PCIe
 
         def step(upload):
             g = state["k"] % G
             state["k"] += 1
-            if upload:                                    # e2e: only the rank's own frame block crosses PCIe
-                n = Bt // world
-                det.uploadFrames(frames[rank * n:(rank + 1) * n], g * Bt + rank * n)
+            if upload:
+                det.uploadPrepared(uprep, g * Bt + rank * nown)
             det.matchResidentSharded(g * Bt, Bt, thr)
             state["pending"].append(g)
             if len(state["pending"]) >= G:                # keep G-1 steps in flight behind the one being fetched
-                state["last"] = det.fetchResident(state["pending"].pop(0) * Bt, Bt, allgather=True, cap=4096 * Bt)
+                det.fetchResidentPrepared(fprep, state["pending"].pop(0) * Bt, allgather=True)
 
         def drain():
             while state["pending"]:
-                state["last"] = det.fetchResident(state["pending"].pop(0) * Bt, Bt, allgather=True, cap=4096 * Bt)
+                det.fetchResidentPrepared(fprep, state["pending"].pop(0) * Bt, allgather=True)
 
         def timed(upload):
-            for _ in range(max(4, W)):
+            for _ in range(max(2 * G + 2, W)):            # every slot group twice: first uses allocate pinned and device buffers
                 step(upload)
             drain()
             barrier()
@@ -380,7 +382,7 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
             return float(t.item())
 
         dt = timed(False)
-        last = state["last"]
+        last = det.lists(fprep)
         # where the step goes on the device (CUDA events of rank 0, a few extra steps outside the timed region)
         det.setProfiling(True); det.getProfile(reset=True)
         for _ in range(4):
@@ -393,9 +395,16 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         det.setOption("upload_async", 1)
         dte = timed(True)
         det.setOption("upload_async", 0)
+        # A/B of the two design choices of the sharded step (same timed loop, no uploads)
+        variants = {}
+        for name, opt in (("host_epilogue_thread", "shard_device_epilogue"), ("no_lane_overlap", "shard_overlap")):
+            det.setOption(opt, 0)
+            variants[name + "_ms_per_step"] = round(1e3 * timed(False) / K, 4)
+            det.setOption(opt, 1)
+        out["variants"] = variants
         value = Bt * K / dt
         e2e = {"value": Bt * K / dte, "unit": "frames/s", "ms_per_step": 1e3 * dte / K, "h2d_bytes_per_step_per_gpu": Bt // world * FRAME_BYTES,
-               "mode": "every rank uploads only its own frame block from pinned host memory, lmb200_match_resident_sharded, lmb200_fetch_resident_allgather (match lists on the host of every rank)"}
+               "mode": "every rank uploads only its own frame block from pinned host memory (lmb200_upload_frames, async), lmb200_match_resident_sharded, lmb200_fetch_resident_allgather (complete match lists in host memory of every rank); %d steps in flight" % G}
         # all ranks must hold the identical merged lists
         sig = torch.tensor([sum(len(g) for g in last), int(sum(float(g.similarity.sum()) for g in last))], device="cuda", dtype=torch.int64)
         lo, hi = sig.clone(), sig.clone()
@@ -404,7 +413,7 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
                     "efficiency_vs_full_set_on_1_gpu": value / (world * single["value"]),
                     "ranks_agree": bool(torch.equal(lo, hi)),
                     "frame_side": "sharded: each rank quantises %d of the %d frames, NCCL all-gather of the quantized maps, every rank spreads all frames" % (Bt // world, Bt),
-                    "collectives_per_step": "1 NCCL group (quantized maps) + ncclAllGather(match buffers) + ncclAllGather(finished lists)"})
+                    "collectives_per_step": "1 NCCL group (quantized maps, lane 3, main communicator) + 1 ncclAllGather (match buffers, compute lane, second communicator); the host epilogue runs on the handle's epilogue thread"})
     # ---- in-run parity bit against the oracle (rank 0; three frames of the last timed step)
     if rank == 0:
         from oracle import oracle as O

@@ -267,19 +267,25 @@ int lmb200_set_template_shard(lmb200_handle h, int rank, int world);
 int lmb200_comm_unique_id(uint8_t* unique_id128);
 int lmb200_comm_init(lmb200_handle h, const uint8_t* unique_id128, int rank, int world);
 int lmb200_comm_destroy(lmb200_handle h);
-/* After lmb200_match_resident on every rank: one ncclAllGather of the fixed-capacity per-frame match
- * buffers on the compute stream, then the rank-ordered concatenation (= reference generation order)
- * goes through the same host sort/unique.  Every rank returns the identical merged list.
- * Template-sharded mode: all ranks hold the same frames. */
+/* Collective fetch of a template-sharded step: every rank returns the identical, complete per-frame lists (all ranks
+ * must call it for the same slot ranges in the same order).  Per step a kernel packs the per-frame match buffers of the
+ * rank's shard into one compact buffer, ONE ncclAllGather over NVLink shares them, and the rank-/position-ordered
+ * concatenation (= the reference's generation order) goes through the same std::sort / std::unique epilogue as the 1-GPU
+ * path.  After lmb200_match_resident_sharded the gather has already been enqueued behind the step's kernels and the
+ * epilogue has run on the handle's epilogue thread: the call then only waits for that thread and copies the lists out.
+ * After plain lmb200_match_resident (template shard set, every rank holds the same frames) it does the same work
+ * synchronously.  Overflowing stores are grown and the step's template side is redone, as in the 1-GPU fetch. */
 int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, int count,
                                     lmb200_match_rec* out, size_t cap, size_t* offsets);
 /* The same template-sharded step with the expensive half of the frame side sharded as well: rank r quantises only the
  * frame block [first + r*n, first + (r+1)*n) (n = count / world) — so only those frames have to be uploaded on rank r —
  * the quantized maps are all-gathered in place over NVLink (one NCCL group), and every rank spreads all frames and
  * scores its template shard.  Needs lmb200_comm_init + lmb200_set_template_shard with the same rank/world; count not a
- * multiple of world falls back to lmb200_match_resident (replicated frame side).  Follow with
- * lmb200_fetch_resident_allgather, which also distributes the host epilogue (rank r sorts/uniques its frame block, a
- * second small all-gather shares the finished lists). */
+ * multiple of world falls back to lmb200_match_resident (replicated frame side).  The call only enqueues: quantisers
+ * and map all-gather on a lane of their own (overlapping the previous step's template side), then spread, matching, the
+ * match gather and its copy to pinned memory on the compute lane; a per-handle epilogue thread merges the gathered
+ * lists when they land.  Follow with lmb200_fetch_resident_allgather; several steps on different slot ranges may be
+ * in flight (up to 4), fetched in submission order.  Do not add templates while steps are in flight. */
 int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, float threshold,
                                   const char* const* class_ids, int n_class_ids);
 /* Pure host helper (no GPU): merge per-rank, generation-ordered partial lists exactly as above.
@@ -293,7 +299,8 @@ int lmb200_shard_plan(const double* costs, int n, int world, int* begin);
 enum {
   LMB200_K_UPLOAD = 0, LMB200_K_PYRDOWN, LMB200_K_CG_QUANTIZE, LMB200_K_DN_QUANTIZE, LMB200_K_MEDIAN,
   LMB200_K_DECIMATE, LMB200_K_LINEARIZE, LMB200_K_SIM_COARSE, LMB200_K_SIM_LOCAL, LMB200_K_PACK,
-  LMB200_K_COMM,           /* NCCL collectives issued on the compute lane (all-gather of the quantized maps) */
+  LMB200_K_COMM,           /* NCCL all-gather of the quantized maps (template-sharded step) */
+  LMB200_K_EPILOGUE,       /* device std::sort + std::unique of the template-sharded step */
   LMB200_K_COUNT
 };
 typedef struct {
@@ -305,12 +312,22 @@ typedef struct {
   long long candidates, matches;
   long long chunks_coarse;            /* 16-byte chunk loads the coarse kernel actually issued (after its early exit) */
 } lmb200_profile;
+/* Test hook for the device epilogue's sort (csrc/sort_emul.h restates libstdc++'s std::sort so that the device returns the
+ * reference's sequence, ties included): runs the restatement (host build) and the real thing on the same records.
+ * mode 0: std::sort, 1: std::partial_sort over the whole range (the heap-sort fallback), 2: std::sort on an input built by
+ * McIlroy's quicksort adversary (template ids are overwritten; forces the depth limit).  Both outputs hold n records. */
+int lmb200_debug_sort_check(const lmb200_match_rec* in, size_t n, int mode, lmb200_match_rec* out_emulated, lmb200_match_rec* out_std);
+
 /* Measurement knobs.  "early_exit" (default 1): 0 switches off the coarse kernel's exact early exit (results are
  * identical either way; the bench reports both so the workload dependence of the exit is visible).
  * "upload_async" (default 0): 1 makes lmb200_upload_frames return without synchronising (pinned host frames that stay
  * valid until the results of the next match on those slots have been fetched).
  * "cuda_graph" (default 1; environment LMB200_NO_GRAPH=1 starts with 0): lmb200_match replays the kernel sequence of one
- * frame as a CUDA graph (re-captured when plan, templates, selection, stores or threshold change). */
+ * frame as a CUDA graph (re-captured when plan, templates, selection, stores or threshold change).
+ * "shard_overlap" (default 1): lmb200_match_resident_sharded runs its quantisers and the all-gather of the quantized maps
+ * on a lane of their own, overlapping the template side of the previous step (0: everything on the compute lane).
+ * "shard_device_epilogue" (default 1): the std::sort + std::unique of a template-sharded step run on the device
+ * (csrc/kernels_epilogue.cu, sequence-identical to libstdc++'s); 0: on the handle's host epilogue thread. */
 int lmb200_set_option(lmb200_handle h, const char* name, int value);
 int lmb200_set_profiling(lmb200_handle h, int enabled);        /* CUDA events around every launch */
 int lmb200_get_profile(lmb200_handle h, lmb200_profile* out, int reset);

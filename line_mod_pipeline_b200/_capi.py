@@ -12,7 +12,7 @@ SIMLUT_CIRCULAR, SIMLUT_LINEAR = 0, 1
 MB_L2_READ, MB_L1_READ, MB_HBM_READ, MB_H2D = range(4)
 OK, E_INVALID, E_SOURCES, E_SIZE, E_FEATURES, E_CLASS, E_IO, E_CUDA, E_TRUNCATED, E_COMM, E_NODEVICE = range(0, -11, -1)
 K_NAMES = ["upload", "pyrdown", "cg_quantize", "dn_quantize", "median", "decimate", "linearize",
-           "sim_coarse", "sim_local", "pack", "comm"]
+           "sim_coarse", "sim_local", "pack", "comm", "epilogue"]
 DBG_QUANTIZED, DBG_LINMEM, DBG_COARSE, DBG_UNSORTED, DBG_MAGNITUDE, DBG_DN_INDICES, DBG_SIMILARITY = range(7)
 
 
@@ -47,7 +47,7 @@ class MatchRec(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 11), ("launches", C.c_longlong * 11), ("bytes_coarse", C.c_longlong),
+    _fields_ = [("ms", C.c_double * len(K_NAMES)), ("launches", C.c_longlong * len(K_NAMES)), ("bytes_coarse", C.c_longlong),
                 ("bytes_local", C.c_longlong), ("frames", C.c_longlong), ("candidates", C.c_longlong),
                 ("matches", C.c_longlong), ("chunks_coarse", C.c_longlong)]
 
@@ -133,6 +133,7 @@ SIGNATURES = {
     "lmb200_comm_destroy": (C.c_int, [_H]),
     "lmb200_fetch_resident_allgather": (C.c_int, [_H, C.c_int, C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_merge_matches": (C.c_int, [_P(_P(MatchRec)), _P(C.c_size_t), C.c_int, _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
+    "lmb200_debug_sort_check": (C.c_int, [_P(MatchRec), C.c_size_t, C.c_int, _P(MatchRec), _P(MatchRec)]),
     "lmb200_shard_plan": (C.c_int, [_P(C.c_double), C.c_int, C.c_int, _P(C.c_int)]),
     "lmb200_postmatch_color": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, _P(MatchRec), C.c_size_t, _P(C.c_int), _P(C.c_int)]),
     "lmb200_group_matches": (C.c_int, [_P(MatchRec), C.c_size_t, C.c_float, C.c_float, _P(C.c_int), _P(C.c_int)]),

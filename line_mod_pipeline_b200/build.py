@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblmb200.so")
-SOURCES = ["kernels_frame.cu", "kernels_spread.cu", "kernels_color.cu", "kernels_depth.cu", "kernels_postmatch.cu", "kernels_match.cu", "detector.cu", "extract.cpp", "persistence.cpp", "comm.cpp", "capi.cpp", "render.cpp", "microbench.cu"]
-HEADERS = ["kernels.cuh", "detector.h", os.path.join("..", "..", "include", "lmb200.h")]
+SOURCES = ["kernels_frame.cu", "kernels_spread.cu", "kernels_color.cu", "kernels_depth.cu", "kernels_postmatch.cu", "kernels_match.cu", "kernels_epilogue.cu", "detector.cu", "extract.cpp", "persistence.cpp", "comm.cpp", "capi.cpp", "render.cpp", "microbench.cu", "sort_check.cpp"]
+HEADERS = ["kernels.cuh", "detector.h", "sort_emul.h", os.path.join("..", "..", "include", "lmb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

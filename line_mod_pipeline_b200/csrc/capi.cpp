@@ -111,6 +111,7 @@ void lmb200_destroy(lmb200_handle h) {
   if (!h) return;
   if (h->device_ready) {
     cudaSetDevice(h->device);
+    shard_jobs_stop(h);
     cudaDeviceSynchronize();
     comm_destroy(h);
     for (auto& lb : h->levels)
@@ -118,13 +119,13 @@ void lmb200_destroy(lmb200_handle h) {
     for (int m = 0; m < LMB200_MAX_MODALITIES; ++m) { h->d_depth[m].release(); h->d_dnraw[m].release(); }
     for (int l = 0; l < LMB200_MAX_LEVELS; ++l) { h->d_hdr[l].release(); h->d_feat[l].release(); h->d_offs[l].release(); }
     lmh::DevBuf* bufs[] = {&h->d_frames, &h->d_table, &h->d_normal_lut, &h->d_sel, &h->d_mag, &h->d_dnidx, &h->d_cand, &h->d_ctr,
-                           &h->d_tpl_start, &h->d_tpl_cnt, &h->d_tpl_alive, &h->d_out, &h->d_gather_send, &h->d_gather_recv, &h->d_resp_sum, &h->d_fin_send, &h->d_fin_recv, &h->d_hue_bits};
+                           &h->d_tpl_start, &h->d_tpl_cnt, &h->d_tpl_alive, &h->d_out, &h->d_gather_send, &h->d_gather_recv, &h->d_resp_sum, &h->d_hue_bits, &h->d_gclass, &h->d_gtid, &h->d_posg};
     for (auto* b : bufs) b->release();
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_gather) cudaFreeHost(h->h_gather);
-    if (h->h_fin) cudaFreeHost(h->h_fin);
-    for (auto& g : h->gsets) { g.send.release(); g.recv.release(); if (g.host) cudaFreeHost(g.host); if (g.ev) cudaEventDestroy(g.ev); }
+    for (auto& g : h->jobs) { g.send.release(); g.recv.release(); if (g.host) cudaFreeHost(g.host); if (g.ev) cudaEventDestroy(g.ev); if (g.ev_q) cudaEventDestroy(g.ev_q); if (g.ev_g) cudaEventDestroy(g.ev_g);
+      g.fin_dev.release(); if (g.fin_host) cudaFreeHost(g.fin_host); if (g.hdr_host) cudaFreeHost(g.hdr_host); }
     for (auto& tk : h->tickets) {
       if (tk.b_ctr) cudaFreeHost(tk.b_ctr);
       if (tk.b_out) cudaFreeHost(tk.b_out);

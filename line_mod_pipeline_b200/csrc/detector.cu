@@ -172,8 +172,10 @@ static int upload_luts(lmb200_detector* h) {
   return LMB200_OK;
 }
 
+static void shard_jobs_quiesce(lmb200_detector* h);
 static int rebuild_templates(lmb200_detector* h) {
   if (!h->templates_dirty) return LMB200_OK;
+  shard_jobs_quiesce(h);   // the epilogue thread reads g_class / g_tid
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
   h->class_list.clear(); h->g_class.clear(); h->g_tid.clear();
   int ci = 0;
@@ -392,6 +394,7 @@ static int ensure_selection(lmb200_detector* h, const char* const* class_ids, in
   std::string key = std::to_string(h->shard_rank) + "/" + std::to_string(h->shard_world) + ":";
   for (int i = 0; i < n_class_ids; ++i) { key += class_ids[i]; key.push_back('\x1f'); }
   if (key == h->sel_key && h->d_sel.p) return LMB200_OK;
+  shard_jobs_quiesce(h);   // the epilogue thread reads pos_of_g
   std::vector<int> sel;
   if (n_class_ids <= 0) {
     sel.resize(h->ntpl);
@@ -668,6 +671,7 @@ static int run_matching(lmb200_detector* h, int first, int count, float threshol
 }
 
 static int grow_capacity(lmb200_detector* h) {
+  shard_jobs_quiesce(h);
   CU(cudaDeviceSynchronize());
   if (h->cand_cap > (1 << 24)) return set_error(h, LMB200_E_CUDA, "candidate buffer overflow persists after growing");
   h->cand_cap *= 4; h->out_cap = h->cand_cap;
@@ -783,7 +787,7 @@ static void drain_tickets(lmb200_detector* h) {
 }
 
 // Host epilogue of n independent frames (record -> Match, std::sort, std::unique) on a few threads.
-static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Cand>>& raws, std::vector<std::vector<Match>>& outs) {
+static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Cand>>& raws, std::vector<std::vector<Match>>& outs, unsigned max_threads = 8u) {
   NvtxRange nvtx("lmb200:epilogue(std::sort, std::unique)");
   const int n = (int)raws.size();
   outs.resize(n);
@@ -792,7 +796,7 @@ static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Ca
   };
   size_t total = 0;
   for (auto& r : raws) total += r.size();
-  int nt = (int)std::min<size_t>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), total / 2048 + 1);
+  int nt = (int)std::min<size_t>(std::min<unsigned>(max_threads, std::max(1u, std::thread::hardware_concurrency())), total / 2048 + 1);
   if (nt <= 1 || n < 2) { work(0, n); return; }
   std::vector<std::thread> pool;
   for (int t = 0; t < nt; ++t) pool.emplace_back(work, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
@@ -816,6 +820,148 @@ static int prepare(lmb200_detector* h, const lmb200_image* frames, int n_frames,
   if (rc) return rc;
   return ensure_selection(h, class_ids, n_class_ids);
 }
+
+static_assert(sizeof(lmk::EpiMatch) == sizeof(lmb200_match_rec), "the device epilogue writes lmb200_match_rec records");
+
+namespace lmh {
+// ---------------------------------------------------------------- template-sharded steps: host epilogue off the critical path
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Gathered match buffers of all ranks (host memory; per rank [2*count header records][gcap match records], see
+// gather_pack_kernel) -> the finished lists of every frame: reference generation order restored (rank-ordered
+// concatenation for contiguous shards; ordered by selection position for interleaved shards: every template lives on
+// exactly one rank and its records are already in raster order), then the 1-GPU epilogue (record -> Match, std::sort,
+// std::unique), so the result is sequence-identical to the unsharded run.
+static void merge_gathered(lmb200_detector* h, const Cand* G, int gcap, int count, unsigned max_threads,
+                           std::vector<lmb200_match_rec>& recs, std::vector<size_t>& offs, long long* candidates, long long* matches,
+                           double* t_reorder, double* t_sort) {
+  const int world = h->comm_world;
+  const double t0 = now_ms();
+  auto rank_base = [&](int r) { return G + (size_t)r * ((size_t)2 * count + gcap); };
+  std::vector<std::vector<Cand>> alls(count);
+  auto gather_frames = [&](int a, int b) {
+    for (int i = a; i < b; ++i) {
+      std::vector<Cand>& all = alls[i];
+      size_t tot = 0;
+      for (int r = 0; r < world; ++r) tot += (size_t)rank_base(r)[2 * i].tsel;
+      all.reserve(tot);
+      for (int r = 0; r < world; ++r) {
+        const Cand* rb = rank_base(r);
+        const Cand* rec = rb + 2 * (size_t)count + rb[2 * i].y;
+        all.insert(all.end(), rec, rec + rb[2 * i].tsel);
+      }
+      if (h->shard_interleaved)
+        std::stable_sort(all.begin(), all.end(), [h](const Cand& a, const Cand& b) { return h->pos_of_g[a.tsel] < h->pos_of_g[b.tsel]; });
+    }
+  };
+  const int nt = count >= 16 ? (int)std::min(4u, std::max(1u, max_threads)) : 1;
+  if (nt == 1) gather_frames(0, count);
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(gather_frames, count * t / nt, count * (t + 1) / nt);
+    for (auto& th : pool) th.join();
+  }
+  const double t1 = now_ms();
+  std::vector<std::vector<Match>> ms;
+  finalize_frames(h, alls, ms, max_threads);
+  size_t total = 0;
+  for (auto& m : ms) total += m.size();
+  recs.resize(total); offs.resize((size_t)count + 1);
+  size_t base = 0;
+  long long nc = 0;
+  for (int i = 0; i < count; ++i) {
+    offs[i] = base;
+    nc += (long long)alls[i].size();
+    for (const Match& mt : ms[i]) {
+      lmb200_match_rec& r = recs[base++];
+      r.x = mt.x; r.y = mt.y; r.similarity = mt.similarity; r.class_index = mt.class_index; r.template_id = mt.template_id;
+    }
+  }
+  offs[count] = base;
+  if (candidates) *candidates = nc;
+  if (matches) *matches = (long long)total;
+  if (t_reorder) *t_reorder = t1 - t0;
+  if (t_sort) *t_sort = now_ms() - t1;
+}
+
+// any header flag set (1: a candidate store overflowed on some rank, 2: the record area was too small) -> synchronous path
+static bool gathered_needs_redo(const Cand* G, int gcap, int count, int world) {
+  for (int r = 0; r < world; ++r)
+    for (int i = 0; i < count; ++i)
+      if (G[(size_t)r * ((size_t)2 * count + gcap) + 2 * i].x) return true;
+  return false;
+}
+
+static void shard_epilogue_loop(lmb200_detector* h) {
+  cudaSetDevice(h->device);
+  for (;;) {
+    ShardJob* job = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(h->epi_mu);
+      h->epi_cv.wait(lk, [h] { return h->epi_stop || !h->epi_queue.empty(); });
+      if (h->epi_queue.empty()) return;       // stop requested and nothing left
+      job = h->epi_queue.front();
+    }
+    const double t0 = now_ms();
+    int state = 3;
+    if (cudaEventSynchronize(job->ev) == cudaSuccess && !gathered_needs_redo(job->host, job->cap, job->count, h->comm_world)) {
+      job->t_wait = now_ms() - t0;
+      const Cand* mine = job->host + (size_t)h->comm_rank * ((size_t)2 * job->count + job->cap);
+      job->bytes_local = 0; job->chunks_coarse = 0;
+      for (int i = 0; i < job->count; ++i) {
+        const Cand& st1 = mine[2 * i + 1];
+        job->bytes_local += (long long)(((unsigned long long)(u32)st1.x << 32) | (u32)st1.tsel);
+        job->chunks_coarse += (long long)(((unsigned long long)(u32)__builtin_bit_cast(int, st1.sim) << 32) | (u32)st1.y);
+      }
+      // few helper threads: one process per GPU shares the host with its peers
+      merge_gathered(h, job->host, job->cap, job->count, 3u, job->recs, job->offs, &job->candidates, &job->matches, &job->t_reorder, &job->t_sort);
+      state = 2;
+    }
+    {
+      std::lock_guard<std::mutex> lk(h->epi_mu);
+      job->state = state;
+      h->epi_queue.pop_front();
+    }
+    h->epi_done_cv.notify_all();
+  }
+}
+
+static void shard_job_submit(lmb200_detector* h, ShardJob* job) {
+  {
+    std::lock_guard<std::mutex> lk(h->epi_mu);
+    if (!h->epi_thread.joinable()) { h->epi_stop = false; h->epi_thread = std::thread(shard_epilogue_loop, h); }
+    job->state = 1;
+    h->epi_queue.push_back(job);
+  }
+  h->epi_cv.notify_one();
+}
+
+// wait until the epilogue thread is done with this entry (no-op when it is idle or already finished)
+static void shard_job_wait(lmb200_detector* h, ShardJob* job) {
+  std::unique_lock<std::mutex> lk(h->epi_mu);
+  h->epi_done_cv.wait(lk, [job] { return job->state != 1; });
+}
+static void shard_job_retire(lmb200_detector* h, ShardJob* job) {
+  shard_job_wait(h, job);
+  job->state = 0;
+}
+static void shard_jobs_quiesce(lmb200_detector* h) {
+  if (!h->epi_thread.joinable()) return;
+  std::unique_lock<std::mutex> lk(h->epi_mu);
+  h->epi_done_cv.wait(lk, [h] { return h->epi_queue.empty(); });
+}
+void shard_jobs_stop(lmb200_detector* h) {
+  if (!h->epi_thread.joinable()) return;
+  {
+    std::lock_guard<std::mutex> lk(h->epi_mu);
+    h->epi_stop = true;
+  }
+  h->epi_cv.notify_all();
+  h->epi_thread.join();
+  for (auto& j : h->jobs) j.state = 0;
+}
+
+}  // namespace lmh
 
 extern "C" {
 
@@ -904,62 +1050,148 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
   h->masks_in_use = false;
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
   const int n = count / world, own = first_slot + h->comm_rank * n;
+  const bool trace = std::getenv("LMB200_TRACE") != nullptr;
+  const double t_begin = trace ? now_ms() : 0.0;
+  double tp[6] = {0, 0, 0, 0, 0, 0};
+  int tpi = 0;
+  auto lap = [&]() { if (trace && tpi < 6) tp[tpi++] = now_ms(); };
   cudaStream_t st = h->lanes[0].stream;
-  rc = wait_async_upload(h);
+  // Lanes.  Quantisers + all-gather of the quantized maps run on lane 3 ("shard_overlap", default on) so that they overlap
+  // the template side of the PREVIOUS step on the compute lane; the compute lane picks the gathered maps up through ev_q.
+  // The map all-gather uses the main communicator, the match gather the second one: NCCL serialises the collectives of one
+  // communicator in issue order, which would chain the maps of step k+1 behind the matches of step k.
+  cudaStream_t sq = h->shard_overlap ? h->lanes[3].stream : st;
+  ShardJob* job = nullptr;
+  for (auto& g : h->jobs) if (g.first == first_slot && g.count == count) job = &g;
+  if (!job) job = &h->jobs[h->job_next++ & 3];
+  shard_job_retire(h, job);          // an unfetched step on this entry: let the epilogue thread finish with it first
+  if (!job->ev) CU(cudaEventCreateWithFlags(&job->ev, cudaEventDisableTiming));
+  if (!job->ev_q) CU(cudaEventCreateWithFlags(&job->ev_q, cudaEventDisableTiming));
+  if (h->upload_pending) {
+    CU(cudaStreamWaitEvent(sq, h->upload_ev, 0));
+    h->upload_pending = false;
+  }
+  if (sq != st)   // the maps of these slots may still be read by an earlier step on the compute lane
+    for (auto& mk : h->resident_marks)
+      if (mk.ev && mk.first < first_slot + count && first_slot < mk.first + mk.count) CU(cudaStreamWaitEvent(sq, mk.ev, 0));
+  lap();
+  rc = run_frame_side(h, own, n, sq, FS_QUANTIZE);
   if (rc) return rc;
-  rc = run_frame_side(h, own, n, st, FS_QUANTIZE);
-  if (rc) return rc;
-  ProfScope ps_comm(h, LMB200_K_COMM, st);
-  rc = comm_group_begin(h);
-  if (rc) return rc;
-  for (int l = 0; l < L; ++l)
-    for (int m = 0; m < M; ++m) {
-      // maps the quantise phase writes: ColorGradient at every level; DepthNormal at level 0 (+ the decimation chain when materialised)
-      const bool written = h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT || l == 0 || h->dn_materialize;
-      if (!written) continue;
-      LevelBuffers& lb = h->levels[l];
-      u8* base = lb.q[m].as<u8>() + (size_t)first_slot * lb.q_stride;
-      rc = comm_allgather(h, base + (size_t)h->comm_rank * n * lb.q_stride, base, (size_t)n * lb.q_stride, st);
-      if (rc) { comm_group_end(h); return rc; }
-    }
-  rc = comm_group_end(h);
-  if (rc) return rc;
-  ps_comm.finish();
+  lap();
+  {
+    ProfScope ps_comm(h, LMB200_K_COMM, sq);
+    rc = comm_group_begin(h);
+    if (rc) return rc;
+    for (int l = 0; l < L; ++l)
+      for (int m = 0; m < M; ++m) {
+        // maps the quantise phase writes: ColorGradient at every level; DepthNormal at level 0 (+ the decimation chain when materialised)
+        const bool written = h->cfg.modalities[m].type == LMB200_COLOR_GRADIENT || l == 0 || h->dn_materialize;
+        if (!written) continue;
+        LevelBuffers& lb = h->levels[l];
+        u8* base = lb.q[m].as<u8>() + (size_t)first_slot * lb.q_stride;
+        rc = comm_allgather(h, base + (size_t)h->comm_rank * n * lb.q_stride, base, (size_t)n * lb.q_stride, sq);
+        if (rc) { comm_group_end(h); return rc; }
+      }
+    rc = comm_group_end(h);
+    if (rc) return rc;
+  }
+  if (sq != st) {
+    CU(cudaEventRecord(job->ev_q, sq));
+    CU(cudaStreamWaitEvent(st, job->ev_q, 0));
+  }
+  lap();
   rc = run_frame_side(h, first_slot, count, st, FS_SPREAD);
   if (rc) return rc;
+  lap();
   rc = run_matching(h, first_slot, count, threshold, st);
   if (rc) return rc;
+  lap();
   ResidentMark& mk = h->resident_marks[h->resident_next++ & 3];
   if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
   mk.first = first_slot; mk.count = count;
   CU(cudaEventRecord(mk.ev, st));
   // The match gather rides on the compute lane right behind the kernels — pack, ncclAllGather and the copy to pinned host
-  // memory need no host decision — so lmb200_fetch_resident_allgather finds every rank's lists waiting for it instead of
-  // running a latency-bound collective of its own.  (Overflowing stores / lists longer than the buffer are detected at
-  // fetch time from the gathered headers and take the synchronous path there.)
+  // memory need no host decision — and the epilogue thread takes over from there (ShardJob in detector.h).  Overflowing
+  // stores / lists longer than the buffer show in the gathered headers and send the fetch down the synchronous path.
   {
-    GatherSet* gs = nullptr;
-    for (auto& g : h->gsets) if (g.first == first_slot && g.count == count) gs = &g;
-    if (!gs) gs = &h->gsets[h->gset_next++ & 3];
     if (h->gather_cap <= 0) h->gather_cap = 256;   // average records per frame the buffer holds; doubles when a step needs more
     const int rec_cap = h->gather_cap * count;
     const size_t bytes = ((size_t)2 * count + rec_cap) * sizeof(Cand);
-    gs->valid = false; gs->first = first_slot; gs->count = count;
-    ALLOC(gs->send, bytes);
-    ALLOC(gs->recv, bytes * world);
-    if (gs->host_bytes < bytes * world) {
-      if (gs->host) { cudaFreeHost(gs->host); gs->host = nullptr; }
-      CU(cudaHostAlloc((void**)&gs->host, bytes * world, cudaHostAllocDefault));
-      gs->host_bytes = bytes * world;
+    job->first = first_slot; job->count = count;
+    ALLOC(job->send, bytes);
+    ALLOC(job->recv, bytes * world);
+    if (job->host_bytes < bytes * world) {
+      if (job->host) { cudaFreeHost(job->host); job->host = nullptr; }
+      CU(cudaHostAlloc((void**)&job->host, bytes * world, cudaHostAllocDefault));
+      job->host_bytes = bytes * world;
     }
-    if (!gs->ev) CU(cudaEventCreateWithFlags(&gs->ev, cudaEventDisableTiming));
+    const bool dev_epi = h->shard_device_epilogue && world <= 64;
+    if (dev_epi) {
+      // finished lists come from the device (kernels_epilogue.cu): tables, scratch and the pinned, device-mapped result area
+      if (h->epi_tables_epoch != h->plan_epoch) {
+        const size_t nb = (size_t)std::max(1, h->ntpl) * sizeof(int);
+        ALLOC(h->d_gclass, nb); ALLOC(h->d_gtid, nb); ALLOC(h->d_posg, nb);
+        if (h->ntpl > 0) {
+          CU(cudaMemcpyAsync(h->d_gclass.p, h->g_class.data(), (size_t)h->ntpl * sizeof(int), cudaMemcpyHostToDevice, st));
+          CU(cudaMemcpyAsync(h->d_gtid.p, h->g_tid.data(), (size_t)h->ntpl * sizeof(int), cudaMemcpyHostToDevice, st));
+          if (h->shard_interleaved) CU(cudaMemcpyAsync(h->d_posg.p, h->pos_of_g.data(), (size_t)h->ntpl * sizeof(int), cudaMemcpyHostToDevice, st));
+          CU(cudaStreamSynchronize(st));   // the sources are pageable vectors: finish the copies before anything can change them
+        }
+        h->epi_tables_epoch = h->plan_epoch;
+      }
+      const size_t fin_cap = (size_t)rec_cap * world;
+      ALLOC(job->fin_dev, fin_cap * sizeof(EpiMatch));
+      if (job->fin_cap < fin_cap) {
+        if (job->fin_host) { cudaFreeHost(job->fin_host); job->fin_host = nullptr; }
+        CU(cudaHostAlloc((void**)&job->fin_host, fin_cap * sizeof(EpiMatch), cudaHostAllocMapped));
+        job->fin_cap = fin_cap;
+      }
+      if (job->hdr_frames < count) {
+        if (job->hdr_host) { cudaFreeHost(job->hdr_host); job->hdr_host = nullptr; }
+        CU(cudaHostAlloc((void**)&job->hdr_host, (size_t)2 * count * sizeof(int4), cudaHostAllocMapped));
+        job->hdr_frames = count;
+      }
+      if (!job->ev_g) CU(cudaEventCreateWithFlags(&job->ev_g, cudaEventDisableTiming));
+      if (job->generation >= 0) CU(cudaStreamWaitEvent(st, job->ev, 0));   // the previous epilogue on this entry still reads recv
+    }
     launch_gather_pack(h->d_ctr.as<SlotCtr>() + first_slot, h->d_out.as<Cand>() + (size_t)first_slot * h->out_cap, h->out_cap,
-                       gs->send.as<Cand>(), rec_cap, count, st);
-    rc = comm_allgather(h, gs->send.p, gs->recv.p, bytes, st);
+                       job->send.as<Cand>(), rec_cap, count, st);
+    rc = comm_allgather(h, job->send.p, job->recv.p, bytes, st, true);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(gs->host, gs->recv.p, bytes * world, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(gs->ev, st));
-    gs->cap = rec_cap; gs->generation = h->buffer_generation; gs->valid = true;
+    job->cap = rec_cap; job->generation = h->buffer_generation;
+    if (dev_epi) {
+      // std::sort + std::unique of every frame on the high-priority lane: the serial sorts (one thread per frame) must not
+      // hold the next step's kernels back on the compute lane
+      cudaStream_t se = h->lanes[1].stream;
+      CU(cudaEventRecord(job->ev_g, st));
+      CU(cudaStreamWaitEvent(se, job->ev_g, 0));
+      EpilogueArgs ea;
+      ea.gathered = job->recv.as<Cand>(); ea.world = world; ea.rank = h->comm_rank; ea.frames = count; ea.gcap = rec_cap;
+      ea.pos_of_g = h->shard_interleaved ? h->d_posg.as<int>() : nullptr;
+      ea.g_class = h->d_gclass.as<int>(); ea.g_tid = h->d_gtid.as<int>();
+      ea.out_dev = job->fin_dev.as<EpiMatch>(); ea.out_cap = (int)std::min<size_t>(job->fin_cap, 0x7fffffff);
+      void* dp = nullptr;
+      CU(cudaHostGetDevicePointer(&dp, job->fin_host, 0)); ea.out_host = (EpiMatch*)dp;
+      CU(cudaHostGetDevicePointer(&dp, job->hdr_host, 0)); ea.hdr = (int4*)dp;
+      {
+        ProfScope ps(h, LMB200_K_EPILOGUE, se);
+        launch_shard_epilogue(ea, se);
+      }
+      CU(cudaEventRecord(job->ev, se));
+      job->state = 4;
+    } else {
+      CU(cudaMemcpyAsync(job->host, job->recv.p, bytes * world, cudaMemcpyDeviceToHost, st));
+      CU(cudaEventRecord(job->ev, st));
+      shard_job_submit(h, job);
+    }
+  }
+  if (trace && h->comm_rank == 0) {
+    const double t_end = now_ms();
+    std::fprintf(stderr, "[lmb200 trace] sharded submit: enqueue %.3f ms", t_end - t_begin);
+    if (t_end - t_begin > 1.0)
+      std::fprintf(stderr, " (prepare %.3f, quantise %.3f, map all-gather %.3f, spread %.3f, matching %.3f, gather + epilogue %.3f)",
+                   tp[0] - t_begin, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], t_end - tp[4]);
+    std::fprintf(stderr, "\n");
   }
   return LMB200_OK;
 }
@@ -1450,6 +1682,8 @@ int lmb200_set_option(lmb200_handle h, const char* name, int value) {
   if (std::strcmp(name, "early_exit") == 0) { h->early_exit = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "upload_async") == 0) { h->upload_async = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return LMB200_OK; }
+  if (std::strcmp(name, "shard_overlap") == 0) { h->shard_overlap = value != 0; return LMB200_OK; }
+  if (std::strcmp(name, "shard_device_epilogue") == 0) { h->shard_device_epilogue = value != 0; return LMB200_OK; }
   return set_error(h, LMB200_E_INVALID, std::string("unknown option ") + name);
 }
 
@@ -1858,35 +2092,72 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   if (first_slot < 0 || count <= 0 || first_slot + count > h->slots) return set_error(h, LMB200_E_INVALID, "bad slot range");
   if (!h->nccl_comm) return set_error(h, LMB200_E_COMM, "communicator not initialised (lmb200_comm_init)");
   cudaSetDevice(h->device);
-  cudaStream_t st = resident_fetch_stream(h, first_slot, count);
   const int world = h->comm_world;
   const bool trace = std::getenv("LMB200_TRACE") != nullptr;
-  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  double tt[5] = {now(), 0, 0, 0, 0};
-  // 1+2. One round trip: a kernel packs {count, overflow flag, counters, first gather_cap matches} of every frame, the
-  //      buffers are all-gathered and copied to pinned host memory.  Every rank sees every flag and count, so all ranks
-  //      take the same decisions: a rank that overflowed its candidate store grows it and redoes its template side, a list
-  //      longer than gather_cap doubles the capacity, and the gather is repeated.
+  const double t_begin = now_ms();
+  auto emit_lists = [&](const std::vector<lmb200_match_rec>& recs, const std::vector<size_t>& offs) {
+    const size_t total = offs[count], w = std::min(total, cap);
+    if (w && out) std::memcpy(out, recs.data(), w * sizeof(lmb200_match_rec));
+    if (offsets) for (int i = 0; i <= count; ++i) offsets[i] = offs[i];
+    return w < total ? LMB200_E_TRUNCATED : LMB200_OK;
+  };
+  // 1. A step submitted through lmb200_match_resident_sharded: its gather rode on the compute lane and the epilogue thread
+  //    has merged it (or is about to): pick the finished lists up.
+  for (auto& job : h->jobs) {
+    if (!(job.state != 0 && job.first == first_slot && job.count == count)) continue;
+    if (job.state == 4) {   // device epilogue: the finished lists are in pinned memory once ev fires
+      CU(cudaEventSynchronize(job.ev));
+      const double t_dev = now_ms() - t_begin;
+      bool ok = job.generation == h->buffer_generation;
+      for (int i = 0; i < count && ok; ++i) ok = job.hdr_host[2 * i].z == 0;
+      job.state = 0;
+      if (!ok) break;       // a flag (store overflow, record area too small, list too long for the device sort): synchronous path below
+      size_t base = 0;
+      int status = LMB200_OK;
+      for (int i = 0; i < count; ++i) {
+        const int4 hd = job.hdr_host[2 * i], c4 = job.hdr_host[2 * i + 1];
+        const size_t nfin = (size_t)hd.x, room = cap > base ? cap - base : 0, w = std::min(nfin, room);
+        if (offsets) offsets[i] = base;
+        if (w && out) std::memcpy(out + base, job.fin_host + hd.y, w * sizeof(lmb200_match_rec));
+        if (w < nfin) status = LMB200_E_TRUNCATED;
+        base += nfin;
+        h->prof.candidates += hd.w; h->prof.matches += hd.x;
+        h->prof.bytes_local += (long long)(((unsigned long long)(u32)c4.y << 32) | (u32)c4.x);
+        h->prof.chunks_coarse += (long long)(((unsigned long long)(u32)c4.w << 32) | (u32)c4.z);
+      }
+      if (offsets) offsets[count] = base;
+      if (h->profiling) collect_profile(h);
+      if (trace && h->comm_rank == 0)
+        std::fprintf(stderr, "[lmb200 trace] allgather fetch: waited %.3f ms for the device (kernels + gather + device epilogue), copy-out %.3f ms\n",
+                     t_dev, now_ms() - t_begin - t_dev);
+      return status;
+    }
+    shard_job_wait(h, &job);
+    const bool ready = job.state == 2 && job.generation == h->buffer_generation;
+    job.state = 0;
+    if (!ready) break;      // flags in the gathered headers, or the stores grew meanwhile: synchronous path below
+    h->prof.bytes_local += job.bytes_local; h->prof.chunks_coarse += job.chunks_coarse;
+    h->prof.candidates += job.candidates; h->prof.matches += job.matches;
+    if (h->profiling) collect_profile(h);
+    const int status = emit_lists(job.recs, job.offs);
+    if (trace && h->comm_rank == 0)
+      std::fprintf(stderr, "[lmb200 trace] allgather fetch: waited %.3f ms for the epilogue thread (its wait for the device %.3f ms, reorder %.3f ms, sort/unique %.3f ms)\n",
+                   now_ms() - t_begin, job.t_wait, job.t_reorder, job.t_sort);
+    return status;
+  }
+  // 2. Synchronous path (plain lmb200_match_resident with a template shard, or a step whose headers carry a flag).  One round
+  //    trip: a kernel packs {count, flags, counters, matches} of every frame, the buffers are all-gathered and copied to
+  //    pinned host memory.  Every rank sees every flag and count, so all ranks take the same decisions: a rank that
+  //    overflowed its candidate store grows it and redoes its template side, a record area that is too small doubles, and
+  //    the gather is repeated.
+  cudaStream_t st = resident_fetch_stream(h, first_slot, count);
   {
     int rc = revalidate_slots(h, first_slot, count);
     if (rc) return rc;
   }
   if (h->gather_cap <= 0) h->gather_cap = 256;    // average records per frame the buffer holds; doubles when a step needs more
-  const Cand* G = nullptr;   // gathered buffers of all ranks in host memory, per rank: [2*count headers][gcap records]
   int gcap = 0;
-  auto rank_base = [&](int r) { return G + (size_t)r * ((size_t)2 * count + gcap); };
-  for (auto& g : h->gsets) {  // the sharded step already gathered on the compute lane: wait for its copy only
-    if (!(g.valid && g.first == first_slot && g.count == count && g.generation == h->buffer_generation)) continue;
-    g.valid = false;
-    CU(cudaEventSynchronize(g.ev));
-    bool redo = false;
-    for (int r = 0; r < world && !redo; ++r)
-      for (int i = 0; i < count; ++i)
-        if (g.host[(size_t)r * ((size_t)2 * count + g.cap) + 2 * i].x) { redo = true; break; }
-    if (!redo) { G = g.host; gcap = g.cap; }
-    break;
-  }
-  while (!G) {
+  for (;;) {
     const int rec_cap = h->gather_cap * count;
     const size_t bytes = ((size_t)2 * count + rec_cap) * sizeof(Cand);
     ALLOC(h->d_gather_send, bytes);
@@ -1916,120 +2187,29 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
       rc = run_matching(h, first_slot, count, thr, h->lanes[0].stream);
       if (rc) return rc;
       CU(cudaStreamSynchronize(h->lanes[0].stream));
+      st = h->lanes[0].stream;
     }
     if (store_over) continue;
     if (small) { h->gather_cap *= 2; continue; }   // every rank sees the flag: all double together
-    G = h->h_gather; gcap = rec_cap;
+    gcap = rec_cap;
+    break;
   }
+  const Cand* mine = h->h_gather + (size_t)h->comm_rank * ((size_t)2 * count + gcap);
   for (int i = 0; i < count; ++i) {
-    const Cand& st1 = rank_base(h->comm_rank)[2 * i + 1];
+    const Cand& st1 = mine[2 * i + 1];
     h->prof.bytes_local += (long long)(((unsigned long long)(u32)st1.x << 32) | (u32)st1.tsel);
     h->prof.chunks_coarse += (long long)(((unsigned long long)(u32)__builtin_bit_cast(int, st1.sim) << 32) | (u32)st1.y);
   }
-  tt[1] = now();
   if (h->profiling) collect_profile(h);
-  tt[2] = now();
-  // 3. restore reference generation order (rank-ordered concatenation for contiguous shards; ordered by selection
-  //    position for interleaved shards: every template lives on exactly one rank and its records are already in
-  //    raster order), then the same epilogue as the 1-GPU path.  With enough frames the host work is DISTRIBUTED: rank r
-  //    finalises the frame block [r*per, (r+1)*per) and a second all-gather shares the finished lists (round 1 had every
-  //    rank sort every frame: ~3.6 ms of redundant host work per 96-frame step, the limiter of that mode).
-  size_t base = 0;
-  int status = LMB200_OK;
-  const bool distribute = world > 1 && count >= 2 * world;
-  const int per = distribute ? (count + world - 1) / world : count;
-  const int lo = distribute ? std::min(count, h->comm_rank * per) : 0, hi = distribute ? std::min(count, lo + per) : count;
-  std::vector<std::vector<Cand>> alls(hi - lo);
-  {
-    auto gather_frames = [&](int a, int b) {
-      for (int i = a; i < b; ++i) {
-        std::vector<Cand>& all = alls[i - lo];
-        for (int r = 0; r < world; ++r) {
-          const Cand* rb = rank_base(r);
-          const Cand* rec = rb + 2 * (size_t)count + rb[2 * i].y;
-          all.insert(all.end(), rec, rec + rb[2 * i].tsel);
-        }
-        if (h->shard_interleaved)
-          std::stable_sort(all.begin(), all.end(), [h](const Cand& a, const Cand& b) { return h->pos_of_g[a.tsel] < h->pos_of_g[b.tsel]; });
-      }
-    };
-    const int nf = hi - lo, nt = nf >= 16 ? 4 : 1;
-    if (nt == 1) gather_frames(lo, hi);
-    else {
-      std::vector<std::thread> pool;
-      for (int t = 0; t < nt; ++t) pool.emplace_back(gather_frames, lo + nf * t / nt, lo + nf * (t + 1) / nt);
-      for (auto& th : pool) th.join();
-    }
-  }
-  tt[3] = now();
-  std::vector<std::vector<Match>> ms;
-  finalize_frames(h, alls, ms);
-  tt[4] = now();
-  if (!distribute) {
-    for (int i = 0; i < count; ++i) {
-      h->prof.candidates += (long long)alls[i].size();
-      h->prof.matches += (long long)ms[i].size();
-      size_t n = 0;
-      if (offsets) offsets[i] = base;
-      if (emit(h, ms[i], out, cap, base, &n) != LMB200_OK) status = LMB200_E_TRUNCATED;
-      base += n;
-    }
-    if (offsets) offsets[count] = base;
-  } else {
-    // Compact per-rank buffer [per header records {count}][records of the block's frames back to back]; its capacity is
-    // derived identically on every rank from the gathered counts (unique can only shrink a list): the largest block total.
-    size_t cap2 = 0;
-    for (int r = 0; r < world; ++r) {
-      size_t tot = 0;
-      for (int i = std::min(count, r * per); i < std::min(count, (r + 1) * per); ++i)
-        for (int q = 0; q < world; ++q) tot += (size_t)rank_base(q)[2 * i].tsel;
-      cap2 = std::max(cap2, tot);
-    }
-    const size_t pitch2 = (size_t)per + cap2, bytes2 = pitch2 * sizeof(lmb200_match_rec);
-    ALLOC(h->d_fin_send, bytes2);
-    ALLOC(h->d_fin_recv, bytes2 * world);
-    if (h->h_fin_bytes < bytes2 * world) {
-      if (h->h_fin) { cudaFreeHost(h->h_fin); h->h_fin = nullptr; }
-      CU(cudaHostAlloc((void**)&h->h_fin, bytes2 * world, cudaHostAllocDefault));
-      h->h_fin_bytes = bytes2 * world;
-    }
-    lmb200_match_rec* mine = h->h_fin + (size_t)h->comm_rank * pitch2;  // staged in place in the pinned receive mirror
-    {
-      lmb200_match_rec* rec = mine + per;
-      for (int j = 0; j < per; ++j) {
-        const int i = lo + j;
-        const int n = i < hi ? (int)ms[j].size() : 0;
-        mine[j].x = n; mine[j].y = 0; mine[j].similarity = 0.f; mine[j].class_index = 0; mine[j].template_id = 0;
-        for (int k = 0; k < n; ++k, ++rec) {
-          const Match& mt = ms[j][k];
-          rec->x = mt.x; rec->y = mt.y; rec->similarity = mt.similarity; rec->class_index = mt.class_index; rec->template_id = mt.template_id;
-        }
-        if (i < hi) { h->prof.candidates += (long long)alls[j].size(); h->prof.matches += (long long)n; }
-      }
-    }
-    CU(cudaMemcpyAsync(h->d_fin_send.p, mine, bytes2, cudaMemcpyHostToDevice, st));
-    int rc = comm_allgather(h, h->d_fin_send.p, h->d_fin_recv.p, bytes2, st, true);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h->h_fin, h->d_fin_recv.p, bytes2 * world, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int r = 0; r < world; ++r) {
-      const lmb200_match_rec* hdr = h->h_fin + (size_t)r * pitch2;
-      const lmb200_match_rec* rec = hdr + per;
-      for (int j = 0; j < per; ++j) {
-        const int i = r * per + j;
-        if (i >= count) break;
-        const size_t n = (size_t)hdr[j].x;
-        if (offsets) offsets[i] = base;
-        const size_t room = cap > base ? cap - base : 0, w = std::min(n, room);
-        if (w) std::memcpy(out + base, rec, w * sizeof(lmb200_match_rec));
-        if (w < n) status = LMB200_E_TRUNCATED;
-        base += n; rec += n;
-      }
-    }
-    if (offsets) offsets[count] = base;
-  }
+  const double t_gather = now_ms();
+  std::vector<lmb200_match_rec> recs; std::vector<size_t> offs;
+  long long nc = 0, nm = 0;
+  double t_reorder = 0, t_sort = 0;
+  merge_gathered(h, h->h_gather, gcap, count, 8u, recs, offs, &nc, &nm, &t_reorder, &t_sort);
+  h->prof.candidates += nc; h->prof.matches += nm;
+  const int status = emit_lists(recs, offs);
   if (trace && h->comm_rank == 0)
-    std::fprintf(stderr, "[lmb200 trace] allgather fetch: wait compute %.3f ms, gather+D2H %.3f ms, reorder %.3f ms, sort/unique %.3f ms, share %.3f ms\n",
-                 tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], now() - tt[4]);
+    std::fprintf(stderr, "[lmb200 trace] allgather fetch (synchronous): gather+D2H %.3f ms, reorder %.3f ms, sort/unique %.3f ms\n",
+                 t_gather - t_begin, t_reorder, t_sort);
   return status;
 }

@@ -2,8 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lmb200.h"
@@ -72,15 +76,26 @@ struct Lane {
 };
 
 struct ProfRec { int family; cudaEvent_t a, b; };
-// Match gather of one sharded step, enqueued on the compute lane right behind the step's kernels
-// (lmb200_match_resident_sharded): the fetch only waits for `ev` and finds every rank's lists in pinned memory.
-struct GatherSet {
+// One template-sharded step in flight (lmb200_match_resident_sharded).  The match gather — pack kernel, ncclAllGather and
+// the copy to pinned host memory — rides on the compute lane right behind the step's kernels, and the host epilogue
+// (reference generation order, record -> Match, std::sort, std::unique of every frame) runs on the handle's epilogue
+// thread as soon as `ev` fires: neither costs the submitting thread anything, and lmb200_fetch_resident_allgather only
+// picks the finished lists up.  No second collective, no host-synchronous rendezvous between the ranks.
+struct ShardJob {
   int first = -1, count = 0, cap = 0;
   long long generation = -1;
-  bool valid = false;
+  int state = 0;        // 0 idle, 1 queued for the epilogue thread, 2 finished lists ready, 3 the gathered flags ask for the synchronous path,
+                        // 4 device epilogue enqueued (finished lists land in fin_host when ev fires)
   DevBuf send, recv;
   lmk::Cand* host = nullptr; size_t host_bytes = 0;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr, ev_q = nullptr;      // results landed in pinned memory / quantized maps of the step gathered
+  cudaEvent_t ev_g = nullptr;                    // match gather done on the compute lane (the device epilogue waits for it on lane 1)
+  DevBuf fin_dev;                                // device epilogue: finished records, device scratch
+  lmk::EpiMatch* fin_host = nullptr; size_t fin_cap = 0;   // ... and their pinned, device-mapped host mirror
+  int4* hdr_host = nullptr; int hdr_frames = 0;  // pinned, device-mapped: per frame {n_final, offset, flags, n_in}, {counters}
+  std::vector<lmb200_match_rec> recs; std::vector<size_t> offs;   // finished lists, frames back to back
+  long long candidates = 0, matches = 0, bytes_local = 0, chunks_coarse = 0;
+  double t_wait = 0, t_reorder = 0, t_sort = 0;
 };
 struct ResidentMark { cudaEvent_t ev = nullptr; int first = 0, count = 0; };  // completion of one lmb200_match_resident call
 
@@ -184,9 +199,13 @@ struct lmb200_detector {
   void* nccl_comm_fetch = nullptr;          // second communicator (ncclCommSplit) for the result-fetch collectives
   lmh::DevBuf d_gather_send, d_gather_recv; int gather_cap = 0;
   lmk::Cand* h_gather = nullptr; size_t h_gather_bytes = 0;
-  lmh::GatherSet gsets[4]; unsigned gset_next = 0;
-  lmh::DevBuf d_fin_send, d_fin_recv;          // finished (sorted + unique) per-frame lists, second all-gather
-  lmb200_match_rec* h_fin = nullptr; size_t h_fin_bytes = 0;
+  lmh::ShardJob jobs[4]; unsigned job_next = 0;
+  std::thread epi_thread; std::mutex epi_mu; std::condition_variable epi_cv, epi_done_cv;   // epilogue thread of the sharded steps
+  std::deque<lmh::ShardJob*> epi_queue; bool epi_stop = false;
+  bool shard_device_epilogue = true;        // lmb200_set_option("shard_device_epilogue"): std::sort/std::unique of the sharded step on the device
+                                            // (kernels_epilogue.cu); 0: on the handle's epilogue thread
+  lmh::DevBuf d_gclass, d_gtid, d_posg; long long epi_tables_epoch = -1;   // device copies of g_class / g_tid / pos_of_g
+  bool shard_overlap = true;                // lmb200_set_option("shard_overlap"): quantise + map all-gather of step k+1 on a lane of their own
 
   // scratch for lmb200_get_template
   std::vector<lmb200_feature> tmp_features;
@@ -221,6 +240,7 @@ void set_create_error(const std::string& msg);
 int comm_unique_id(uint8_t* id128, std::string& err);
 int comm_init(lmb200_detector* h, const uint8_t* id128, int rank, int world);
 int comm_destroy(lmb200_detector* h);
+void shard_jobs_stop(lmb200_detector* h);   // detector.cu: drains and joins the epilogue thread
 int comm_allgather(lmb200_detector* h, const void* send, void* recv, size_t bytes, cudaStream_t st, bool fetch_path = false);
 int comm_group_begin(lmb200_detector* h);
 int comm_group_end(lmb200_detector* h);

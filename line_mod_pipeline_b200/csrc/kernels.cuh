@@ -180,6 +180,19 @@ void launch_pack(const MatchParams& mp, Cand* out, int out_cap, cudaStream_t st)
 // multi-GPU: compact send buffer of the match all-gather: [2*frames header records][rec_cap match records, frames back to back]
 void launch_gather_pack(const SlotCtr* ctr, const Cand* out, int out_cap, Cand* send, int rec_cap, int frames, cudaStream_t st);
 
+// ------------------------------------------------------------------ device epilogue of the template-sharded step (kernels_epilogue.cu)
+constexpr int EPI_SORT_CAP = 4096;     // records per frame (all ranks together) the device sort takes; longer lists go to the host
+struct EpiMatch { int x, y; float sim; int class_index, template_id; };   // = lmb200_match_rec
+struct EpilogueArgs {
+  const Cand* gathered;                // [world][2*frames header records + gcap match records] (gather_pack_kernel, all-gathered)
+  int world, rank, frames, gcap;
+  const int* pos_of_g;                 // interleaved shards: global template index -> selection position; null: rank-ordered concatenation
+  const int* g_class; const int* g_tid;  // global template index -> class index / template id
+  EpiMatch* out_dev; EpiMatch* out_host; int out_cap;   // device scratch and its pinned host mirror (device-mapped), records
+  int4* hdr;                           // pinned [2*frames]: {n_final, offset, flags, n_in}, {this rank's local_bytes lo, hi, coarse_chunks lo, hi}
+};                                     // flags: 1/2 from the gathered headers (store overflow / record area too small), 4 list too long, 8 output too small
+void launch_shard_epilogue(const EpilogueArgs& a, cudaStream_t st);
+
 // ------------------------------------------------------------------ post-match colour check (kernels_postmatch.cu)
 // bits: [rows][(cols+31)/32] u32, bit x%32 of word x/32 = pixel (y, x) lies in the HSV range (cvtColor BGR2HSV + inRange)
 void launch_hsv_inrange_bits(const u8* bgr, int rows, int cols, const u8 lower[3], const u8 upper[3], u32* bits, cudaStream_t st);

@@ -20,6 +20,31 @@ class LinemodError(RuntimeError):
 MATCH_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("similarity", np.float32),
                         ("class_index", np.int32), ("template_id", np.int32)])
 assert MATCH_DTYPE.itemsize == C.sizeof(K.MatchRec)
+_MATCH_REC_DTYPE = np.dtype((np.record, MATCH_DTYPE))
+
+
+class MatchArray(np.ndarray):
+    """Per-frame match list: a structured array whose fields also read as attributes (m.x, m.similarity, m[0].template_id).
+    np.recarray offers the same but costs ~20 us per slice, which at 128 frames per step was more than a sharded step's
+    whole device time; this subclass slices at plain-ndarray speed."""
+    __slots__ = ()
+
+    def __getattr__(self, name):           # only reached when normal attribute lookup fails
+        if name in MATCH_DTYPE.fields:
+            return self[name].view(np.ndarray)
+        raise AttributeError(name)
+
+
+def _as_matches(a):
+    return a.view(_MATCH_REC_DTYPE).view(MatchArray)
+
+
+def _split(out, offs, count, copy=True):
+    """One flat result buffer + offsets -> list of per-frame MatchArray (ONE copy of the used records, then views)."""
+    o = np.frombuffer(offs, dtype=np.uintp, count=count + 1).tolist()
+    flat = out[:o[count]]
+    flat = _as_matches(flat.copy() if copy else flat)
+    return [flat[o[i]:o[i + 1]] for i in range(count)]
 
 
 def ColorGradient(weak_threshold=10.0, num_features=63, strong_threshold=55.0):
@@ -266,7 +291,7 @@ class Detector:
             if rc == K.E_TRUNCATED:
                 cap = int(n.value)
                 continue
-            res = out[:n.value].view(np.recarray)
+            res = _as_matches(out[:n.value])
             return (res, qimgs) if quantized_images else res
 
     def _frames(self, frames):
@@ -291,7 +316,7 @@ class Detector:
             if rc == K.E_TRUNCATED:
                 cap = int(offs[len(frames)])
                 continue
-            return [out[offs[i]:offs[i + 1]].copy().view(np.recarray) for i in range(len(frames))]
+            return _split(out, offs, len(frames))
 
     def _outbuf(self, cap):
         """Reusable (uninitialised) result buffer: zero-filling tens of MB per call would dominate a batch call."""
@@ -358,6 +383,33 @@ class Detector:
         ids, nids = _cstr_array(class_ids)
         self._check(self._L.lmb200_match_resident_sharded(self._h, first_slot, count, C.c_float(threshold), ids, nids))
 
+    def prepareUpload(self, frames):
+        """Marshals a frame list once (ctypes image array) so uploadPrepared() costs one lmb200_upload_frames call."""
+        arr, keep, nsrc = self._frames(frames)
+        return dict(arr=arr, keep=keep, nsrc=nsrc, n=len(frames))
+
+    def uploadPrepared(self, prep, first_slot=0):
+        self._check(self._L.lmb200_upload_frames(self._h, prep["arr"], prep["n"], prep["nsrc"], first_slot))
+
+    def prepareFetch(self, count, cap=None):
+        """Result buffers of fetchResidentPrepared(): records of all frames back to back in prep['out'], frame i at
+        prep['offs'][i] .. prep['offs'][i+1] (what a C caller of lmb200_fetch_resident[_allgather] holds)."""
+        cap = cap or 1024 * count
+        return dict(n=count, cap=cap, out=np.empty(cap, MATCH_DTYPE), offs=(C.c_size_t * (count + 1))())
+
+    def fetchResidentPrepared(self, prep, first_slot, allgather=False):
+        """One C-ABI call into the prepared buffers; returns the number of records.  lists(prep) makes the per-frame views."""
+        fn = self._L.lmb200_fetch_resident_allgather if allgather else self._L.lmb200_fetch_resident
+        rc = self._check(fn(self._h, first_slot, prep["n"], prep["out"].ctypes.data_as(C.POINTER(K.MatchRec)), prep["cap"], prep["offs"]),
+                         allow=(K.E_TRUNCATED,))
+        if rc == K.E_TRUNCATED:
+            raise LinemodError(rc, "prepared output buffer too small: need %d records" % prep["offs"][prep["n"]])
+        return int(prep["offs"][prep["n"]])
+
+    @staticmethod
+    def lists(prep, copy=True):
+        return _split(prep["out"], prep["offs"], prep["n"], copy)
+
     def fetchResident(self, first_slot, count, allgather=False, cap=None):
         cap = cap or 1024 * count
         fn = self._L.lmb200_fetch_resident_allgather if allgather else self._L.lmb200_fetch_resident
@@ -371,7 +423,7 @@ class Detector:
                 if allgather:
                     raise LinemodError(rc, "output capacity too small for a collective fetch; pass cap=")
                 continue
-            return [out[offs[i]:offs[i + 1]].copy().view(np.recarray) for i in range(count)]
+            return _split(out, offs, count)
 
     def synchronize(self):
         self._check(self._L.lmb200_synchronize(self._h))
@@ -447,7 +499,7 @@ class Detector:
         self._check(self._L.lmb200_debug_fetch(self._h, kind, slot, index, buf.ctypes.data, C.byref(n2)))
         buf = buf[:n2.value]
         if kind in (K.DBG_COARSE, K.DBG_UNSORTED):
-            return buf.view(MATCH_DTYPE).view(np.recarray)
+            return _as_matches(buf.view(MATCH_DTYPE))
         if kind == K.DBG_MAGNITUDE:
             return buf.view(np.float32)
         if kind == K.DBG_DN_INDICES:
@@ -538,7 +590,7 @@ def merge_matches(parts):
     rc = L.lmb200_merge_matches(ptrs, counts, len(parts), out.ctypes.data_as(C.POINTER(K.MatchRec)), len(out), C.byref(n))
     if rc:
         raise LinemodError(rc, "merge failed")
-    return out[:n.value].view(np.recarray)
+    return _as_matches(out[:n.value])
 
 
 def shard_plan(costs, world):

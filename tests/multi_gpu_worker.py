@@ -4,7 +4,9 @@ BASELINE configs[3]: 20 000 templates in 10 classes, template-sharded across N G
 ncclAllGather.  Both step variants must equal the oracle on every frame, on every rank:
   * lmb200_match_resident          (frame side replicated on every rank)
   * lmb200_match_resident_sharded  (quantisers sharded by frame block + NCCL all-gather of the quantized maps)
-and lmb200_fetch_resident_allgather must do so with the replicated host epilogue (few frames) and the distributed one."""
+and lmb200_fetch_resident_allgather must do so on its synchronous path (after lmb200_match_resident; a sharded step whose
+gathered headers carry the "record area too small" flag) and on the asynchronous one (gather on the compute lane + the
+handle's epilogue thread), with one and with two sharded steps in flight."""
 import os
 import sys
 
@@ -30,7 +32,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_frames = 2 * world * 2                      # multiple of world, >= 2*world: the distributed epilogue runs
     frames = [list(synth.make_frame(i)) for i in range(n_frames)]
-    det = lm.getDefaultLINEMOD(device=local, max_batch=n_frames)
+    det = lm.getDefaultLINEMOD(device=local, max_batch=2 * n_frames)
     ora = O.Detector([dict(type=O.CG), dict(type=O.DN)], [5, 8], sim_lut=det.getSimilarityLut(), normal_lut=det.getNormalLut())
     planted = 0
     for m in synth.object_masks(0) + synth.object_masks(1):
@@ -55,21 +57,35 @@ def main():
     ok = True
     checked = 0
     wants = {}
-    for variant in ("replicated", "sharded", "few_frames"):
-        thr = 80.0 if variant != "few_frames" else 62.0
+    n = n_frames // world
+    blank = [np.zeros_like(frames[0][0]), np.zeros_like(frames[0][1])]
+    for variant in ("replicated", "sharded", "sharded_host_epilogue", "few_frames", "sharded_many_matches", "two_in_flight_a", "two_in_flight_b"):
+        thr = 62.0 if variant in ("few_frames", "sharded_many_matches") else 80.0
         nf = n_frames if variant != "few_frames" else 3
-        if variant == "sharded":
+        order = list(range(n_frames))
+        if variant == "two_in_flight_b":
+            continue                                # fetched inside two_in_flight_a's iteration
+        # std::sort + std::unique on the device (default) or on the handle's host epilogue thread
+        det.setOption("shard_device_epilogue", 0 if variant == "sharded_host_epilogue" else 1)
+        if variant.startswith("sharded") or variant == "two_in_flight_a":
             # only the rank's own frame block is uploaded: the other blocks arrive as quantized maps over NCCL
-            n = n_frames // world
-            det2 = det
-            blank = [np.zeros_like(frames[0][0]), np.zeros_like(frames[0][1])]
-            det2.uploadFrames([frames[i] if rank * n <= i < (rank + 1) * n else blank for i in range(n_frames)], 0)
-            det2.matchResidentSharded(0, nf, thr)
+            det.uploadFrames([frames[i] if rank * n <= i < (rank + 1) * n else blank for i in range(n_frames)], 0)
+            det.matchResidentSharded(0, nf, thr)
+            if variant == "two_in_flight_a":        # a second step on the other slot group (frames in reverse order) before the first fetch
+                rev = order[::-1]
+                det.uploadFrames([frames[rev[i]] if rank * n <= i < (rank + 1) * n else blank for i in range(n_frames)], n_frames)
+                det.matchResidentSharded(n_frames, nf, thr)
         else:
             det.uploadFrames(frames[:nf], 0)
             det.matchResident(0, nf, thr)
         got = det.fetchResident(0, nf, allgather=True, cap=400000)
-        for i in range(rank, nf, world):           # every rank holds every list: each checks its share against the oracle
+        if variant == "two_in_flight_a":
+            got2 = det.fetchResident(n_frames, nf, allgather=True, cap=400000)
+            if [tup(g) for g in got2] != [tup(g) for g in got[::-1]]:
+                ok = False
+                print("rank %d: the second step in flight differs from the first (reversed frame order)" % rank, flush=True)
+        ncheck = min(nf, world) if variant == "sharded_many_matches" else nf   # the low threshold costs the oracle seconds per frame
+        for i in range(rank, ncheck, world):       # every rank holds every list: each checks its share against the oracle
             key = (i, thr)
             if key not in wants:
                 wants[key] = tup(ora.match(frames[i], thr, threads=max(1, O.max_threads() // world)).matches(0))

@@ -241,3 +241,32 @@ def test_group_matches_equals_the_reference_loop():
                 kept += 1
         got, ng = lm.group_matches(m, radius, ratio)
         assert ng == kept and np.array_equal(got, want), trial
+
+
+def test_device_sort_restatement_equals_std_sort():
+    """csrc/sort_emul.h (what the device epilogue runs) must leave the records in exactly std::sort's order, ties included:
+    Match::operator< looks at (similarity, template_id) only and std::sort is not stable, so the reference's sequence — and
+    which duplicates std::unique then finds adjacent — depends on libstdc++'s algorithm."""
+    L = lm.capi.lib()
+    rng = np.random.default_rng(7)
+    MR = lm.capi.MatchRec
+
+    def check(n, mode, sims=40, tids=50):
+        a = np.zeros(n, lm.MATCH_DTYPE)
+        a["x"] = rng.integers(0, 640, n); a["y"] = rng.integers(0, 480, n)
+        a["similarity"] = 80.0 + 0.5 * rng.integers(0, sims, n)      # few distinct values: ties everywhere
+        a["class_index"] = rng.integers(0, 10, n); a["template_id"] = rng.integers(0, tids, n)
+        e, s = np.zeros(n, lm.MATCH_DTYPE), np.zeros(n, lm.MATCH_DTYPE)
+        rc = L.lmb200_debug_sort_check(a.ctypes.data_as(C.POINTER(MR)), n, mode, e.ctypes.data_as(C.POINTER(MR)), s.ctypes.data_as(C.POINTER(MR)))
+        assert rc == 0
+        assert e.tobytes() == s.tobytes(), "n=%d mode=%d: restated sort differs from libstdc++'s" % (n, mode)
+        return s
+
+    for n in list(range(0, 40)) + [63, 64, 65, 100, 257, 1000, 4096, 5000]:
+        for rep in range(3):
+            check(n, 0)
+            check(n, 0, sims=2, tids=3)        # almost everything ties
+            check(n, 1)                        # heap sort (std::partial_sort over the whole range)
+    for n in (17, 100, 1000, 5000):
+        s = check(n, 2)                        # McIlroy's adversary: the depth limit is hit, heap-sort fallback inside std::sort
+        assert list(s["template_id"]) == sorted(s["template_id"])
