@@ -27,6 +27,7 @@ import json
 import os
 import subprocess
 import sys
+import gc
 import threading
 import time
 
@@ -52,6 +53,7 @@ def parse():
     ap.add_argument("--threshold", type=float, default=80.0)
     ap.add_argument("--ts-templates", type=int, default=20000, help="template_sharded leg: templates (configs[3]: 20 000)")
     ap.add_argument("--ts-frames", type=int, default=128, help="template_sharded leg: frames per step (all ranks together)")
+    ap.add_argument("--ts-groups", type=int, default=4, help="template_sharded leg: slot groups = steps in flight + 1 (2..4)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--template-cache", default="", help="YAML(.gz) written/read through the product's persistence; skips addTemplate when present")
     ap.add_argument("--no-e2e", action="store_true")
@@ -270,7 +272,7 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
     """BASELINE configs[3] / north_star's multi-GPU split.  Returns the dict for the JSON line (rank 0) or None."""
     Bt = args.ts_frames - args.ts_frames % max(1, world)
     thr = args.threshold
-    G = 3                                                 # slot groups: two steps in flight on the GPU while the host fetches a third
+    G = max(2, min(4, args.ts_groups))                    # slot groups: G-1 steps in flight on the GPU while the host fetches the oldest
     det = lm.getDefaultLINEMOD(device=local, max_batch=G * Bt)
     bgr0, depth0 = synth.make_frame(0)
     planted = build_templates_sharded_set(det, args.ts_templates, bgr0, depth0)
@@ -371,12 +373,14 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
                 step(upload)
             drain()
             barrier()
+            gc.disable()                                  # a collection on ANY rank stalls every rank at the next collective
             t0 = time.perf_counter()
             for _ in range(K):
                 step(upload)
             drain()                                       # the last step's gather + merge belongs to the timed region
             barrier()
             dt = time.perf_counter() - t0
+            gc.enable()
             t = torch.tensor([dt], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
@@ -397,10 +401,11 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         det.setOption("upload_async", 0)
         # A/B of the two design choices of the sharded step (same timed loop, no uploads)
         variants = {}
-        for name, opt in (("host_epilogue_thread", "shard_device_epilogue"), ("no_lane_overlap", "shard_overlap")):
-            det.setOption(opt, 0)
+        for name, opt, val, dflt in (("host_epilogue_thread", "shard_device_epilogue", 0, 1), ("spread_on_frame_lane", "shard_overlap", 2, 1),
+                                     ("no_lane_overlap", "shard_overlap", 0, 1)):
+            det.setOption(opt, val)
             variants[name + "_ms_per_step"] = round(1e3 * timed(False) / K, 4)
-            det.setOption(opt, 1)
+            det.setOption(opt, dflt)
         out["variants"] = variants
         value = Bt * K / dt
         e2e = {"value": Bt * K / dte, "unit": "frames/s", "ms_per_step": 1e3 * dte / K, "h2d_bytes_per_step_per_gpu": Bt // world * FRAME_BYTES,

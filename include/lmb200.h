@@ -325,7 +325,8 @@ int lmb200_debug_sort_check(const lmb200_match_rec* in, size_t n, int mode, lmb2
  * "cuda_graph" (default 1; environment LMB200_NO_GRAPH=1 starts with 0): lmb200_match replays the kernel sequence of one
  * frame as a CUDA graph (re-captured when plan, templates, selection, stores or threshold change).
  * "shard_overlap" (default 1): lmb200_match_resident_sharded runs its quantisers and the all-gather of the quantized maps
- * on a lane of their own, overlapping the template side of the previous step (0: everything on the compute lane).
+ * (1), or those and spread + linearize (2), on a high-priority lane of their own, overlapping the template side of the
+ * previous step (0: everything on the compute lane).
  * "shard_device_epilogue" (default 1): the std::sort + std::unique of a template-sharded step run on the device
  * (csrc/kernels_epilogue.cu, sequence-identical to libstdc++'s); 0: on the handle's host epilogue thread. */
 int lmb200_set_option(lmb200_handle h, const char* name, int value);

@@ -89,7 +89,9 @@ int ensure_device(lmb200_detector* h) {
   for (int i = 0; i < LMB200_LANES; ++i) {
     // lane 1 (copies, NCCL, result fetches) runs at the highest priority: its small kernels and collectives must not queue
     // behind the compute lanes' grids of the next step
-    CU(cudaStreamCreateWithPriority(&h->lanes[i].stream, cudaStreamNonBlocking, i == 1 ? prio_hi : prio_lo));
+    // lane 5 (quantisers + NCCL all-gather of the sharded step's frame side) too: a collective that waits for CTA slots
+    // behind a 0.8 ms template-side grid on ONE rank stalls the same collective on every other rank
+    CU(cudaStreamCreateWithPriority(&h->lanes[i].stream, cudaStreamNonBlocking, (i == 1 || i == 5) ? prio_hi : prio_lo));
   }
   h->device_ready = true;
   return LMB200_OK;
@@ -1056,11 +1058,13 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
   int tpi = 0;
   auto lap = [&]() { if (trace && tpi < 6) tp[tpi++] = now_ms(); };
   cudaStream_t st = h->lanes[0].stream;
-  // Lanes.  Quantisers + all-gather of the quantized maps run on lane 3 ("shard_overlap", default on) so that they overlap
-  // the template side of the PREVIOUS step on the compute lane; the compute lane picks the gathered maps up through ev_q.
+  // Lanes.  Quantisers and the all-gather of the quantized maps (shard_overlap = 1, the default; 2: spread + linearize
+  // too — measured slower at 8 GPUs: both sides are L2-heavy) run on lane 5, so that the frame side of step k+1 overlaps
+  // the template side of step k on the compute lane; the compute lane picks the step up through ev_q.
   // The map all-gather uses the main communicator, the match gather the second one: NCCL serialises the collectives of one
   // communicator in issue order, which would chain the maps of step k+1 behind the matches of step k.
-  cudaStream_t sq = h->shard_overlap ? h->lanes[3].stream : st;
+  cudaStream_t sq = h->shard_overlap ? h->lanes[5].stream : st;
+  const bool spread_on_sq = h->shard_overlap >= 2;
   ShardJob* job = nullptr;
   for (auto& g : h->jobs) if (g.first == first_slot && g.count == count) job = &g;
   if (!job) job = &h->jobs[h->job_next++ & 3];
@@ -1095,13 +1099,17 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
     rc = comm_group_end(h);
     if (rc) return rc;
   }
-  if (sq != st) {
+  if (sq != st && !spread_on_sq) {
     CU(cudaEventRecord(job->ev_q, sq));
     CU(cudaStreamWaitEvent(st, job->ev_q, 0));
   }
   lap();
-  rc = run_frame_side(h, first_slot, count, st, FS_SPREAD);
+  rc = run_frame_side(h, first_slot, count, spread_on_sq ? sq : st, FS_SPREAD);
   if (rc) return rc;
+  if (sq != st && spread_on_sq) {
+    CU(cudaEventRecord(job->ev_q, sq));
+    CU(cudaStreamWaitEvent(st, job->ev_q, 0));
+  }
   lap();
   rc = run_matching(h, first_slot, count, threshold, st);
   if (rc) return rc;
@@ -1682,7 +1690,7 @@ int lmb200_set_option(lmb200_handle h, const char* name, int value) {
   if (std::strcmp(name, "early_exit") == 0) { h->early_exit = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "upload_async") == 0) { h->upload_async = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return LMB200_OK; }
-  if (std::strcmp(name, "shard_overlap") == 0) { h->shard_overlap = value != 0; return LMB200_OK; }
+  if (std::strcmp(name, "shard_overlap") == 0) { h->shard_overlap = value < 0 ? 0 : value > 2 ? 2 : value; return LMB200_OK; }
   if (std::strcmp(name, "shard_device_epilogue") == 0) { h->shard_device_epilogue = value != 0; return LMB200_OK; }
   return set_error(h, LMB200_E_INVALID, std::string("unknown option ") + name);
 }

@@ -13,7 +13,7 @@
 #include "../../include/lmb200.h"
 #include "kernels.cuh"
 
-#define LMB200_LANES 5
+#define LMB200_LANES 6
 
 namespace lmh {
 
@@ -134,7 +134,8 @@ struct lmb200_detector {
   // ---- device ----
   bool device_ready = false;
   int device = -1;
-  lmh::Lane lanes[LMB200_LANES];   // 0: compute, 1: copy, 2..4: extra compute lanes of the batch path
+  lmh::Lane lanes[LMB200_LANES];   // 0: compute, 1: copy / device epilogue (high priority), 2..4: extra compute lanes of the batch path,
+                                   // 5: frame side of the template-sharded step (quantisers + map all-gather; high priority)
   lmh::DevBuf d_table, d_normal_lut;
   bool luts_dirty = true;
 
@@ -205,7 +206,7 @@ struct lmb200_detector {
   bool shard_device_epilogue = true;        // lmb200_set_option("shard_device_epilogue"): std::sort/std::unique of the sharded step on the device
                                             // (kernels_epilogue.cu); 0: on the handle's epilogue thread
   lmh::DevBuf d_gclass, d_gtid, d_posg; long long epi_tables_epoch = -1;   // device copies of g_class / g_tid / pos_of_g
-  bool shard_overlap = true;                // lmb200_set_option("shard_overlap"): quantise + map all-gather of step k+1 on a lane of their own
+  int shard_overlap = 1;                // lmb200_set_option("shard_overlap"): quantise + map all-gather of step k+1 on a lane of their own
 
   // scratch for lmb200_get_template
   std::vector<lmb200_feature> tmp_features;

@@ -57,23 +57,51 @@ __device__ __forceinline__ void transpose4(u32 r0, u32 r1, u32 r2, u32 r3, u32& 
   c2 = __byte_perm(u01, u23, 0x5410); c3 = __byte_perm(u01, u23, 0x7632);
 }
 
-// OR-reduce a staged band: raw[NR][RW] -> spread band in raw[0..NV)[0..PW) (NV = NR - (T-1) rows, PW words).
-// vb is scratch of NV*RW words.  All threads of the CTA call it; contains the barriers.
-template <int T>
-__device__ __forceinline__ void or_reduce(u32* raw, u32* vb, int NV, int RW, int PW, int tid, int nthr) {
-  // vertical: a warp per row keeps the index arithmetic division-free
-  for (int r = tid >> 5; r < NV; r += nthr >> 5)
-    for (int w = tid & 31; w < RW; w += 32) {
-      u32 v = raw[r * RW + w];
+// Staged band -> spread band.  band[NV][RW] (RW words per row, right halo of T-1 pixels included) receives
+//   spread(y, x) = OR of q over [y, y+T) x [x, x+T)      (upstream spread(): dst(y, x) |= src(y + r, x + c), clipped)
+// for the NV rows from image row y0 and the PW*4 pixel columns from x0.
+// Phase A — a thread owns (word column, segment of SEG rows): it reads its SEG + T-1 words straight from global memory
+//   (independent loads, all in flight together; round 1's row-at-a-time staging spent 41 % of the kernel's instructions
+//   and most of its stalls here), keeps the last T-1 rows in registers and stores the vertical OR.
+// Phase B — horizontal OR on words (funnel shifts), results held in registers across the barrier and written in place.
+// FAST: own-level map, 4-byte aligned rows, no mask.  Otherwise load_q_word (decimated reads, masks, ragged edges).
+// All threads of the CTA call it; ends with a barrier.
+template <int T, int SEG, int MAXV, bool FAST>
+__device__ __forceinline__ void stage_spread(const SpreadArgs& a, const u8* __restrict__ qf, const u8* __restrict__ mf, bool vec,
+                                             int y0, int x0, int NV, int RW, int PW, u32* band, int tid, int nthr) {
+  const int rows = a.g.rows, cols = a.g.cols;
+  const int nseg = (NV + SEG - 1) / SEG;
+  for (int it = tid; it < RW * nseg; it += nthr) {
+    const int sg = it / RW, w = it - sg * RW;
+    const int r0 = sg * SEG, gx = x0 + 4 * w;
+    const bool colok = gx < cols;                       // FAST: cols % 4 == 0 and gx % 4 == 0, so the whole word is inside
+    const u8* p = qf + (size_t)(y0 + r0) * a.q_pitch + gx;
+    u32 in[SEG + T - 1];
 #pragma unroll
-      for (int k = 1; k < T; ++k) v |= raw[(r + k) * RW + w];
-      vb[r * RW + w] = v;
+    for (int k = 0; k < SEG + T - 1; ++k) {
+      const int gy = y0 + r0 + k;
+      if (FAST) in[k] = (colok && gy < rows) ? __ldg(reinterpret_cast<const u32*>(p + (size_t)k * a.q_pitch)) : 0u;
+      else in[k] = load_q_word(a, qf, mf, gy, gx, vec);
     }
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      u32 v = in[j];
+#pragma unroll
+      for (int k = 1; k < T; ++k) v |= in[j + k];
+      if (r0 + j < NV) band[(r0 + j) * RW + w] = v;
+    }
+  }
   __syncthreads();
   constexpr int NW = (T + 2) / 4 + 1;  // words a T-wide window starting in word w can touch: bytes 4w .. 4w+3+T-1
-  for (int r = tid >> 5; r < NV; r += nthr >> 5)
-    for (int w = tid & 31; w < PW; w += 32) {
-      const u32* p = vb + r * RW + w;
+  const int total = NV * PW;
+  u32 hv[MAXV];
+#pragma unroll
+  for (int q = 0; q < MAXV; ++q) {
+    const int it = tid + q * nthr;
+    hv[q] = 0u;
+    if (it < total) {
+      const int r = it / PW, w = it - r * PW;
+      const u32* p = band + r * RW + w;
       u32 ww[NW + 1];
 #pragma unroll
       for (int j = 0; j < NW; ++j) ww[j] = (w + j < RW) ? p[j] : 0u;
@@ -81,8 +109,18 @@ __device__ __forceinline__ void or_reduce(u32* raw, u32* vb, int NV, int RW, int
       u32 v = 0;
 #pragma unroll
       for (int k = 0; k < T; ++k) v |= __funnelshift_r(ww[k >> 2], ww[(k >> 2) + 1], (k & 3) * 8);
-      raw[r * RW + w] = v;
+      hv[q] = v;
     }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < MAXV; ++q) {
+    const int it = tid + q * nthr;
+    if (it < total) {
+      const int r = it / PW, w = it - r * PW;
+      band[r * RW + w] = hv[q];
+    }
+  }
   __syncthreads();
 }
 
@@ -93,17 +131,17 @@ struct StripCfg {
   static constexpr int PW = PXW / 4;                    // ... in words
   static constexpr int RW = ((PXW + T - 1 + 3) / 4) | 1;  // staged words per row (right halo T-1), odd: lanes = rows hit distinct banks for odd T
   static constexpr int NV = R * T;                      // spread rows
-  static constexpr int NR = NV + T - 1;                 // staged rows (bottom halo)
-  static constexpr size_t SMEM = (size_t)(NR + NV) * RW * 4 + 256 * sizeof(uint2);
+  static constexpr int SEG = T >= 16 ? 8 : 16;          // rows per thread in phase A (registers: SEG + T - 1 words)
+  static constexpr int MAXV = (NV * PW + 255) / 256;    // phase-B words per thread
+  static constexpr size_t SMEM = (size_t)NV * RW * 4 + 256 * sizeof(uint2);
 };
 
-template <int T, int R>
-__global__ void __launch_bounds__(256) spread_strip_kernel(SpreadArgs a) {
+template <int T, int R, bool FAST>
+__global__ void __launch_bounds__(256, T >= 16 ? 2 : 5) spread_strip_kernel(SpreadArgs a) {
   typedef StripCfg<T, R> C;
   extern __shared__ __align__(16) u8 sp_smem[];
   uint2* tab = reinterpret_cast<uint2*>(sp_smem);
-  u32* raw = reinterpret_cast<u32*>(sp_smem + 256 * sizeof(uint2));
-  u32* vb = raw + C::NR * C::RW;
+  u32* band = reinterpret_cast<u32*>(sp_smem + 256 * sizeof(uint2));
   const int tid = threadIdx.x;
   const int strip = blockIdx.x, rg = blockIdx.y, frame = blockIdx.z;
   const u8* qf = a.q + (size_t)frame * a.q_stride;
@@ -112,12 +150,9 @@ __global__ void __launch_bounds__(256) spread_strip_kernel(SpreadArgs a) {
   const int y0 = rg * C::NV, x0 = strip * C::PXW;
   const bool vec = a.q_step == 1 && ((a.q_pitch & 3) == 0) && ((reinterpret_cast<size_t>(qf) & 3) == 0) &&
                    (!mf || (((a.g.cols & 3) == 0) && ((reinterpret_cast<size_t>(mf) & 3) == 0)));
-  for (int r = tid >> 5; r < C::NR; r += 8)
-    for (int w = tid & 31; w < C::RW; w += 32) raw[r * C::RW + w] = load_q_word(a, qf, mf, y0 + r, x0 + 4 * w, vec);
-  __syncthreads();
-  or_reduce<T>(raw, vb, C::NV, C::RW, C::PW, tid, 256);
+  stage_spread<T, C::SEG, C::MAXV, FAST>(a, qf, mf, vec, y0, x0, C::NV, C::RW, C::PW, band, tid, 256);
 
-  const u8* sb = reinterpret_cast<const u8*>(raw);
+  const u8* sb = reinterpret_cast<const u8*>(band);
   u8* lmf = a.lm + (size_t)frame * a.lm_stride;
   const int H = a.g.H, W = a.g.W;
   const u32 per = a.g.per_label, plane = a.g.plane;
@@ -156,7 +191,10 @@ __global__ void __launch_bounds__(256) spread_strip_kernel(SpreadArgs a) {
 
 // ------------------------------------------------------------------------------------------------ flat nibble layout
 // Tile = R decimated rows x CW decimated columns (CW a multiple of 8; the launcher makes W % 8 == 0 a precondition).
-template <int T>
+// Small tiles on purpose: the coarsest level is 1/4 of the pixels and 1/16 of the output bytes of the level below, so
+// only many short CTAs fill 148 SMs (5 tiles per frame left the kernel at 0.36 waves and 25 % of the warp slots).
+constexpr int FLAT_MAXV = 8;       // phase-B words per thread the launcher's tiles need at most
+template <int T, bool FAST>
 __global__ void __launch_bounds__(256) spread_flat_kernel(SpreadArgs a, int R, int CW) {
   extern __shared__ __align__(16) u8 sp_smem[];
   uint2* tab = reinterpret_cast<uint2*>(sp_smem);
@@ -167,21 +205,17 @@ __global__ void __launch_bounds__(256) spread_flat_kernel(SpreadArgs a, int R, i
   const int nrows = min(R, H - rg * R);            // decimated rows of this tile
   const int PW = cw * T / 4;                       // cw % 8 == 0 -> whole words
   const int RW = ((cw * T + T - 1 + 3) / 4) | 1;
-  const int NV = nrows * T, NR = NV + T - 1;
-  u32* raw = reinterpret_cast<u32*>(sp_smem + 256 * sizeof(uint2));
-  u32* vb = raw + (R * T + T - 1) * (((CW * T + T - 1 + 3) / 4) | 1);
+  const int NV = nrows * T;
+  u32* band = reinterpret_cast<u32*>(sp_smem + 256 * sizeof(uint2));
   const u8* qf = a.q + (size_t)frame * a.q_stride;
   const u8* mf = a.mask ? a.mask + (size_t)frame * a.mask_stride : nullptr;
   tab[tid] = __ldg(a.table + tid);
   const int y0 = rg * R * T, x0 = c0 * T;
   const bool vec = a.q_step == 1 && ((a.q_pitch & 3) == 0) && ((reinterpret_cast<size_t>(qf) & 3) == 0) &&
                    (!mf || (((a.g.cols & 3) == 0) && ((reinterpret_cast<size_t>(mf) & 3) == 0)));
-  for (int r = tid >> 5; r < NR; r += 8)
-    for (int w = tid & 31; w < RW; w += 32) raw[r * RW + w] = load_q_word(a, qf, mf, y0 + r, x0 + 4 * w, vec);
-  __syncthreads();
-  or_reduce<T>(raw, vb, NV, RW, PW, tid, 256);
+  stage_spread<T, 4, FLAT_MAXV, FAST>(a, qf, mf, vec, y0, x0, NV, RW, PW, band, tid, 256);
 
-  const u8* sb = reinterpret_cast<const u8*>(raw);
+  const u8* sb = reinterpret_cast<const u8*>(band);
   u8* out = a.lmn + (size_t)frame * a.lmn_stride;
   const u32 HW = (u32)H * W;
   const u32 per_n = (u32)(T * T) * HW / 2;         // nibble-packed bytes per label
@@ -218,24 +252,39 @@ __global__ void __launch_bounds__(256) spread_flat_kernel(SpreadArgs a, int R, i
   }
 }
 
+// FAST path of stage_spread: the map is this level's own (no decimated read), unmasked, and every row is a whole number of
+// aligned words
+static bool fast_loads(const SpreadArgs& a) {
+  return a.q_step == 1 && !a.mask && (a.q_pitch & 3) == 0 && (a.g.cols & 3) == 0 && (a.q_stride & 3) == 0 &&
+         (reinterpret_cast<size_t>(a.q) & 3) == 0;
+}
+
 template <int T, int R>
 void launch_strip(const SpreadArgs& a, int frames, cudaStream_t st) {
   typedef StripCfg<T, R> C;
-  if (C::SMEM > 48 * 1024) cudaFuncSetAttribute(spread_strip_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  static_assert(C::SMEM <= 48 * 1024, "strip tile exceeds the default dynamic shared memory");
   dim3 grid(a.g.strips, (a.g.H + R - 1) / R, frames);
-  spread_strip_kernel<T, R><<<grid, 256, C::SMEM, st>>>(a);
+  if (fast_loads(a)) spread_strip_kernel<T, R, true><<<grid, 256, C::SMEM, st>>>(a);
+  else spread_strip_kernel<T, R, false><<<grid, 256, C::SMEM, st>>>(a);
 }
 
 template <int T>
 void launch_flat(const SpreadArgs& a, int frames, cudaStream_t st) {
   const int W = a.g.W, H = a.g.H;
   int CW = W <= 64 ? W : 64;                        // W % 8 == 0, so every chunk is a multiple of 8 too
-  int R = 48 / T; if (R < 1) R = 1; if (R > H) R = H;
+  int R = 16 / T; if (R < 1) R = 1; if (R > H) R = H;   // ~16 image rows per tile
+  while (R > 1 && (R * T) * (CW * T / 4) > 256 * FLAT_MAXV) --R;
+  while (CW > 8 && (R * T) * (CW * T / 4) > 256 * FLAT_MAXV) CW -= 8;
   const int RWmax = ((CW * T + T - 1 + 3) / 4) | 1;
-  const size_t smem = (size_t)(2 * R * T + T - 1) * RWmax * 4 + 256 * sizeof(uint2);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)(R * T) * RWmax * 4 + 256 * sizeof(uint2);
   dim3 grid((W + CW - 1) / CW, (H + R - 1) / R, frames);
-  spread_flat_kernel<T><<<grid, 256, smem, st>>>(a, R, CW);
+  if (fast_loads(a)) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spread_flat_kernel<T, true><<<grid, 256, smem, st>>>(a, R, CW);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spread_flat_kernel<T, false><<<grid, 256, smem, st>>>(a, R, CW);
+  }
 }
 
 // Returns false when the geometry is not covered (the caller then runs round 1's generic kernels).
