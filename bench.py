@@ -49,10 +49,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU (configs[2]: 64)")
+    ap.add_argument("--slots", type=int, default=0, help="frame slots of the detector (max_batch); 0 = frames per step.  More slots = larger chunks / deeper buffering in the streaming batch path")
     ap.add_argument("--templates", type=int, default=3000)
     ap.add_argument("--threshold", type=float, default=80.0)
     ap.add_argument("--ts-templates", type=int, default=20000, help="template_sharded leg: templates (configs[3]: 20 000)")
     ap.add_argument("--ts-frames", type=int, default=128, help="template_sharded leg: frames per step (all ranks together)")
+    ap.add_argument("--no-ts-grid", action="store_true", help="template_sharded leg: skip the 2-D (template shards x frame groups) layout")
     ap.add_argument("--ts-groups", type=int, default=4, help="template_sharded leg: slot groups = steps in flight + 1 (2..4)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--template-cache", default="", help="YAML(.gz) written/read through the product's persistence; skips addTemplate when present")
@@ -350,40 +352,46 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
         uid = uid.cuda()
         dist.broadcast(uid, 0)
         det.commInit(uid.cpu().numpy(), rank, world)
-        state = {"k": 0, "pending": []}
         nown = Bt // world
-        uprep = det.prepareUpload(frames[rank * nown:(rank + 1) * nown])   # e2e: only the rank's own frame block crosses PCIe
 
-        def step(upload):
-            g = state["k"] % G
-            state["k"] += 1
-            if upload:
-                det.uploadPrepared(uprep, g * Bt + rank * nown)
-            det.matchResidentSharded(g * Bt, Bt, thr)
-            state["pending"].append(g)
-            if len(state["pending"]) >= G:                # keep G-1 steps in flight behind the one being fetched
-                det.fetchResidentPrepared(fprep, state["pending"].pop(0) * Bt, allgather=True)
+        def make_runner(Bs, fp, up, own_off):
+            """Pipelined sharded steps of Bs frames on G slot groups: step(upload), drain(), timed(upload) -> seconds (max over ranks)."""
+            state = {"k": 0, "pending": []}
 
-        def drain():
-            while state["pending"]:
-                det.fetchResidentPrepared(fprep, state["pending"].pop(0) * Bt, allgather=True)
+            def step(upload):
+                g = state["k"] % G
+                state["k"] += 1
+                if upload:                                    # e2e: only the rank's own frame block crosses PCIe
+                    det.uploadPrepared(up, g * Bs + own_off)
+                det.matchResidentSharded(g * Bs, Bs, thr)
+                state["pending"].append(g)
+                if len(state["pending"]) >= G:                # keep G-1 steps in flight behind the one being fetched
+                    det.fetchResidentPrepared(fp, state["pending"].pop(0) * Bs, allgather=True)
 
-        def timed(upload):
-            for _ in range(max(2 * G + 2, W)):            # every slot group twice: first uses allocate pinned and device buffers
-                step(upload)
-            drain()
-            barrier()
-            gc.disable()                                  # a collection on ANY rank stalls every rank at the next collective
-            t0 = time.perf_counter()
-            for _ in range(K):
-                step(upload)
-            drain()                                       # the last step's gather + merge belongs to the timed region
-            barrier()
-            dt = time.perf_counter() - t0
-            gc.enable()
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
+            def drain():
+                while state["pending"]:
+                    det.fetchResidentPrepared(fp, state["pending"].pop(0) * Bs, allgather=True)
+
+            def timed(upload):
+                for _ in range(max(2 * G + 2, W)):            # every slot group twice: first uses allocate pinned and device buffers
+                    step(upload)
+                drain()
+                barrier()
+                gc.disable()                                  # a collection on ANY rank stalls every rank at the next collective
+                t0 = time.perf_counter()
+                for _ in range(K):
+                    step(upload)
+                drain()                                       # the last step's gather + merge belongs to the timed region
+                barrier()
+                dt = time.perf_counter() - t0
+                gc.enable()
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            return step, drain, timed
+
+        uprep = det.prepareUpload(frames[rank * nown:(rank + 1) * nown])
+        step, drain, timed = make_runner(Bt, fprep, uprep, rank * nown)
 
         dt = timed(False)
         last = det.lists(fprep)
@@ -419,6 +427,44 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
                     "ranks_agree": bool(torch.equal(lo, hi)),
                     "frame_side": "sharded: each rank quantises %d of the %d frames, NCCL all-gather of the quantized maps, every rank spreads all frames" % (Bt // world, Bt),
                     "collectives_per_step": "1 NCCL group (quantized maps, lane 3, main communicator) + 1 ncclAllGather (match buffers, compute lane, second communicator); the host epilogue runs on the handle's epilogue thread"})
+        # ---- 2-D layout on the same box: T template shards x 2 frame groups (world = 2 T).  Every group is a template-sharded
+        #      step of its own (own NCCL communicator) on half of the step's frames, so the replicated part of the step — spread +
+        #      linearize of every frame on every rank — halves.  Same call sequence, nothing new in the library.
+        if world >= 4 and world % 2 == 0 and Bt % (2 * world) == 0 and not args.no_ts_grid:
+            Tn = world // 2
+            tr, fg = rank % Tn, rank // Tn
+            det.synchronize()
+            det.setTemplateShard(tr, Tn)
+            ids = []
+            for leader in range(0, world, Tn):
+                u = torch.zeros(128, dtype=torch.uint8)
+                if rank == leader:
+                    u = torch.from_numpy(lm.comm_unique_id().copy())
+                u = u.cuda()
+                dist.broadcast(u, leader)
+                ids.append(u.cpu().numpy())
+            det.commInit(ids[fg], tr, Tn)
+            Bg = Bt // 2
+            gframes = frames[fg * Bg:(fg + 1) * Bg]
+            for g in range(G):
+                det.uploadFrames(gframes, g * Bg)
+            fprep2 = det.prepareFetch(Bg, cap=4096 * Bg)
+            nown2 = Bg // Tn
+            uprep2 = det.prepareUpload(gframes[tr * nown2:(tr + 1) * nown2])
+            _, _, timed2 = make_runner(Bg, fprep2, uprep2, tr * nown2)
+            dt2 = timed2(False)
+            last2 = det.lists(fprep2)
+            det.setOption("upload_async", 1)
+            dte2 = timed2(True)
+            det.setOption("upload_async", 0)
+            same = all(tup(last2[i]) == tup(res1[fg * Bg + i]) for i in range(Bg))      # every frame, against this rank's own 1-GPU run
+            okt = torch.tensor([1 if same else 0], device="cuda")
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            v2 = Bt * K / dt2
+            out["grid_2d"] = {"layout": "%d template shards x 2 frame groups" % Tn, "frames_per_step": Bt, "value": v2, "ms_per_step": 1e3 * dt2 / K,
+                              "e2e": {"value": Bt * K / dte2, "unit": "frames/s", "ms_per_step": 1e3 * dte2 / K},
+                              "efficiency_vs_full_set_on_1_gpu": v2 / (world * single["value"]),
+                              "equals_1_gpu_run_on_every_frame_and_rank": bool(int(okt.item()) == 1)}
     # ---- in-run parity bit against the oracle (rank 0; three frames of the last timed step)
     if rank == 0:
         from oracle import oracle as O
@@ -525,14 +571,14 @@ def main():
     bgr0, depth0 = synth.make_frame(0)
     if args.template_cache and os.path.exists(args.template_cache):
         det0 = lm.Detector.read(args.template_cache)
-        det = lm.getDefaultLINEMOD(device=local, max_batch=B)
+        det = lm.getDefaultLINEMOD(device=local, max_batch=max(B, args.slots))
         for cid in det0.classIds():
             for t in range(det0.numTemplates(cid)):
                 det.addSyntheticTemplate(det0.getTemplates(cid, t), cid)
         planted = det.numTemplates("planted")
         det0.close()
     else:
-        det = lm.getDefaultLINEMOD(device=local, max_batch=B)
+        det = lm.getDefaultLINEMOD(device=local, max_batch=max(B, args.slots))
         planted = build_templates_product(det, n_tpl, bgr0, depth0)
         if args.template_cache and rank == 0:
             det.write(args.template_cache)

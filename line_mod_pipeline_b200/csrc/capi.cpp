@@ -135,6 +135,7 @@ void lmb200_destroy(lmb200_handle h) {
     for (auto& mk : h->resident_marks) if (mk.ev) cudaEventDestroy(mk.ev);
     if (h->upload_ev) cudaEventDestroy(h->upload_ev);
     if (h->match_graph) cudaGraphExecDestroy(h->match_graph);
+    for (auto e : h->fork_ev) if (e) cudaEventDestroy(e);
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < LMB200_LANES; ++i) {

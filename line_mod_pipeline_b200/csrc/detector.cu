@@ -501,14 +501,17 @@ static bool chunk_is_contiguous(lmb200_detector* h, const lmb200_image* frames, 
 // FS_SPREAD (spread + response + linearize).  The template-sharded multi-GPU step quantises only the rank's own frame
 // block, all-gathers the quantized maps over NCCL and then spreads every frame (lmb200_match_resident_sharded).
 enum { FS_ALL = 0, FS_QUANTIZE = 1, FS_SPREAD = 2 };
-static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st, int phase = FS_ALL) {
+// only_m >= 0: that modality's chain alone (level order), without the response-sum memset — the single-frame graph runs
+// the modalities as parallel branches (lmb200_match).
+static int run_frame_side(lmb200_detector* h, int first, int count, cudaStream_t st, int phase = FS_ALL, int only_m = -1) {
   NvtxRange nvtx(phase == FS_QUANTIZE ? "lmb200:quantize" : phase == FS_SPREAD ? "lmb200:spread_linearize" : "lmb200:frame_side");
   const int M = h->cfg.num_modalities, L = h->cfg.pyramid_levels;
-  if (phase != FS_QUANTIZE)
+  if (phase != FS_QUANTIZE && only_m < 0)
     CU(cudaMemsetAsync(h->d_resp_sum.as<u32>() + (size_t)first * MAX_MOD, 0, (size_t)count * MAX_MOD * sizeof(u32), st));
   for (int l = 0; l < L; ++l) {
     LevelBuffers& lb = h->levels[l];
     for (int m = 0; m < M; ++m) {
+      if (only_m >= 0 && m != only_m) continue;
       const lmb200_modality& mod = h->cfg.modalities[m];
       u8* q = lb.q[m].as<u8>() + (size_t)first * lb.q_stride;
       if (phase == FS_SPREAD) {
@@ -1325,7 +1328,26 @@ int lmb200_match(lmb200_handle h, const lmb200_image* sources, int n_sources, fl
       lmb200_profile before = h->prof;
       cudaGraph_t g = nullptr;
       CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int r1 = run_frame_side(h, 0, 1, st);
+      // The modalities' chains (ColorGradient: quantise / pyrDown / spread per level; DepthNormal: quantise + spreads)
+      // are independent until the template side: one graph branch each, forked and joined through events, so a single
+      // frame's small grids run side by side instead of one after the other.
+      int r1 = LMB200_OK;
+      const int Mm = h->cfg.num_modalities;
+      if (Mm > 1 && Mm <= 4) {
+        for (auto& e : h->fork_ev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaMemsetAsync(h->d_resp_sum.as<u32>(), 0, MAX_MOD * sizeof(u32), st);
+        cudaEventRecord(h->fork_ev[0], st);
+        for (int m = 1; m < Mm && !r1; ++m) {
+          cudaStream_t sb = h->lanes[1 + m].stream;     // lanes 2..4
+          cudaStreamWaitEvent(sb, h->fork_ev[0], 0);
+          r1 = run_frame_side(h, 0, 1, sb, FS_ALL, m);
+          cudaEventRecord(h->fork_ev[m], sb);
+        }
+        if (!r1) r1 = run_frame_side(h, 0, 1, st, FS_ALL, 0);
+        for (int m = 1; m < Mm; ++m) cudaStreamWaitEvent(st, h->fork_ev[m], 0);
+      } else {
+        r1 = run_frame_side(h, 0, 1, st);
+      }
       int r2 = r1 ? r1 : run_matching(h, 0, 1, threshold, st);
       int r3 = r2 ? r2 : enqueue_result_copies(h, 0, 1, st);
       cudaError_t ce = cudaStreamEndCapture(st, &g);

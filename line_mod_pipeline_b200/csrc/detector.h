@@ -188,6 +188,7 @@ struct lmb200_detector {
   // single-frame CUDA graph (lmb200_match)
   cudaGraphExec_t match_graph = nullptr; long long plan_epoch = 0, graph_epoch = -1; uint32_t graph_thr_bits = 0; bool graph_early_exit = true;
   long long graph_launches[LMB200_K_COUNT] = {0}; bool use_graph = true;
+  cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork / join events of the graph's per-modality branches
   bool upload_async = false;             // lmb200_set_option("upload_async"): lmb200_upload_frames returns without synchronising
   bool early_exit = true;                // lmb200_set_option("early_exit"): measurement runs switch the coarse kernel's exact exit off
   std::vector<lmh::ProfRec> prof_pending;
