@@ -555,7 +555,7 @@ def main():
 
     # ---- measured roofs of this device (and of the shared host path: every rank copies at once)
     roofs = {"l2_read_GBps": microbench(L, K_.MB_L2_READ), "l1_read_GBps": microbench(L, K_.MB_L1_READ),
-             "hbm_read_GBps": microbench(L, K_.MB_HBM_READ), "how": "lmb200_microbench (csrc/microbench.cu): 128-bit loads, best of 8 launches"}
+             "hbm_read_GBps": microbench(L, K_.MB_HBM_READ), "how": "lmb200_microbench (csrc/microbench.cu): 128-bit loads, two kernel forms, best of 8 launches each"}
     if dist is not None:
         dist.barrier()
     h2d = microbench(L, K_.MB_H2D, B * FRAME_BYTES, 8)
@@ -773,7 +773,7 @@ def main():
                     "algorithmic_GBps": kernels[dom]["algorithmic_GBps"], "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"]}
         if same_shape and nj.get("l2_bytes_per_launch"):
             roofline["achieved"] = round(nj["l2_bytes_per_launch"] / t_launch / 1e9, 1)
-            roofline["achieved_how"] = "L2->L1 bytes of one launch (ncu lts sectors, profiles/ncu_traffic.json, same launch shape) / live CUDA-event time"
+            roofline["achieved_how"] = "L2->L1 read bytes + L1->L2 write bytes of one launch (ncu l1tex__m_xbar2l1tex_read_bytes + lts write sectors, profiles/ncu_traffic.json, same launch shape) / live CUDA-event time"
         else:
             roofline["achieved"] = kernels[dom]["requested_GBps"]
             roofline["achieved_how"] = "bytes the kernel requested (counted on the device, after the early exit) / live CUDA-event time: an UPPER bound of its L2 traffic (part of it hits L1)"

@@ -16,7 +16,7 @@ KEEP = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elap
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
-        "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sectors_srcunit_tex_op_write.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum",
         "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
 
@@ -54,7 +54,9 @@ def main():
         summary[name] = d
         if "dram__bytes_read.sum" in d:
             traffic[name] = {"dram_bytes_per_launch": d["dram__bytes_read.sum"] + d.get("dram__bytes_write.sum", 0.0),
-                             "l2_bytes_per_launch": 32.0 * (d.get("lts__t_sectors_op_read.sum", 0.0) + d.get("lts__t_sectors_op_write.sum", 0.0)),
+                             # L2 -> L1 read bytes (crossbar into the SMs) + L1 -> L2 write sectors: what the kernel moved through L2
+                             "l2_bytes_per_launch": d.get("l1tex__m_xbar2l1tex_read_bytes.sum", 32.0 * d.get("lts__t_sectors_srcunit_tex_op_read.sum", 0.0))
+                                                    + 32.0 * d.get("lts__t_sectors_srcunit_tex_op_write.sum", 0.0),
                              "l1_sector_bytes_per_launch": 32.0 * d.get("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", 0.0)}
     json.dump(summary, open(out, "w"), indent=1)
     print("wrote", out, "kernels:", list(summary))
