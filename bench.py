@@ -276,6 +276,8 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
     thr = args.threshold
     G = max(2, min(4, args.ts_groups))                    # slot groups: G-1 steps in flight on the GPU while the host fetches the oldest
     det = lm.getDefaultLINEMOD(device=local, max_batch=G * Bt)
+    if world > 1:
+        det.setOption("host_threads", max(2, len(os.sched_getaffinity(0)) // world))
     bgr0, depth0 = synth.make_frame(0)
     planted = build_templates_sharded_set(det, args.ts_templates, bgr0, depth0)
     L = lm.capi.lib()
@@ -583,6 +585,8 @@ def main():
         if args.template_cache and rank == 0:
             det.write(args.template_cache)
 
+    if world > 1:   # one process per GPU: the host epilogue threads of all ranks share the box's cores
+        det.setOption("host_threads", max(2, len(os.sched_getaffinity(0)) // world))
     # ---- frames: pinned host memory (e2e) + resident copies (value); ranks stream disjoint frames
     nb, nd = ROWS * COLS * 3, ROWS * COLS * 2
     ptr = C.c_void_p()
@@ -691,6 +695,9 @@ def main():
                "d2h_bytes_per_step": B * (32 + 1024 * 16), "ms_per_step": 1e3 * dt / K,
                "mode": "lmb200_match_batch_submit/_collect, step k+1 submitted before step k is collected",
                "h2d_GBps_all_gpus": h2d_GBps, "frac_of_h2d_roof": h2d_GBps / roofs["h2d_GBps_all_gpus"] if roofs["h2d_GBps_all_gpus"] else None,
+               # the timed region ends with the slowest rank, and the ranks' host links are not equal (NUMA / PCIe topology):
+               # the same figure against N x the slowest link measured when all ranks copy at once
+               "frac_of_slowest_link_roof": h2d_GBps / (world * roofs["h2d_GBps_per_gpu_min"]) if roofs.get("h2d_GBps_per_gpu_min") else None,
                "blocking_call": {"value": B * K * world / dt_sync, "ms_per_step": 1e3 * dt_sync / K}}
         # single-frame latency of the reference-facing call (configs[1] literally: one frame, host buffers in, sorted matches
         # out): lmb200_match, whose kernel sequence is replayed as a CUDA graph; the blocking batch call with one frame beside it

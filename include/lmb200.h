@@ -318,6 +318,16 @@ typedef struct {
  * McIlroy's quicksort adversary (template ids are overwritten; forces the depth limit).  Both outputs hold n records. */
 int lmb200_debug_sort_check(const lmb200_match_rec* in, size_t n, int mode, lmb200_match_rec* out_emulated, lmb200_match_rec* out_std);
 
+/* Test hook for the device epilogue of the template-sharded step (csrc/kernels_epilogue.cu) on ONE GPU: `gathered` is what
+ * the match all-gather leaves in device memory — per rank [2*frames header records][gcap match records], a record being
+ * four 32-bit words {global template index, x, y, similarity as float bits}; header 2f = {count, flags, offset into the
+ * rank's record area, 0}, header 2f+1 = counters.  pos_of_g (nullable: rank-ordered concatenation) maps a global template
+ * index to its selection position.  Returns the finished records (frame f at hdr[8f+1], hdr[8f+0] of them) and the
+ * per-frame header words {n_final, offset, flags, n_in}, {counters of `rank`}. */
+int lmb200_debug_shard_epilogue(const int32_t* gathered, int world, int rank, int frames, int gcap, const int32_t* pos_of_g,
+                                const int32_t* g_class, const int32_t* g_tid, int ntpl, lmb200_match_rec* out, size_t out_cap,
+                                int32_t* hdr);
+
 /* Measurement knobs.  "early_exit" (default 1): 0 switches off the coarse kernel's exact early exit (results are
  * identical either way; the bench reports both so the workload dependence of the exit is visible).
  * "upload_async" (default 0): 1 makes lmb200_upload_frames return without synchronising (pinned host frames that stay
@@ -327,6 +337,8 @@ int lmb200_debug_sort_check(const lmb200_match_rec* in, size_t n, int mode, lmb2
  * "shard_overlap" (default 1): lmb200_match_resident_sharded runs its quantisers and the all-gather of the quantized maps
  * (1), or those and spread + linearize (2), on a high-priority lane of their own, overlapping the template side of the
  * previous step (0: everything on the compute lane).
+ * "host_threads" (default 8): threads the host epilogue (std::sort / std::unique per frame) of one fetch / collect may use;
+ * with one process per GPU set it to (host cores / processes).
  * "shard_device_epilogue" (default 1): the std::sort + std::unique of a template-sharded step run on the device
  * (csrc/kernels_epilogue.cu, sequence-identical to libstdc++'s); 0: on the handle's host epilogue thread. */
 int lmb200_set_option(lmb200_handle h, const char* name, int value);

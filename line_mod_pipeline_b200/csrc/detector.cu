@@ -792,7 +792,8 @@ static void drain_tickets(lmb200_detector* h) {
 }
 
 // Host epilogue of n independent frames (record -> Match, std::sort, std::unique) on a few threads.
-static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Cand>>& raws, std::vector<std::vector<Match>>& outs, unsigned max_threads = 8u) {
+static void finalize_frames(lmb200_detector* h, const std::vector<std::vector<Cand>>& raws, std::vector<std::vector<Match>>& outs, unsigned max_threads = 0u) {
+  if (max_threads == 0u) max_threads = (unsigned)std::max(1, h->host_threads);
   NvtxRange nvtx("lmb200:epilogue(std::sort, std::unique)");
   const int n = (int)raws.size();
   outs.resize(n);
@@ -1713,6 +1714,7 @@ int lmb200_set_option(lmb200_handle h, const char* name, int value) {
   if (std::strcmp(name, "upload_async") == 0) { h->upload_async = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "shard_overlap") == 0) { h->shard_overlap = value < 0 ? 0 : value > 2 ? 2 : value; return LMB200_OK; }
+  if (std::strcmp(name, "host_threads") == 0) { h->host_threads = value < 1 ? 1 : value > 64 ? 64 : value; return LMB200_OK; }
   if (std::strcmp(name, "shard_device_epilogue") == 0) { h->shard_device_epilogue = value != 0; return LMB200_OK; }
   return set_error(h, LMB200_E_INVALID, std::string("unknown option ") + name);
 }
@@ -2235,7 +2237,7 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
   std::vector<lmb200_match_rec> recs; std::vector<size_t> offs;
   long long nc = 0, nm = 0;
   double t_reorder = 0, t_sort = 0;
-  merge_gathered(h, h->h_gather, gcap, count, 8u, recs, offs, &nc, &nm, &t_reorder, &t_sort);
+  merge_gathered(h, h->h_gather, gcap, count, (unsigned)std::max(1, h->host_threads), recs, offs, &nc, &nm, &t_reorder, &t_sort);
   h->prof.candidates += nc; h->prof.matches += nm;
   const int status = emit_lists(recs, offs);
   if (trace && h->comm_rank == 0)

@@ -13,6 +13,9 @@
 // Every rank finishes every frame itself: ~25 k records per 128-frame step are nothing next to a second collective plus
 // a host sort on the critical path (round 1: ~3.6 ms per step; this kernel: well under 0.3 ms on a lane of its own).
 // Frames with more than EPI_SORT_CAP records, and steps whose headers carry an overflow flag, are flagged for the host path.
+#include <cstring>
+
+#include "../../include/lmb200.h"
 #include "kernels.cuh"
 #include "sort_emul.h"
 
@@ -163,3 +166,53 @@ void launch_shard_epilogue(const EpilogueArgs& a, cudaStream_t st) {
 }
 
 }  // namespace lmk
+
+// Test hook (include/lmb200.h): runs shard_epilogue_kernel on host-made "gathered" buffers, through the same pinned,
+// device-mapped result area as the product path, so the single-GPU suite covers the device epilogue of the sharded step.
+extern "C" int lmb200_debug_shard_epilogue(const int32_t* gathered, int world, int rank, int frames, int gcap, const int32_t* pos_of_g,
+                                           const int32_t* g_class, const int32_t* g_tid, int ntpl, lmb200_match_rec* out, size_t out_cap,
+                                           int32_t* hdr) {
+  using namespace lmk;
+  if (!gathered || !g_class || !g_tid || !out || !hdr || world < 1 || world > EPI_MAX_WORLD || rank < 0 || rank >= world || frames < 1 ||
+      gcap < 0 || ntpl < 1 || out_cap < 1 || out_cap > 0x7fffffff)
+    return LMB200_E_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return LMB200_E_NODEVICE; }
+  const size_t recs = (size_t)world * ((size_t)2 * frames + gcap);
+  Cand* d_g = nullptr; int *d_pos = nullptr, *d_cls = nullptr, *d_tid = nullptr; EpiMatch* d_out = nullptr;
+  EpiMatch* h_out = nullptr; int4* h_hdr = nullptr;
+  int rc = LMB200_OK;
+  auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == LMB200_OK) rc = LMB200_E_CUDA; return e == cudaSuccess; };
+  ok(cudaMalloc(&d_g, recs * sizeof(Cand)));
+  ok(cudaMalloc(&d_cls, (size_t)ntpl * 4)); ok(cudaMalloc(&d_tid, (size_t)ntpl * 4));
+  if (pos_of_g) ok(cudaMalloc(&d_pos, (size_t)ntpl * 4));
+  ok(cudaMalloc(&d_out, out_cap * sizeof(EpiMatch)));
+  ok(cudaHostAlloc((void**)&h_out, out_cap * sizeof(EpiMatch), cudaHostAllocMapped));
+  ok(cudaHostAlloc((void**)&h_hdr, (size_t)2 * frames * sizeof(int4), cudaHostAllocMapped));
+  if (rc == LMB200_OK) {
+    ok(cudaMemcpy(d_g, gathered, recs * sizeof(Cand), cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(d_cls, g_class, (size_t)ntpl * 4, cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(d_tid, g_tid, (size_t)ntpl * 4, cudaMemcpyHostToDevice));
+    if (pos_of_g) ok(cudaMemcpy(d_pos, pos_of_g, (size_t)ntpl * 4, cudaMemcpyHostToDevice));
+    std::memset(h_hdr, 0xFF, (size_t)2 * frames * sizeof(int4));
+    EpilogueArgs ea;
+    ea.gathered = d_g; ea.world = world; ea.rank = rank; ea.frames = frames; ea.gcap = gcap;
+    ea.pos_of_g = d_pos; ea.g_class = d_cls; ea.g_tid = d_tid;
+    ea.out_dev = d_out; ea.out_cap = (int)out_cap;
+    void* dp = nullptr;
+    ok(cudaHostGetDevicePointer(&dp, h_out, 0)); ea.out_host = (EpiMatch*)dp;
+    ok(cudaHostGetDevicePointer(&dp, h_hdr, 0)); ea.hdr = (int4*)dp;
+    if (rc == LMB200_OK) {
+      launch_shard_epilogue(ea, 0);
+      ok(cudaDeviceSynchronize());
+    }
+    if (rc == LMB200_OK) {
+      std::memcpy(out, h_out, out_cap * sizeof(EpiMatch));
+      std::memcpy(hdr, h_hdr, (size_t)2 * frames * sizeof(int4));
+    }
+  }
+  cudaFree(d_g); cudaFree(d_cls); cudaFree(d_tid); cudaFree(d_pos); cudaFree(d_out);
+  if (h_out) cudaFreeHost(h_out);
+  if (h_hdr) cudaFreeHost(h_hdr);
+  return rc;
+}

@@ -270,3 +270,30 @@ def test_device_sort_restatement_equals_std_sort():
     for n in (17, 100, 1000, 5000):
         s = check(n, 2)                        # McIlroy's adversary: the depth limit is hit, heap-sort fallback inside std::sort
         assert list(s["template_id"]) == sorted(s["template_id"])
+
+
+def test_python_mirror_matches_the_header():
+    """The ctypes mirror's profile struct and kernel-family names follow include/lmb200.h's enum (a mismatch would shift
+    every counter read through lmb200_get_profile)."""
+    hdr = open(os.path.join(ROOT, "include", "lmb200.h")).read()
+    body = hdr[hdr.index("LMB200_K_UPLOAD"):hdr.index("LMB200_K_COUNT")]
+    names = re.findall(r"LMB200_K_([A-Z_]+)", "LMB200_K_UPLOAD" + body[len("LMB200_K_UPLOAD"):])
+    assert [n.lower() for n in names] == K.K_NAMES
+    assert C.sizeof(K.Profile) == 8 * (2 * len(K.K_NAMES) + 6)
+
+
+def test_match_array_reads_like_the_reference_match():
+    """Per-frame results: structured arrays whose fields read as attributes on the array and on its elements (what
+    np.recarray offered at 20 us per slice)."""
+    from line_mod_pipeline_b200.detector import _split, MatchArray
+    out = np.zeros(10, lm.MATCH_DTYPE)
+    out["x"] = np.arange(10); out["similarity"] = 90.0 - np.arange(10); out["template_id"] = 7
+    offs = (C.c_size_t * 4)(0, 3, 3, 10)
+    lists = _split(out, offs, 3)
+    assert [len(l) for l in lists] == [3, 0, 7] and all(isinstance(l, MatchArray) for l in lists)
+    assert list(lists[2].x) == list(range(3, 10)) and float(lists[0].similarity.sum()) == 90.0 + 89.0 + 88.0
+    assert lists[2][0].x == 3 and lists[2][0].template_id == 7 and [int(m.x) for m in lists[0]] == [0, 1, 2]
+    out["x"] = -1                                  # _split copied: the lists do not alias the reusable call buffer
+    assert lists[0][0].x == 0
+    with pytest.raises(AttributeError):
+        lists[0].no_such_field

@@ -3,6 +3,7 @@
 Everything here needs a B200 (`-m gpu`).  Sizes are the BASELINE.json configs where the oracle
 finishes in seconds, plus edge cases (ragged geometry, empty sets, malformed templates, masks).
 """
+import ctypes as C
 import hashlib
 import numpy as np
 import pytest
@@ -669,3 +670,107 @@ def test_postmatch_color_check_equals_oracle_and_cv2(fixture_frame):
         assert checked >= 5
     with pytest.raises(lm.LinemodError):
         lm.getDefaultLINEMOD().postmatchColor(res[:1], (0, 0, 0), (1, 1, 1))   # no frame resident
+
+
+def _epilogue_case(rng, world, frames, max_per_rank, ntpl, interleaved, sims, tid_mod, gcap_extra=0):
+    """Builds what the match all-gather leaves in device memory for a synthetic sharded step and the expected finished
+    lists: generation order (by selection position for interleaved shards, rank-ordered concatenation otherwise), then the
+    library's own host epilogue (lmb200_merge_matches = std::sort + std::unique)."""
+    L = lm.capi.lib()
+    MR = lm.capi.MatchRec
+    perm = rng.permutation(ntpl).astype(np.int32)              # selection order: position p holds global template perm[p]
+    pos_of_g = np.empty(ntpl, np.int32); pos_of_g[perm] = np.arange(ntpl, dtype=np.int32)
+    g_class = (np.arange(ntpl) % 3).astype(np.int32)
+    g_tid = (np.arange(ntpl) % tid_mod).astype(np.int32)
+    lists = [[None] * frames for _ in range(world)]
+    for r in range(world):
+        # templates of rank r in its own generation order
+        mine = perm[r::world] if interleaved else perm[r * (ntpl // world):(r + 1) * (ntpl // world)]
+        if not interleaved:
+            mine = np.sort(mine)                               # contiguous shards: global index order within the rank is irrelevant to the kernel
+        for f in range(frames):
+            n = int(rng.integers(0, max_per_rank + 1)) if rng.random() > 0.15 else 0
+            k = np.sort(rng.integers(0, len(mine), n))         # several records per template, templates in generation order
+            rec = np.zeros((n, 4), np.int32)
+            rec[:, 0] = mine[k]
+            rec[:, 1] = rng.integers(0, 8, n) * 5; rec[:, 2] = rng.integers(0, 6, n) * 5   # few positions: exact duplicates happen
+            rec[:, 3] = (80.0 + 0.5 * rng.integers(0, sims, n)).astype(np.float32).view(np.int32)
+            lists[r][f] = rec
+    gcap = max(1, max(sum(len(lists[r][f]) for f in range(frames)) for r in range(world))) + gcap_extra
+    stride = 2 * frames + gcap
+    G = np.zeros((world, stride, 4), np.int32)
+    for r in range(world):
+        off = 0
+        for f in range(frames):
+            n = len(lists[r][f])
+            G[r, 2 * f] = (n, 0, off, 0)
+            G[r, 2 * f + 1] = (100 * r + f, 0, 7 * r + f, 0)    # counters: must come back for `rank`
+            G[r, 2 * frames + off: 2 * frames + off + n] = lists[r][f]
+            off += n
+    want = []
+    for f in range(frames):
+        cat = np.concatenate([lists[r][f] for r in range(world)]) if world else np.zeros((0, 4), np.int32)
+        if interleaved and len(cat):
+            cat = cat[np.argsort(pos_of_g[cat[:, 0]], kind="stable")]
+        m = np.zeros(len(cat), lm.MATCH_DTYPE)
+        m["x"], m["y"], m["similarity"] = cat[:, 1], cat[:, 2], cat[:, 3].view(np.float32)
+        m["class_index"], m["template_id"] = g_class[cat[:, 0]], g_tid[cat[:, 0]]
+        out = np.zeros(max(1, len(m)), lm.MATCH_DTYPE)
+        n_out = C.c_size_t(0)
+        parts = (C.POINTER(MR) * 1)(m.ctypes.data_as(C.POINTER(MR)))
+        counts = (C.c_size_t * 1)(len(m))
+        rc = L.lmb200_merge_matches(parts, counts, 1, out.ctypes.data_as(C.POINTER(MR)), len(out), C.byref(n_out))
+        assert rc == 0
+        want.append((len(cat), out[:n_out.value].copy()))
+    return G, gcap, pos_of_g if interleaved else None, g_class, g_tid, want
+
+
+@pytest.mark.parametrize("world,frames,max_per_rank,interleaved", [(1, 3, 200, False), (2, 5, 300, True), (3, 4, 150, True),
+                                                                   (8, 16, 120, True), (8, 2, 500, True), (8, 3, 1300, True), (4, 6, 100, False)])
+def test_device_epilogue_of_the_sharded_step(world, frames, max_per_rank, interleaved):
+    """shard_epilogue_kernel (generation-order merge + libstdc++'s std::sort + std::unique on the device) against the host
+    epilogue, on one GPU: ties on (similarity, template_id) everywhere, exact duplicates, empty frames, 1-8 ranks."""
+    L = lm.capi.lib()
+    MR = lm.capi.MatchRec
+    rng = np.random.default_rng(100 * world + frames)
+    ntpl = 64 * world
+    G, gcap, pos, g_class, g_tid, want = _epilogue_case(rng, world, frames, max_per_rank, ntpl, interleaved, sims=6, tid_mod=7)
+    total = sum(n for n, _ in want)
+    out = np.zeros(max(1, total), lm.MATCH_DTYPE)
+    hdr = np.zeros((2 * frames, 4), np.int32)
+    rank = world - 1
+    rc = L.lmb200_debug_shard_epilogue(G.ctypes.data, world, rank, frames, gcap, pos.ctypes.data if pos is not None else None,
+                                       g_class.ctypes.data, g_tid.ctypes.data, ntpl, out.ctypes.data_as(C.POINTER(MR)), len(out), hdr.ctypes.data)
+    assert rc == 0
+    off = 0
+    for f in range(frames):
+        n_in, fin = want[f]
+        n_final, offset, flags, n_seen = (int(v) for v in hdr[2 * f])
+        if n_in > 4096:
+            assert flags & 4, "frame %d: %d records must be flagged for the host path" % (f, n_in)
+        else:
+            assert flags == 0 and n_seen == n_in and offset == off, (f, flags, n_seen, n_in, offset, off)
+            got = out[offset:offset + n_final]
+            assert n_final == len(fin) and got.tobytes() == fin.tobytes(), "frame %d: device epilogue differs from std::sort + std::unique" % f
+            assert tuple(int(v) for v in hdr[2 * f + 1]) == (100 * rank + f, 0, 7 * rank + f, 0)
+        off += n_in
+
+
+def test_device_epilogue_flags():
+    """A store-overflow / too-small flag in any rank's header, and an output area that is too small, must flag the frame."""
+    L = lm.capi.lib()
+    MR = lm.capi.MatchRec
+    rng = np.random.default_rng(5)
+    G, gcap, pos, g_class, g_tid, want = _epilogue_case(rng, 2, 3, 50, 128, True, sims=4, tid_mod=5)
+    G[1, 2 * 1, 1] = 2                                          # rank 1 says: my record area was too small for frame 1
+    out = np.zeros(4096, lm.MATCH_DTYPE)
+    hdr = np.zeros((6, 4), np.int32)
+    assert L.lmb200_debug_shard_epilogue(G.ctypes.data, 2, 0, 3, gcap, pos.ctypes.data, g_class.ctypes.data, g_tid.ctypes.data, 128,
+                                         out.ctypes.data_as(C.POINTER(MR)), len(out), hdr.ctypes.data) == 0
+    assert hdr[2, 2] & 2 and hdr[0, 2] == 0 and hdr[4, 2] == 0
+    G[1, 2 * 1, 1] = 0
+    small = max(1, want[0][0])                                  # room for frame 0 only
+    out = np.zeros(small, lm.MATCH_DTYPE)
+    assert L.lmb200_debug_shard_epilogue(G.ctypes.data, 2, 0, 3, gcap, pos.ctypes.data, g_class.ctypes.data, g_tid.ctypes.data, 128,
+                                         out.ctypes.data_as(C.POINTER(MR)), len(out), hdr.ctypes.data) == 0
+    assert hdr[0, 2] == 0 and (want[1][0] == 0 or hdr[2, 2] & 8)
