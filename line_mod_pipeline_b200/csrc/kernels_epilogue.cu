@@ -159,9 +159,8 @@ __global__ void __launch_bounds__(256) shard_epilogue_kernel(EpilogueArgs a) {
 }
 
 void launch_shard_epilogue(const EpilogueArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
-  const size_t smem = (size_t)EPI_SORT_CAP * 16;
-  if (!attr_set) { cudaFuncSetAttribute(shard_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  const size_t smem = (size_t)EPI_SORT_CAP * 16;   // 64 KB: above the default limit, opted in per device (the attribute is per context)
+  cudaFuncSetAttribute(shard_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (a.frames > 0) shard_epilogue_kernel<<<a.frames, 256, smem, st>>>(a);
 }
 

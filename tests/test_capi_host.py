@@ -60,6 +60,12 @@ def test_detector_surface_host_side():
     assert e.value.code == K.E_FEATURES
     with pytest.raises(lm.LinemodError):
         d.addSyntheticTemplate(tps[0][:3], "x")          # wrong pyramid size
+    for opt, val in (("early_exit", 0), ("upload_async", 1), ("cuda_graph", 0), ("shard_overlap", 2), ("shard_device_epilogue", 0),
+                     ("host_threads", 3)):
+        d.setOption(opt, val)                            # measurement / deployment knobs are host state: no device needed
+    with pytest.raises(lm.LinemodError):
+        d.setOption("no_such_option", 1)
+    d.close()                                            # a handle that never touched the device (no epilogue thread to join)
 
 
 def test_tables():
