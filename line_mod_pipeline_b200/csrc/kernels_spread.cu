@@ -64,9 +64,10 @@ __device__ __forceinline__ void transpose4(u32 r0, u32 r1, u32 r2, u32 r3, u32& 
 //   (independent loads, all in flight together; round 1's row-at-a-time staging spent 41 % of the kernel's instructions
 //   and most of its stalls here), keeps the last T-1 rows in registers and stores the vertical OR.
 // Phase B — horizontal OR on words (funnel shifts), results held in registers across the barrier and written in place.
-// FAST: own-level map, 4-byte aligned rows, no mask.  Otherwise load_q_word (decimated reads, masks, ragged edges).
-// All threads of the CTA call it; ends with a barrier.
-template <int T, int SEG, int MAXV, bool FAST>
+// FAST = 1: own-level map, 4-byte aligned rows, no mask.  FAST = 2: the 2x nearest-neighbour decimation of a finer map read
+// in place (DepthNormal level 1: pixels gx..gx+3 are the even bytes of ONE aligned 8-byte load of the finer row 2*gy).
+// FAST = 0: load_q_word (other decimations, masks, ragged edges).  All threads of the CTA call it; ends with a barrier.
+template <int T, int SEG, int MAXV, int FAST>
 __device__ __forceinline__ void stage_spread(const SpreadArgs& a, const u8* __restrict__ qf, const u8* __restrict__ mf, bool vec,
                                              int y0, int x0, int NV, int RW, int PW, u32* band, int tid, int nthr) {
   const int rows = a.g.rows, cols = a.g.cols;
@@ -75,13 +76,17 @@ __device__ __forceinline__ void stage_spread(const SpreadArgs& a, const u8* __re
     const int sg = it / RW, w = it - sg * RW;
     const int r0 = sg * SEG, gx = x0 + 4 * w;
     const bool colok = gx < cols;                       // FAST: cols % 4 == 0 and gx % 4 == 0, so the whole word is inside
-    const u8* p = qf + (size_t)(y0 + r0) * a.q_pitch + gx;
+    const u8* p = qf + (size_t)(y0 + r0) * a.q_pitch * (FAST == 2 ? 2 : 1) + (size_t)gx * (FAST == 2 ? 2 : 1);
     u32 in[SEG + T - 1];
 #pragma unroll
     for (int k = 0; k < SEG + T - 1; ++k) {
       const int gy = y0 + r0 + k;
-      if (FAST) in[k] = (colok && gy < rows) ? __ldg(reinterpret_cast<const u32*>(p + (size_t)k * a.q_pitch)) : 0u;
-      else in[k] = load_q_word(a, qf, mf, gy, gx, vec);
+      if (FAST == 1) in[k] = (colok && gy < rows) ? __ldg(reinterpret_cast<const u32*>(p + (size_t)k * a.q_pitch)) : 0u;
+      else if (FAST == 2) {
+        uint2 v = make_uint2(0u, 0u);
+        if (colok && gy < rows) v = __ldg(reinterpret_cast<const uint2*>(p + (size_t)k * 2 * a.q_pitch));
+        in[k] = __byte_perm(v.x, v.y, 0x6420);
+      } else in[k] = load_q_word(a, qf, mf, gy, gx, vec);
     }
 #pragma unroll
     for (int j = 0; j < SEG; ++j) {
@@ -136,7 +141,7 @@ struct StripCfg {
   static constexpr size_t SMEM = (size_t)NV * RW * 4 + 256 * sizeof(uint2);
 };
 
-template <int T, int R, bool FAST>
+template <int T, int R, int FAST>
 __global__ void __launch_bounds__(256, T >= 16 ? 2 : 5) spread_strip_kernel(SpreadArgs a) {
   typedef StripCfg<T, R> C;
   extern __shared__ __align__(16) u8 sp_smem[];
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(256, T >= 16 ? 2 : 5) spread_strip_kernel(Spre
 // Small tiles on purpose: the coarsest level is 1/4 of the pixels and 1/16 of the output bytes of the level below, so
 // only many short CTAs fill 148 SMs (5 tiles per frame left the kernel at 0.36 waves and 25 % of the warp slots).
 constexpr int FLAT_MAXV = 8;       // phase-B words per thread the launcher's tiles need at most
-template <int T, bool FAST>
+template <int T, int FAST>
 __global__ void __launch_bounds__(256) spread_flat_kernel(SpreadArgs a, int R, int CW) {
   extern __shared__ __align__(16) u8 sp_smem[];
   uint2* tab = reinterpret_cast<uint2*>(sp_smem);
@@ -252,11 +257,15 @@ __global__ void __launch_bounds__(256) spread_flat_kernel(SpreadArgs a, int R, i
   }
 }
 
-// FAST path of stage_spread: the map is this level's own (no decimated read), unmasked, and every row is a whole number of
-// aligned words
-static bool fast_loads(const SpreadArgs& a) {
-  return a.q_step == 1 && !a.mask && (a.q_pitch & 3) == 0 && (a.g.cols & 3) == 0 && (a.q_stride & 3) == 0 &&
-         (reinterpret_cast<size_t>(a.q) & 3) == 0;
+// FAST paths of stage_spread (0: none).  1: the map is this level's own, unmasked, every row a whole number of aligned
+// words.  2: the map is the finer level's, decimated by two in place: rows 2*gy, aligned 8-byte loads.
+static int fast_loads(const SpreadArgs& a) {
+  if (a.mask || (a.g.cols & 3) != 0) return 0;
+  if (a.q_step == 1 && (a.q_pitch & 3) == 0 && (a.q_stride & 3) == 0 && (reinterpret_cast<size_t>(a.q) & 3) == 0) return 1;
+  if (a.q_step == 2 && (a.q_pitch & 7) == 0 && (a.q_stride & 7) == 0 && (reinterpret_cast<size_t>(a.q) & 7) == 0 &&
+      a.q_pitch >= 2 * a.g.cols)
+    return 2;
+  return 0;
 }
 
 template <int T, int R>
@@ -264,8 +273,11 @@ void launch_strip(const SpreadArgs& a, int frames, cudaStream_t st) {
   typedef StripCfg<T, R> C;
   static_assert(C::SMEM <= 48 * 1024, "strip tile exceeds the default dynamic shared memory");
   dim3 grid(a.g.strips, (a.g.H + R - 1) / R, frames);
-  if (fast_loads(a)) spread_strip_kernel<T, R, true><<<grid, 256, C::SMEM, st>>>(a);
-  else spread_strip_kernel<T, R, false><<<grid, 256, C::SMEM, st>>>(a);
+  switch (fast_loads(a)) {
+    case 1: spread_strip_kernel<T, R, 1><<<grid, 256, C::SMEM, st>>>(a); break;
+    case 2: spread_strip_kernel<T, R, 2><<<grid, 256, C::SMEM, st>>>(a); break;
+    default: spread_strip_kernel<T, R, 0><<<grid, 256, C::SMEM, st>>>(a);
+  }
 }
 
 template <int T>
@@ -278,12 +290,16 @@ void launch_flat(const SpreadArgs& a, int frames, cudaStream_t st) {
   const int RWmax = ((CW * T + T - 1 + 3) / 4) | 1;
   const size_t smem = (size_t)(R * T) * RWmax * 4 + 256 * sizeof(uint2);
   dim3 grid((W + CW - 1) / CW, (H + R - 1) / R, frames);
-  if (fast_loads(a)) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spread_flat_kernel<T, true><<<grid, 256, smem, st>>>(a, R, CW);
+  const int fast = fast_loads(a);
+  if (fast == 1) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spread_flat_kernel<T, 1><<<grid, 256, smem, st>>>(a, R, CW);
+  } else if (fast == 2) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spread_flat_kernel<T, 2><<<grid, 256, smem, st>>>(a, R, CW);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spread_flat_kernel<T, false><<<grid, 256, smem, st>>>(a, R, CW);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(spread_flat_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spread_flat_kernel<T, 0><<<grid, 256, smem, st>>>(a, R, CW);
   }
 }
 
