@@ -210,9 +210,11 @@ __device__ __forceinline__ void realign_add(const uint4& A, const uint4& B, u32 
 // One word-shift bucket: its (padded) row count n is a multiple of 3, so the loop is groups of 3 rows only:
 // all loads first (6 x LDG.128 in flight per lane), then realign + one 3-input add per word (3*4 = 12 fits a
 // nibble), then the spill into byte sums.
+// CW_SHFL (experiment, -DCW_SHFL): a lane's second chunk is its right neighbour's first one, so it is taken with four
+// shuffles instead of a second LDG.128; only the last active lane loads it.  act = ballot of the lanes inside this call.
 template <int WS, bool SAFE>
 __device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const uint2* __restrict__ lst, int k0, int n,
-                                             int pos0, int P, u32 per_label, NibAcc& acc) {
+                                             int pos0, int P, u32 per_label, NibAcc& acc, u32 act = 0xffffffffu, bool last = false) {
   for (int k = k0; k < k0 + n; k += 3) {
     uint2 e[3];  // (chunk byte offset, funnel shift) straight from the plan: no per-row address arithmetic
     uint4 A[3], B[3];
@@ -221,7 +223,14 @@ __device__ __forceinline__ void accum_bucket(const u8* __restrict__ lmb, const u
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const uint4* p = reinterpret_cast<const uint4*>(lmb + e[j].x);
+#ifdef CW_SHFL
+      A[j] = __ldg(p);
+      B[j].x = __shfl_down_sync(act, A[j].x, 1); B[j].y = __shfl_down_sync(act, A[j].y, 1);
+      B[j].z = __shfl_down_sync(act, A[j].z, 1); B[j].w = __shfl_down_sync(act, A[j].w, 1);
+      if (last) B[j] = __ldg(p + 1);
+#else
       A[j] = __ldg(p); B[j] = __ldg(p + 1);
+#endif
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -297,12 +306,22 @@ __device__ __forceinline__ int coarse_sweep(const CoarseCtx& cx, const u8* const
       const u32 bk = cx.hdr.bkt(m);
       const int n0 = bk & 255, n1 = (bk >> 8) & 255, n2 = (bk >> 16) & 255, n3 = bk >> 24;
       const uint2* lst = cx.lst + m * COARSE_SLOTS;
-      cx.chunks += 2u * (u32)(n0 + n1 + n2 + n3) * (u32)__popc(__ballot_sync(0xffffffffu, rem > 0));
+      const u32 act_m = __ballot_sync(0xffffffffu, rem > 0);   // a prefix of the warp: rem falls with the lane
+      cx.chunks += 2u * (u32)(n0 + n1 + n2 + n3) * (u32)__popc(act_m);
       if (rem > 0) {  // lanes past template_positions sit the modality out (one branch, not one per group)
+#ifdef CW_SHFL
+        const u32 act = act_m;
+        const bool last = lane == 31 - __clz(act);
+        accum_bucket<0, SAFE>(lmb, lst, 0, n0, pos0, P, cx.per_label, acc, act, last);
+        accum_bucket<1, SAFE>(lmb, lst, n0, n1, pos0, P, cx.per_label, acc, act, last);
+        accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, pos0, P, cx.per_label, acc, act, last);
+        accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, pos0, P, cx.per_label, acc, act, last);
+#else
         accum_bucket<0, SAFE>(lmb, lst, 0, n0, pos0, P, cx.per_label, acc);
         accum_bucket<1, SAFE>(lmb, lst, n0, n1, pos0, P, cx.per_label, acc);
         accum_bucket<2, SAFE>(lmb, lst, n0 + n1, n2, pos0, P, cx.per_label, acc);
         accum_bucket<3, SAFE>(lmb, lst, n0 + n1 + n2, n3, pos0, P, cx.per_label, acc);
+#endif
       }
       if (SAFE && !tail_once && rem > 0 && rem < 32) acc.mask_tail(rem);  // at most one lane per modality: the row tail
 #pragma unroll
