@@ -337,6 +337,8 @@ int lmb200_debug_shard_epilogue(const int32_t* gathered, int world, int rank, in
  * "shard_overlap" (default 1): lmb200_match_resident_sharded runs its quantisers and the all-gather of the quantized maps
  * (1), or those and spread + linearize (2), on a high-priority lane of their own, overlapping the template side of the
  * previous step (0: everything on the compute lane).
+ * "resident_overlap" (default 1): lmb200_match_resident runs the frame side of a step (>= 8 frames) on the high-priority
+ * frame lane and the template side on the compute lane; consecutive calls on different slot ranges overlap.
  * "host_threads" (default 8): threads the host epilogue (std::sort / std::unique per frame) of one fetch / collect may use;
  * with one process per GPU set it to (host cores / processes).
  * "shard_device_epilogue" (default 1): the std::sort + std::unique of a template-sharded step run on the device

@@ -136,6 +136,7 @@ void lmb200_destroy(lmb200_handle h) {
     if (h->upload_ev) cudaEventDestroy(h->upload_ev);
     if (h->match_graph) cudaGraphExecDestroy(h->match_graph);
     for (auto e : h->fork_ev) if (e) cudaEventDestroy(e);
+    if (h->fs_done) cudaEventDestroy(h->fs_done);
     for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < LMB200_LANES; ++i) {

@@ -1017,10 +1017,30 @@ int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float thre
   rc = ensure_selection(h, class_ids, n_class_ids);
   if (rc) return rc;
   cudaStream_t st = h->lanes[0].stream;
-  rc = wait_async_upload(h);
+  // "resident_overlap" (default on): the frame side runs on the high-priority frame lane and the template side on the
+  // compute lane, chained by an event — consecutive calls on DIFFERENT slot ranges (double buffering) then overlap the
+  // issue-bound quantisers of step k+1 with the latency-bound similarity kernels of step k.  Calls on the same range
+  // serialise through the range's completion mark, exactly as before.
+  // (profiling keeps one lane: per-kernel CUDA-event times are only meaningful without a concurrent kernel)
+  cudaStream_t sf = h->resident_overlap && !h->profiling && count >= 8 ? h->lanes[5].stream : st;
+  if (sf != st) {
+    if (h->upload_pending) {
+      CU(cudaStreamWaitEvent(sf, h->upload_ev, 0));
+      h->upload_pending = false;
+    }
+    for (auto& mk : h->resident_marks)   // earlier steps still reading (or, for the frame buffers, uploads ordered behind) these slots
+      if (mk.ev && mk.first < first_slot + count && first_slot < mk.first + mk.count) CU(cudaStreamWaitEvent(sf, mk.ev, 0));
+    if (!h->fs_done) CU(cudaEventCreateWithFlags(&h->fs_done, cudaEventDisableTiming));
+  } else {
+    rc = wait_async_upload(h);
+    if (rc) return rc;
+  }
+  rc = run_frame_side(h, first_slot, count, sf);
   if (rc) return rc;
-  rc = run_frame_side(h, first_slot, count, st);
-  if (rc) return rc;
+  if (sf != st) {
+    CU(cudaEventRecord(h->fs_done, sf));
+    CU(cudaStreamWaitEvent(st, h->fs_done, 0));
+  }
   rc = run_matching(h, first_slot, count, threshold, st);
   if (rc) return rc;
   // completion event of this slot range: the fetch calls wait on it from the copy stream, so a fetch of step k does
@@ -1714,6 +1734,7 @@ int lmb200_set_option(lmb200_handle h, const char* name, int value) {
   if (std::strcmp(name, "upload_async") == 0) { h->upload_async = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "shard_overlap") == 0) { h->shard_overlap = value < 0 ? 0 : value > 2 ? 2 : value; return LMB200_OK; }
+  if (std::strcmp(name, "resident_overlap") == 0) { h->resident_overlap = value != 0; return LMB200_OK; }
   if (std::strcmp(name, "host_threads") == 0) { h->host_threads = value < 1 ? 1 : value > 64 ? 64 : value; return LMB200_OK; }
   if (std::strcmp(name, "shard_device_epilogue") == 0) { h->shard_device_epilogue = value != 0; return LMB200_OK; }
   return set_error(h, LMB200_E_INVALID, std::string("unknown option ") + name);

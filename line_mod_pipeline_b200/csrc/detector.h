@@ -190,6 +190,8 @@ struct lmb200_detector {
   long long graph_launches[LMB200_K_COUNT] = {0}; bool use_graph = true;
   cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork / join events of the graph's per-modality branches
   bool upload_async = false;             // lmb200_set_option("upload_async"): lmb200_upload_frames returns without synchronising
+  bool resident_overlap = true;          // lmb200_set_option("resident_overlap"): lmb200_match_resident runs the frame side on the frame lane
+  cudaEvent_t fs_done = nullptr;
   int host_threads = 8;                  // lmb200_set_option("host_threads"): threads of the host epilogue (sort/unique) of one fetch/collect;
                                          // one process per GPU shares the host's cores with its peers
   bool early_exit = true;                // lmb200_set_option("early_exit"): measurement runs switch the coarse kernel's exact exit off
