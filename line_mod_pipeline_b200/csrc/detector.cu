@@ -997,6 +997,16 @@ int lmb200_upload_frames(lmb200_handle h, const lmb200_image* frames, int n_fram
   return LMB200_OK;
 }
 
+// The ring keeps the completion marks of the last four resident steps; lanes that run AHEAD of the compute lane (frame
+// lane, asynchronous upload lane) order themselves behind earlier readers of a slot range through these marks.  A mark
+// that leaves the ring (a fifth distinct slot range in flight) can no longer be found by range, so both lanes are made to
+// wait for it here: they execute in order, hence everything they do later is behind that step as well.
+static cudaError_t evict_mark(lmb200_detector* h, const ResidentMark& mk) {
+  cudaError_t e = cudaStreamWaitEvent(h->lanes[5].stream, mk.ev, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->lanes[2].stream, mk.ev, 0);
+  return e;
+}
+
 // the compute lane picks up frames uploaded asynchronously
 static int wait_async_upload(lmb200_detector* h) {
   if (h->upload_pending) {
@@ -1047,6 +1057,7 @@ int lmb200_match_resident(lmb200_handle h, int first_slot, int count, float thre
   // not queue behind the kernels of step k+1 that were already enqueued on the compute stream
   ResidentMark& mk = h->resident_marks[h->resident_next++ & 3];
   if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
+  else CU(evict_mark(h, mk));
   mk.first = first_slot; mk.count = count;
   CU(cudaEventRecord(mk.ev, st));
   return LMB200_OK;
@@ -1140,6 +1151,7 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
   lap();
   ResidentMark& mk = h->resident_marks[h->resident_next++ & 3];
   if (!mk.ev) CU(cudaEventCreateWithFlags(&mk.ev, cudaEventDisableTiming));
+  else CU(evict_mark(h, mk));
   mk.first = first_slot; mk.count = count;
   CU(cudaEventRecord(mk.ev, st));
   // The match gather rides on the compute lane right behind the kernels — pack, ncclAllGather and the copy to pinned host
@@ -1152,12 +1164,12 @@ int lmb200_match_resident_sharded(lmb200_handle h, int first_slot, int count, fl
     job->first = first_slot; job->count = count;
     ALLOC(job->send, bytes);
     ALLOC(job->recv, bytes * world);
-    if (job->host_bytes < bytes * world) {
+    const bool dev_epi = h->shard_device_epilogue && world <= 64;
+    if (!dev_epi && job->host_bytes < bytes * world) {   // host epilogue thread: the gathered buffers are copied to pinned memory
       if (job->host) { cudaFreeHost(job->host); job->host = nullptr; }
       CU(cudaHostAlloc((void**)&job->host, bytes * world, cudaHostAllocDefault));
       job->host_bytes = bytes * world;
     }
-    const bool dev_epi = h->shard_device_epilogue && world <= 64;
     if (dev_epi) {
       // finished lists come from the device (kernels_epilogue.cu): tables, scratch and the pinned, device-mapped result area
       if (h->epi_tables_epoch != h->plan_epoch) {
