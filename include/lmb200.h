@@ -328,6 +328,12 @@ int lmb200_debug_shard_epilogue(const int32_t* gathered, int world, int rank, in
                                 const int32_t* g_class, const int32_t* g_tid, int ntpl, lmb200_match_rec* out, size_t out_cap,
                                 int32_t* hdr);
 
+/* The HOST merge of a template-sharded step on caller-made gathered buffers (same layout as lmb200_debug_shard_epilogue;
+ * no device needed): generation order restored, record -> match, std::sort, std::unique.  offsets has frames + 1 entries. */
+int lmb200_debug_merge_gathered(const int32_t* gathered, int world, int frames, int gcap, const int32_t* pos_of_g,
+                                const int32_t* g_class, const int32_t* g_tid, int ntpl, lmb200_match_rec* out, size_t cap,
+                                size_t* offsets);
+
 /* Measurement knobs.  "early_exit" (default 1): 0 switches off the coarse kernel's exact early exit (results are
  * identical either way; the bench reports both so the workload dependence of the exit is visible).
  * "upload_async" (default 0): 1 makes lmb200_upload_frames return without synchronising (pinned host frames that stay

@@ -136,6 +136,8 @@ SIGNATURES = {
     "lmb200_debug_sort_check": (C.c_int, [_P(MatchRec), C.c_size_t, C.c_int, _P(MatchRec), _P(MatchRec)]),
     "lmb200_debug_shard_epilogue": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                               _P(MatchRec), C.c_size_t, C.c_void_p]),
+    "lmb200_debug_merge_gathered": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                              _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_shard_plan": (C.c_int, [_P(C.c_double), C.c_int, C.c_int, _P(C.c_int)]),
     "lmb200_postmatch_color": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, _P(MatchRec), C.c_size_t, _P(C.c_int), _P(C.c_int)]),
     "lmb200_group_matches": (C.c_int, [_P(MatchRec), C.c_size_t, C.c_float, C.c_float, _P(C.c_int), _P(C.c_int)]),

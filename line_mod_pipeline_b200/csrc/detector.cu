@@ -2278,3 +2278,34 @@ extern "C" int lmb200_fetch_resident_allgather(lmb200_handle h, int first_slot, 
                  t_gather - t_begin, t_reorder, t_sort);
   return status;
 }
+
+// Test hook (include/lmb200.h): the HOST merge of a template-sharded step — the code the synchronous fetch path and the
+// epilogue thread run (merge_gathered) — on caller-made gathered buffers; no device is touched, so the CPU suite and the
+// gloo multi-rank test cover the wire format and the generation-order merge.
+extern "C" int lmb200_debug_merge_gathered(const int32_t* gathered, int world, int frames, int gcap, const int32_t* pos_of_g,
+                                           const int32_t* g_class, const int32_t* g_tid, int ntpl, lmb200_match_rec* out, size_t cap,
+                                           size_t* offsets) {
+  if (!gathered || !g_class || !g_tid || !offsets || world < 1 || frames < 1 || gcap < 0 || ntpl < 1) return LMB200_E_INVALID;
+  static_assert(sizeof(Cand) == 4 * sizeof(int32_t), "a gathered record is four 32-bit words");
+  lmb200_detector tmp;
+  tmp.comm_world = world; tmp.comm_rank = 0;
+  tmp.ntpl = ntpl;
+  tmp.g_class.assign(g_class, g_class + ntpl);
+  tmp.g_tid.assign(g_tid, g_tid + ntpl);
+  tmp.shard_interleaved = pos_of_g != nullptr;
+  if (pos_of_g) tmp.pos_of_g.assign(pos_of_g, pos_of_g + ntpl);
+  tmp.host_threads = 2;
+  const Cand* G = reinterpret_cast<const Cand*>(gathered);
+  if (gathered_needs_redo(G, gcap, frames, world)) return set_error(nullptr, LMB200_E_INVALID, "a gathered header carries a flag");
+  for (int r = 0; r < world; ++r)     // never index past a rank's record area
+    for (int i = 0; i < frames; ++i) {
+      const Cand& h0 = G[(size_t)r * ((size_t)2 * frames + gcap) + 2 * i];
+      if (h0.tsel < 0 || h0.y < 0 || (long long)h0.y + h0.tsel > gcap) return LMB200_E_INVALID;
+    }
+  std::vector<lmb200_match_rec> recs; std::vector<size_t> offs;
+  merge_gathered(&tmp, G, gcap, frames, 2u, recs, offs, nullptr, nullptr, nullptr, nullptr);
+  const size_t total = offs[frames], w = std::min(total, cap);
+  if (w && out) std::memcpy(out, recs.data(), w * sizeof(lmb200_match_rec));
+  for (int i = 0; i <= frames; ++i) offsets[i] = offs[i];
+  return w < total ? LMB200_E_TRUNCATED : LMB200_OK;
+}

@@ -303,3 +303,27 @@ def test_match_array_reads_like_the_reference_match():
     assert lists[0][0].x == 0
     with pytest.raises(AttributeError):
         lists[0].no_such_field
+
+
+@pytest.mark.parametrize("world,frames,max_per_rank,interleaved", [(1, 3, 200, False), (2, 5, 300, True), (8, 6, 120, True), (4, 6, 100, False)])
+def test_host_merge_of_a_sharded_step(world, frames, max_per_rank, interleaved):
+    """lmb200_debug_merge_gathered = the merge the synchronous allgather fetch and the epilogue thread run: the gathered wire
+    format of `world` ranks -> reference generation order -> std::sort + std::unique, against the same lists built in numpy
+    and finished by lmb200_merge_matches.  (The device epilogue is checked against the same cases in test_gpu_parity.py.)"""
+    from helpers import sharded_step_case
+    L = lm.capi.lib()
+    rng = np.random.default_rng(1000 * world + frames)
+    ntpl = 64 * world
+    G, gcap, pos, g_class, g_tid, want = sharded_step_case(rng, world, frames, max_per_rank, ntpl, interleaved, sims=6, tid_mod=7)
+    total = sum(n for n, _ in want)
+    out = np.zeros(max(1, total), lm.MATCH_DTYPE)
+    offs = (C.c_size_t * (frames + 1))()
+    rc = L.lmb200_debug_merge_gathered(G.ctypes.data, world, frames, gcap, pos.ctypes.data if pos is not None else None, g_class.ctypes.data,
+                                       g_tid.ctypes.data, ntpl, out.ctypes.data_as(C.POINTER(lm.capi.MatchRec)), len(out), offs)
+    assert rc == 0
+    for f in range(frames):
+        got = out[offs[f]:offs[f + 1]]
+        assert got.tobytes() == want[f][1].tobytes(), "frame %d differs" % f
+    G[world - 1, 0, 1] = 1                                    # a store-overflow flag in a header: the merge must refuse
+    assert L.lmb200_debug_merge_gathered(G.ctypes.data, world, frames, gcap, None, g_class.ctypes.data, g_tid.ctypes.data, ntpl,
+                                         out.ctypes.data_as(C.POINTER(lm.capi.MatchRec)), len(out), offs) == K.E_INVALID
