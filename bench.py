@@ -428,7 +428,7 @@ def template_sharded_leg(args, lm, synth, torch, dist, rank, world, local, K, W)
                     "efficiency_vs_full_set_on_1_gpu": value / (world * single["value"]),
                     "ranks_agree": bool(torch.equal(lo, hi)),
                     "frame_side": "sharded: each rank quantises %d of the %d frames, NCCL all-gather of the quantized maps, every rank spreads all frames" % (Bt // world, Bt),
-                    "collectives_per_step": "1 NCCL group (quantized maps, lane 3, main communicator) + 1 ncclAllGather (match buffers, compute lane, second communicator); the host epilogue runs on the handle's epilogue thread"})
+                    "collectives_per_step": "1 NCCL group (quantized maps, frame lane, main communicator) + 1 ncclAllGather (match buffers, compute lane, second communicator); std::sort + std::unique of every frame on the device (epilogue lane), finished lists land in pinned host memory"})
         # ---- 2-D layout on the same box: T template shards x 2 frame groups (world = 2 T).  Every group is a template-sharded
         #      step of its own (own NCCL communicator) on half of the step's frames, so the replicated part of the step — spread +
         #      linearize of every frame on every rank — halves.  Same call sequence, nothing new in the library.
