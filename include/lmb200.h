@@ -232,6 +232,14 @@ int lmb200_host_free(void* p);
  * the image (cv::fillPoly would clip it) or whose template is unknown gets inside = total = -1. */
 int lmb200_postmatch_color(lmb200_handle h, int slot, const uint8_t* lower_hsv, const uint8_t* upper_hsv,
                            const lmb200_match_rec* matches, size_t n, int* inside, int* total);
+/* medianMat of HighLevelLineMOD::depthCheck (src/HighLevelLinemod.cpp:336-349, :436-457), host code: depth values 0 and 1
+ * count as 65535 (threshold at 1, inverted, saturating add), the crop bb = {x, y, width, height} (must lie inside the image, as cv::Mat::operator()(Rect) demands) is
+ * flattened row by row, std::nth_element puts the (n/4)-th value in place and element n / median_position is returned — with
+ * the reference's median_position = 5 that is an element of the unordered lower part, whose identity depends on libstdc++'s
+ * introselect: the function makes the same call on the same sequence, so it returns the reference's value.
+ * depthCheck itself is then  abs((int)median - (int)template_median_depth - depth_offset) < step_size. */
+int lmb200_postmatch_median_depth(const uint16_t* depth, int rows, int cols, size_t step_bytes, const int* bb4, int median_position,
+                                  uint16_t* median);
 /* groupSimilarMatches + discardSmallMatchGroups (src/HighLevelLinemod.cpp:206-253), host code: group_of_match[i] = index
  * of the surviving group the match belongs to (groups in order of their first member) or -1 when its group was discarded
  * (size * 100 / biggest <= discard_group_ratio). */

@@ -140,6 +140,7 @@ SIGNATURES = {
                                               _P(MatchRec), C.c_size_t, _P(C.c_size_t)]),
     "lmb200_shard_plan": (C.c_int, [_P(C.c_double), C.c_int, C.c_int, _P(C.c_int)]),
     "lmb200_postmatch_color": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, _P(MatchRec), C.c_size_t, _P(C.c_int), _P(C.c_int)]),
+    "lmb200_postmatch_median_depth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, _P(C.c_int), C.c_int, _P(C.c_uint16)]),
     "lmb200_group_matches": (C.c_int, [_P(MatchRec), C.c_size_t, C.c_float, C.c_float, _P(C.c_int), _P(C.c_int)]),
     "lmb200_set_option": (C.c_int, [_H, C.c_char_p, C.c_int]),
     "lmb200_set_profiling": (C.c_int, [_H, C.c_int]),

@@ -1740,6 +1740,24 @@ int lmb200_group_matches(const lmb200_match_rec* matches, size_t n, float radius
   return LMB200_OK;
 }
 
+int lmb200_postmatch_median_depth(const uint16_t* depth, int rows, int cols, size_t step_bytes, const int* bb4, int median_position,
+                                  uint16_t* median) {
+  if (!depth || !bb4 || !median || rows <= 0 || cols <= 0 || median_position <= 0) return LMB200_E_INVALID;
+  const int x = bb4[0], y = bb4[1], w = bb4[2], hgt = bb4[3];
+  if (x < 0 || y < 0 || w <= 0 || hgt <= 0 || x + w > cols || y + hgt > rows) return LMB200_E_INVALID;   // cv::Mat ROI assertion
+  const size_t step = step_bytes ? step_bytes : (size_t)cols * sizeof(uint16_t);
+  std::vector<uint16_t> v;
+  v.reserve((size_t)w * hgt);
+  for (int r = 0; r < hgt; ++r) {
+    const uint16_t* row = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(depth) + (size_t)(y + r) * step) + x;
+    // threshold(in, 1, 65535, THRESH_BINARY) keeps values > 1; 65535 - that, added with saturation: 0 and 1 become 65535
+    for (int c = 0; c < w; ++c) v.push_back(row[c] > 1 ? row[c] : (uint16_t)65535);
+  }
+  std::nth_element(v.begin(), v.begin() + v.size() / 4, v.end());
+  *median = v[v.size() / (size_t)median_position];
+  return LMB200_OK;
+}
+
 int lmb200_set_option(lmb200_handle h, const char* name, int value) {
   if (!h || !name) return LMB200_E_INVALID;
   if (std::strcmp(name, "early_exit") == 0) { h->early_exit = value != 0; return LMB200_OK; }

@@ -68,3 +68,40 @@ def test_color_check_composition_equals_the_reference_formulation():
             assert bool(PM.color_check(hue, mask, percent)) == bool(ref)
             verdicts.add(bool(ref))
     assert verdicts == {True, False}
+
+
+def test_median_depth_of_depth_check(tmp_path):
+    """lmb200_postmatch_median_depth = HighLevelLineMOD::medianMat (src/HighLevelLinemod.cpp:336-349): the sequence it
+    selects from is pinned against cv2 (threshold / subtract / saturating add / ROI), the (n/4)-th order statistic against
+    numpy, and the reference's vec[n/5] — an element std::nth_element leaves in unspecified order — against the same
+    libstdc++ call compiled separately."""
+    import ctypes as C
+    import subprocess
+    import cv2
+    import line_mod_pipeline_b200 as lm
+    L = lm.capi.lib()
+    rng = np.random.default_rng(11)
+    depth = rng.integers(0, 1500, (120, 160)).astype(np.uint16)
+    depth[rng.random(depth.shape) < 0.2] = 0
+    depth[rng.random(depth.shape) < 0.02] = 1
+    src = tmp_path / "nth.cpp"
+    src.write_text("#include <algorithm>\n#include <cstdio>\n#include <vector>\n#include <cstdint>\n"
+                   "int main(int c, char** v) { std::vector<uint16_t> a; unsigned x; FILE* f = fopen(v[1], \"r\");"
+                   " while (fscanf(f, \"%u\", &x) == 1) a.push_back((uint16_t)x); fclose(f);"
+                   " std::nth_element(a.begin(), a.begin() + a.size() / 4, a.end()); printf(\"%u\\n\", (unsigned)a[a.size() / 5]); }\n")
+    exe = tmp_path / "nth"
+    subprocess.run(["g++", "-O2", "-o", str(exe), str(src)], check=True)
+    for bb in [(10, 20, 50, 40), (0, 0, 160, 120), (100, 90, 60, 30), (5, 5, 1, 1), (7, 3, 9, 2)]:
+        x, y, w, h = bb
+        _, inv = cv2.threshold(depth, 1, 65535, cv2.THRESH_BINARY)
+        seq = cv2.add(depth, 65535 - inv)[y:y + h, x:x + w].reshape(-1)
+        bb4 = (C.c_int * 4)(*bb)
+        out = C.c_uint16(0)
+        assert L.lmb200_postmatch_median_depth(depth.ctypes.data, 120, 160, 0, bb4, 4, C.byref(out)) == 0
+        assert out.value == int(np.sort(seq)[len(seq) // 4])
+        assert L.lmb200_postmatch_median_depth(depth.ctypes.data, 120, 160, 0, bb4, 5, C.byref(out)) == 0
+        (tmp_path / "seq.txt").write_text(" ".join(str(int(v)) for v in seq))
+        want = int(subprocess.run([str(exe), str(tmp_path / "seq.txt")], capture_output=True, text=True, check=True).stdout)
+        assert out.value == want and out.value <= int(np.sort(seq)[len(seq) // 4])
+    bad = (C.c_int * 4)(100, 100, 80, 40)                  # leaves the image: cv::Mat::operator()(Rect) asserts
+    assert L.lmb200_postmatch_median_depth(depth.ctypes.data, 120, 160, 0, bad, 5, C.byref(out)) == lm.capi.E_INVALID
