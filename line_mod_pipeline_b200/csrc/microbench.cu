@@ -29,7 +29,6 @@ __global__ void __launch_bounds__(256) read_kernel(const uint4* __restrict__ buf
         if (idx >= span16) idx -= span16;
         v[k] = MODE == 0 ? __ldcg(buf + idx) : __ldg(buf + idx);
       }
-#pragma unroll
       a0 += v[0].x ^ v[0].w; a1 += v[1].y ^ v[1].z; a2 += v[2].x ^ v[2].y; a3 += v[3].z ^ v[3].w;
     }
   }
