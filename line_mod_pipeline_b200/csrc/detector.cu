@@ -1508,6 +1508,10 @@ static int batch_enqueue(lmb200_detector* h, BatchTicket& tk) {
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     tk.events.push_back(ev);
   }
+  // resident steps (lmb200_match_resident[_sharded]) still in flight read the same frame slots: the copy stream orders
+  // itself behind their completion marks (free when they have long finished)
+  for (auto& mk : h->resident_marks)
+    if (mk.ev) CU(cudaStreamWaitEvent(Cs, mk.ev, 0));
   const bool trace = std::getenv("LMB200_TRACE") != nullptr;
   std::vector<cudaEvent_t> tev;  // trace: 4 timing events per chunk (copy start/end, compute start/end)
   if (trace) { tev.resize(4 * (size_t)nchunks); for (auto& e : tev) cudaEventCreate(&e); }
