@@ -219,6 +219,60 @@ class Detector {
     check(lmb200_read_classes(h_, ids.data(), (int)ids.size(), format.c_str()));
   }
 
+  // ---- throughput / multi-GPU entry points (not in upstream; INTEGRATION.md sections 4 and 6) --------------------------
+  // Device-resident steps: upload `n` frames (views[i] = the frame's sources) into slots [first_slot, first_slot + n),
+  // match them (enqueue only; steps on different slot ranges overlap), fetch the per-frame lists later.
+  void uploadFrames(const std::vector<std::vector<ImageView>>& frames, int first_slot = 0) {
+    std::vector<lmb200_image> src;
+    for (auto& f : frames) for (auto& s : f) src.push_back(s.c());
+    check(lmb200_upload_frames(h_, src.data(), (int)frames.size(), frames.empty() ? 0 : (int)frames[0].size(), first_slot));
+  }
+  void matchResident(int first_slot, int count, float threshold, const std::vector<std::string>& class_ids = {}) {
+    std::vector<const char*> ids;
+    for (auto& s : class_ids) ids.push_back(s.c_str());
+    check(lmb200_match_resident(h_, first_slot, count, threshold, ids.empty() ? nullptr : ids.data(), (int)ids.size()));
+  }
+  // per-frame match lists of slots [first_slot, first_slot + count); allgather = the collective fetch of a template-sharded step
+  std::vector<std::vector<Match>> fetchResident(int first_slot, int count, bool allgather = false, size_t capacity = 0) {
+    if (!capacity) capacity = (size_t)4096 * (size_t)count;
+    std::vector<lmb200_match_rec> rec(capacity);
+    std::vector<size_t> offs((size_t)count + 1);
+    int rc = allgather ? lmb200_fetch_resident_allgather(h_, first_slot, count, rec.data(), capacity, offs.data())
+                       : lmb200_fetch_resident(h_, first_slot, count, rec.data(), capacity, offs.data());
+    check(rc);
+    const std::vector<std::string> ids = classIds();
+    std::vector<std::vector<Match>> out((size_t)count);
+    for (int i = 0; i < count; ++i)
+      for (size_t k = offs[i]; k < offs[i + 1]; ++k) {
+        Match m;
+        m.x = rec[k].x; m.y = rec[k].y; m.similarity = rec[k].similarity; m.template_id = rec[k].template_id;
+        m.class_id = rec[k].class_index >= 0 && rec[k].class_index < (int)ids.size() ? ids[rec[k].class_index] : std::string();
+        out[i].push_back(m);
+      }
+    return out;
+  }
+  // One process per GPU: this handle scores shard `rank` of `world` (interleaved over the selection list) ...
+  void setTemplateShard(int rank, int world) { check(lmb200_set_template_shard(h_, rank, world)); }
+  // ... over an NCCL communicator (unique id from commUniqueId() on one rank, shipped to the others by the application)
+  static std::vector<uint8_t> commUniqueId() {
+    std::vector<uint8_t> id(128);
+    int rc = lmb200_comm_unique_id(id.data());
+    if (rc) throw Error(rc, lmb200_last_error(nullptr));
+    return id;
+  }
+  void commInit(const std::vector<uint8_t>& unique_id128, int rank, int world) {
+    if (unique_id128.size() != 128) throw Error(LMB200_E_INVALID, "the NCCL unique id is 128 bytes");
+    check(lmb200_comm_init(h_, unique_id128.data(), rank, world));
+  }
+  // template-sharded step: quantisers sharded by frame block + all-gather of the maps, spread, match, match all-gather and
+  // the sort/unique epilogue on the device; follow with fetchResident(first_slot, count, true)
+  void matchResidentSharded(int first_slot, int count, float threshold, const std::vector<std::string>& class_ids = {}) {
+    std::vector<const char*> ids;
+    for (auto& s : class_ids) ids.push_back(s.c_str());
+    check(lmb200_match_resident_sharded(h_, first_slot, count, threshold, ids.empty() ? nullptr : ids.data(), (int)ids.size()));
+  }
+  void setOption(const std::string& name, int value) { check(lmb200_set_option(h_, name.c_str(), value)); }
+
   lmb200_handle handle() const { return h_; }
 
  private:

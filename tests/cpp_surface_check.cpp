@@ -54,6 +54,20 @@ int main(int argc, char** argv) {
   } catch (const lm::Error& e) {
     if (e.code != LMB200_E_NODEVICE) { std::printf("unexpected: %s\n", e.what()); return 10; }
   }
+  // throughput / multi-GPU wrappers: host-side state changes work anywhere, device work obeys the same no-device rule
+  det->setOption("host_threads", 2);
+  det->setTemplateShard(0, 1);
+  try { det->setOption("no_such_option", 1); return 13; } catch (const lm::Error& e) { if (e.code != LMB200_E_INVALID) return 14; }
+  try {
+    std::vector<lm::ImageView> view = {lm::ImageView(bgr.data(), 480, 640, LMB200_8UC3), lm::ImageView(depth.data(), 480, 640, LMB200_16UC1)};
+    det->uploadFrames({view, view}, 0);
+    det->matchResident(0, 2, 80.f);
+    std::vector<std::vector<lm::Match>> lists = det->fetchResident(0, 2);
+    if (lists.size() != 2) return 15;
+    std::printf("resident step ran on a GPU: %zu + %zu matches\n", lists[0].size(), lists[1].size());
+  } catch (const lm::Error& e) {
+    if (e.code != LMB200_E_NODEVICE) { std::printf("unexpected: %s\n", e.what()); return 16; }
+  }
   std::printf("CPP_SURFACE_OK\n");
   return 0;
 }
